@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py -- measures the batched transform hot path on B200 (and the reference's CPU path beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input.  Default workload = BASELINE.json
+configs[1]: 1-D real float nfft=4096, batch=32768, forward (kiss_fftr) then inverse (kiss_fftri) -- two kernel
+launches per step.  Other BASELINE configs are selectable with --workload for investigation; they are parity
+test cases, not the headline line.
+
+Printed JSON (one line, rank 0):
+  value        whole-job GFLOP/s with inputs resident in HBM (5*N*log2N per complex transform, 2.5*N*log2N per
+               real transform), CUDA-event timed, max over ranks
+  e2e          same metric through the host-pointer C-ABI calls (kiss_fftr_batch / kiss_fftri_batch ...) with
+               pinned host buffers: H2D + kernels + D2H inside the timed region
+  roofline     dominant kernel: algorithmic HBM bytes per launch / its mean launch time (CUDA events around every
+               launch inside the timed region) vs the measured copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline the compiled reference (oracle/_ref) -- or the oracle port when that is absent -- on the host
+               cores, bounded sample of the same workload
+`--impl reference` times only the CPU reference arm and prints the same line shape.
+Multi-GPU (torchrun, one rank per GPU): batches shard by rank with no communication => weak scaling.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "batched FFT GFLOP/s (5N*log2N)"
+
+# name -> dict(kind, tname, nfft|dims, batch)
+WORKLOADS = {
+    "r2c4096": dict(kind="real", tname="float", nfft=4096, batch=32768,
+                    desc="1-D real float R2C+C2R nfft=4096 batch=32768 (kiss_fftr/kiss_fftri) -- BASELINE configs[1]"),
+    "c2c1024": dict(kind="c2c", tname="float", nfft=1024, batch=65536,
+                    desc="1-D complex float C2C nfft=1024 batch=65536 -- BASELINE configs[0]"),
+    "c2c1000": dict(kind="c2c", tname="float", nfft=1000, batch=100000, desc="mixed radix nfft=1000 float -- configs[2]"),
+    "c2c1155": dict(kind="c2c", tname="float", nfft=1155, batch=100000, desc="mixed radix nfft=1155 float -- configs[2]"),
+    "z2z1000": dict(kind="c2c", tname="double", nfft=1000, batch=100000, desc="mixed radix nfft=1000 double -- configs[2]"),
+    "z2z1155": dict(kind="c2c", tname="double", nfft=1155, batch=100000, desc="mixed radix nfft=1155 double -- configs[2]"),
+    "q15_2048": dict(kind="c2c", tname="int16_t", nfft=2048, batch=65536, desc="Q15 C2C nfft=2048 batch=65536 -- configs[3]"),
+    "q31_2048": dict(kind="c2c", tname="int32_t", nfft=2048, batch=65536, desc="Q31 C2C nfft=2048 batch=65536 -- configs[3]"),
+    "fftnd256": dict(kind="nd", tname="float", dims=(256, 256, 256), batch=1, desc="3-D complex float 256^3 kiss_fftnd"),
+    "fftnd512": dict(kind="nd", tname="float", dims=(512, 512, 512), batch=1, desc="3-D complex float 512^3 kiss_fftnd"),
+    "fftnd1024": dict(kind="nd", tname="float", dims=(1024, 1024, 1024), batch=1,
+                      desc="3-D complex float 1024^3 kiss_fftnd (single GPU) -- configs[4]"),
+}
+DTYPE_NAME = {"float": "f32", "double": "f64", "int16_t": "q15", "int32_t": "q31"}
+NP = {"float": np.float32, "double": np.float64, "int16_t": np.int16, "int32_t": np.int32}
+
+
+def flops_per_step(w):
+    if w["kind"] == "real":      # forward + inverse real transform
+        n = w["nfft"]
+        return 2 * 2.5 * n * math.log2(n) * w["batch"]
+    if w["kind"] == "c2c":
+        n = w["nfft"]
+        return 5.0 * n * math.log2(n) * w["batch"]
+    n = int(np.prod(w["dims"]))
+    return 5.0 * n * math.log2(n)
+
+
+def esz(tname):
+    return np.dtype(NP[tname]).itemsize
+
+
+def algorithmic_bytes(w):
+    """per launch of the dominant kernel: one read + one write of every element"""
+    s = esz(w["tname"])
+    if w["kind"] == "real":      # R2C launch: N scalars in, N/2+1 complex out (C2R is the mirror image)
+        n = w["nfft"]
+        return (n * s + (n // 2 + 1) * 2 * s) * w["batch"]
+    if w["kind"] == "c2c":
+        return 2 * w["nfft"] * 2 * s * w["batch"]
+    return 2 * int(np.prod(w["dims"])) * 2 * s   # one axis pass
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def known_traffic(name):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(name)
+    except Exception:
+        return None
+
+
+# ---- clocks ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.tmp,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        sm, smax, reasons = [], [], set()
+        with open(self.tmp.name) as f:
+            for line in f:
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    smax.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        os.unlink(self.tmp.name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(smax))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---- CPU reference arm -------------------------------------------------------------------------------------
+def cpu_reference(w, reps=3, budget_rows=None):
+    """times the reference's own CPU implementation (oracle/_ref when compiled here, else the oracle port) on a
+    bounded sample of the workload with all host threads (batch-parallel harness; cfgs are read-only, reference
+    README.md:217).  Returns (gflops, info dict)."""
+    from oracle import loader
+    tname = w["tname"]
+    dtype = NP[tname]
+    have_ref = loader.have_reference(tname)
+    drv = loader.CpuDriver()
+    cores = os.cpu_count() or 1
+    threads = min(cores, drv.max_threads()) if have_ref else 1
+    s = esz(tname)
+    if w["kind"] in ("real", "c2c"):
+        n = w["nfft"]
+        rows = budget_rows or min(w["batch"], max(256, 512 * threads))
+        sub = dict(w, batch=rows)
+        if w["kind"] == "c2c":
+            x = loader.random_input(tname, (rows, n), 1)
+            out = np.empty_like(x)
+            if have_ref:
+                t = drv.run(loader.reference_lib_path(tname), loader.K_FFT, [n], 0, x, out, rows, n * 2 * s, n * 2 * s, threads, reps)
+            else:
+                o = loader.Oracle(tname)
+                t0 = time.perf_counter()
+                o.fft(x)
+                t = time.perf_counter() - t0
+        else:
+            x = loader.random_input(tname, (rows, n), 1, complex_=False)
+            X = np.empty((rows, n // 2 + 1, 2), dtype)
+            y = np.empty_like(x)
+            if have_ref:
+                lp = loader.reference_lib_path(tname)
+                t = drv.run(lp, loader.K_FFTR, [n], 0, x, X, rows, n * s, (n // 2 + 1) * 2 * s, threads, reps)
+                t += drv.run(lp, loader.K_FFTRI, [n], 1, X, y, rows, (n // 2 + 1) * 2 * s, n * s, threads, reps)
+            else:
+                o = loader.Oracle(tname)
+                t0 = time.perf_counter()
+                o.fftri(o.fftr(x))
+                t = time.perf_counter() - t0
+        sample = "%d of %d transforms, %s" % (rows, w["batch"], "forward+inverse" if w["kind"] == "real" else "forward")
+        gf = flops_per_step(sub) / t / 1e9
+    else:
+        dims = w["dims"]
+        sdims = tuple(min(d, 128) for d in dims)       # the CPU needs minutes beyond 256^3; bounded sample
+        x = loader.random_input(tname, sdims, 1)
+        out = np.empty_like(x)
+        if have_ref:
+            t = drv.run(loader.reference_lib_path(tname), loader.K_FFTND, list(sdims), 0, x, out, 1, 0, 0, 1, 1)
+        else:
+            t0 = time.perf_counter()
+            loader.Oracle(tname).fftnd(x)
+            t = time.perf_counter() - t0
+        threads = 1
+        sample = "%s grid instead of %s (kiss_fftnd is single-threaded)" % ("x".join(map(str, sdims)), "x".join(map(str, dims)))
+        gf = flops_per_step(dict(w, dims=sdims)) / t / 1e9
+    info = {"value": gf, "unit": "GFLOP/s", "cores": threads, "kind": "reference" if have_ref else "port", "sample": sample,
+            "seconds": t, "host_cores": cores}
+    return gf, info
+
+
+# ---- GPU arm ----------------------------------------------------------------------------------------------
+def run_ours(args, w, rank, world, local_rank):
+    import torch
+    import kissfft_b200
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = kissfft_b200.get(w["tname"])
+    tdt = {"float": torch.float32, "double": torch.float64, "int16_t": torch.int16, "int32_t": torch.int32}[w["tname"]]
+    stream = torch.cuda.current_stream().cuda_stream
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1234 + rank)
+
+    def synth(shape):
+        if w["tname"] in ("float", "double"):
+            return (torch.rand(shape, generator=gen, device="cuda", dtype=tdt) * 2 - 1)
+        half = (32767 if w["tname"] == "int16_t" else 2147483647) // 2
+        return torch.randint(-half, half + 1, shape, generator=gen, device="cuda", dtype=torch.int64).to(tdt)
+
+    launches_per_step = 0
+    kernels = []          # (label, callable) executed per step, each one kernel launch
+    if w["kind"] == "real":
+        n, b = w["nfft"], w["batch"]
+        nb = n // 2 + 1
+        d_x = synth((b, n))
+        d_X = torch.empty((b, nb, 2), device="cuda", dtype=tdt)
+        d_y = torch.empty_like(d_x)
+        cf, ci = lib.allocr(n, False), lib.allocr(n, True)
+        kernels = [("r2c", lambda: lib.fftr_batch_dev(cf, d_x, d_X, b, n, nb, stream)),
+                   ("c2r", lambda: lib.fftri_batch_dev(ci, d_X, d_y, b, nb, n, stream))]
+        h_x = torch.empty((b, n), dtype=tdt).pin_memory()
+        h_x.copy_(d_x)
+        h_X = torch.empty((b, nb, 2), dtype=tdt).pin_memory()
+        h_y = torch.empty((b, n), dtype=tdt).pin_memory()
+
+        def e2e_step():
+            lib.fftr_batch(cf, h_x, h_X, b)
+            lib.fftri_batch(ci, h_X, h_y, b)
+        h2d = h_x.numel() * h_x.element_size() + h_X.numel() * h_X.element_size()
+        d2h = h_X.numel() * h_X.element_size() + h_y.numel() * h_y.element_size()
+    elif w["kind"] == "c2c":
+        n, b = w["nfft"], w["batch"]
+        d_x = synth((b, n, 2))
+        d_X = torch.empty_like(d_x)
+        cf = lib.alloc(n, False)
+        kernels = [("c2c", lambda: lib.fft_batch_dev(cf, d_x, d_X, b, n, n, 1, stream))]
+        h_x = torch.empty((b, n, 2), dtype=tdt).pin_memory()
+        h_x.copy_(d_x)
+        h_X = torch.empty((b, n, 2), dtype=tdt).pin_memory()
+
+        def e2e_step():
+            lib.fft_batch(cf, h_x, h_X, b)
+        h2d = d2h = h_x.numel() * h_x.element_size()
+    else:
+        dims = w["dims"]
+        d_x = synth(tuple(dims) + (2,))
+        d_X = torch.empty_like(d_x)
+        d_w = torch.empty_like(d_x)
+        cf = lib.allocnd(dims, False)
+        kernels = [("fftnd", lambda: lib.fftnd_dev(cf, d_x, d_X, d_w, stream))]
+        e2e_step = None
+        h2d = d2h = 0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (also builds device tables, sets kernel attributes)
+    for _ in range(max(args.warmup, 3)):
+        for _, k in kernels:
+            k()
+    barrier()
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    l0 = lib.launch_count()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(kernels) + 1)] for _ in range(args.steps)]
+    barrier()
+    for s in range(args.steps):
+        ev[s][0].record()
+        for j, (_, k) in enumerate(kernels):
+            k()
+            ev[s][j + 1].record()
+    barrier()
+    launches = lib.launch_count() - l0
+    total_ms = ev[0][0].elapsed_time(ev[-1][-1])
+    per_kernel_ms = [float(np.mean([ev[s][j].elapsed_time(ev[s][j + 1]) for s in range(args.steps)])) for j in range(len(kernels))]
+    clk = clocks.stop() if clocks else None
+
+    # end to end through the host-pointer API (pinned host buffers, copies inside the timed region)
+    e2e_ms = None
+    if e2e_step is not None:
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+
+    t = torch.tensor([total_ms, e2e_ms if e2e_ms is not None else 0.0], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_max = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+    value = flops_per_step(w) * world / (ms_per_step * 1e-3) / 1e9
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        jdom = int(np.argmax(per_kernel_ms))
+        if w["kind"] == "nd":
+            abytes = algorithmic_bytes(w) * len(w["dims"])     # the fftnd call = ndims axis-pass launches
+            dom_ms = per_kernel_ms[0]
+            dom_label = "kf axis pass x%d" % len(w["dims"])
+        else:
+            abytes = algorithmic_bytes(w)
+            dom_ms = per_kernel_ms[jdom]
+            dom_label = kernels[jdom][0]
+        achieved = abytes / (dom_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": DTYPE_NAME[w["tname"]], "data": "synthetic",
+            "config": {"workload": w["desc"], "name": args.workload, "batch_per_gpu": w["batch"],
+                       "flop_convention": "5*N*log2N per complex transform, 2.5*N*log2N per real transform",
+                       "l2": "inputs larger than L2 (no flush needed)" if abytes > 300e6 else "working set may fit L2",
+                       "parallelism": "batch sharded across %d GPU(s), no communication" % world},
+            "kernel_ms": {k[0]: ms for k, ms in zip(kernels, per_kernel_ms)},
+            "roofline": {"bound": "hbm", "kernel": dom_label, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
+                         "algorithmic_bytes": abytes, "traffic": known_traffic(args.workload)},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+        }
+        if e2e_ms is not None:
+            line["e2e"] = {"value": flops_per_step(w) * world / (e2e_max * 1e-3) / 1e9, "unit": "GFLOP/s",
+                           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_max,
+                           "api": "kiss_fftr_batch+kiss_fftri_batch" if w["kind"] == "real" else "kiss_fft_batch"}
+        else:
+            line["e2e"] = None
+        if world == 1:
+            try:
+                _, info = cpu_reference(w)
+                line["cpu_baseline"] = info
+            except Exception as exc:   # the baseline is reported, never required for the GPU number
+                line["cpu_baseline"] = {"error": str(exc)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args, w, rank, world):
+    if rank != 0:
+        return
+    vals, info = [], None
+    for _ in range(max(1, args.warmup)):
+        cpu_reference(w, reps=1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        gf, info = cpu_reference(w, reps=1)
+        vals.append(gf)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = float(np.median(vals))
+    info = dict(info, value=value)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": DTYPE_NAME[w["tname"]], "data": "synthetic",
+            "config": {"workload": w["desc"], "name": args.workload,
+                       "flop_convention": "5*N*log2N per complex transform, 2.5*N*log2N per real transform"},
+            "cpu_baseline": info,
+            "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="r2c4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+    else:
+        run_ours(args, w, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

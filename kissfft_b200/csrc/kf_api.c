@@ -1,0 +1,961 @@
+/*
+ * kf_api.c -- host side of kissfft-b200, plain C.
+ *
+ * Implements the reference's public API (include/kiss_fft.h, kiss_fftr.h, kiss_fftnd.h, kiss_fftndr.h) and
+ * the batched device-pointer extension (include/kiss_fft_cuda.h) on top of the CUDA launchers of
+ * kf_launch.cu.  What lives here:
+ *   - the planner: radix schedule and twiddle tables, generated on the host in double precision with the
+ *     reference's exact expressions so that the Q15/Q31 tables are bit-identical
+ *     (kf_factor kiss_fft.c:306-328, twiddles kiss_fft.c:361-367, split twiddles kiss_fftr.c:53-59);
+ *   - the cfg objects: single free()-able POD blocks honouring the mem/lenmem placement protocol
+ *     (kiss_fft.h:94-115) -- they contain no device handles, so they may be copied or freed at will;
+ *   - a per-(device, nfft, direction) cache of device-side tables, released by kiss_fft_cleanup();
+ *   - pointer classification: host pointers are staged through the GPU, device pointers run in place;
+ *   - the axis-pass orchestration of kiss_fftnd / kiss_fftndr (kiss_fftnd.c:156-188, kiss_fftndr.c:86-132).
+ * There is no CPU transform code in this file or anywhere in the library.
+ */
+#include <cuda_runtime_api.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/kiss_fft_cuda.h"
+#include "kf_internal.h"
+
+#ifdef FIXED_POINT
+# if (FIXED_POINT == 32)
+#  define KF_SAMP_MAX 2147483647
+# else
+#  define KF_SAMP_MAX 32767
+# endif
+#endif
+
+#define KF_MAGIC_1D 0x4b463144u
+#define KF_MAGIC_R 0x4b465245u
+#define KF_MAGIC_ND 0x4b464e44u
+#define KF_MAGIC_NDR 0x4b464e52u
+
+struct kiss_fft_state {
+    uint32_t magic;
+    int nfft;
+    int inverse;
+    int nstages;
+    int factors[2 * KFCU_MAXSTAGES]; /* p0,m0,p1,m1,... like the reference's factors[] */
+    kiss_fft_cpx twiddles[1];        /* nfft entries */
+};
+
+struct kiss_fftr_state {
+    uint32_t magic;
+    int nfft; /* real length */
+    kiss_fft_cfg substate;
+    kiss_fft_cpx *super_twiddles; /* nfft/4 entries */
+};
+
+struct kiss_fftnd_state {
+    uint32_t magic;
+    int ndims;
+    int inverse;
+    long long dimprod;
+    int *dims;
+    kiss_fft_cfg *states;
+};
+
+struct kiss_fftndr_state {
+    uint32_t magic;
+    int dimReal;
+    long long dimOther;
+    int ndims;
+    int inverse;
+    kiss_fftr_cfg cfg_r;
+    kiss_fftnd_cfg cfg_nd; /* over dims[0..ndims-2]; NULL when ndims == 1 */
+};
+
+/* ---- error reporting (reference convention: "[ERROR] file:line msg" on stderr, kiss_fft_log.h:20-32) ---- */
+static __thread char tls_err[256];
+
+static void kf_error(const char *file, int line, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tls_err, sizeof(tls_err), fmt, ap);
+    va_end(ap);
+#ifndef NDEBUG
+    fprintf(stderr, "[ERROR] %s:%d %s\n", file, line, tls_err);
+#endif
+}
+#define KF_ERROR(...) kf_error(__FILE__, __LINE__, __VA_ARGS__)
+
+static int kf_cuda_fail(const char *file, int line, const char *what, int code)
+{
+    if (code > 0)
+        kf_error(file, line, "%s: CUDA error %d (%s)", what, code, cudaGetErrorString((cudaError_t)code));
+    else
+        kf_error(file, line, "%s: error %d", what, code);
+    return code;
+}
+#define KF_CHECK(expr)                                                    \
+    do {                                                                  \
+        int kf_rc_ = (int)(expr);                                         \
+        if (kf_rc_ != 0) return kf_cuda_fail(__FILE__, __LINE__, #expr, kf_rc_); \
+    } while (0)
+
+const char *kiss_fft_cuda_last_error(void) { return tls_err; }
+long long kiss_fft_cuda_launch_count(void) { return kfcu_launch_count(); }
+int kiss_fft_cuda_scalar_bytes(void) { return (int)sizeof(kiss_fft_scalar); }
+int kiss_fft_cuda_is_fixed_point(void)
+{
+#ifdef FIXED_POINT
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+/* ---- planner -------------------------------------------------------------------------------------------- */
+
+/* trig -> scalar, the reference's KISS_FFT_COS/SIN (_kiss_fft_guts.h:127-139) */
+static kiss_fft_scalar kf_scalar_from(double x)
+{
+#ifdef FIXED_POINT
+    return (kiss_fft_scalar)floor(.5 + KF_SAMP_MAX * x);
+#else
+    return (kiss_fft_scalar)x;
+#endif
+}
+
+/* 4s first, then 2s, then 3, 5, 7, ...; once p exceeds floor(sqrt(n_original)) the remainder is prime
+ * (kiss_fft.c:306-328).  Returns the number of stages. */
+static int kf_plan_radices(int n, int *facbuf)
+{
+    int p = 4, ns = 0;
+    const double root = floor(sqrt((double)n));
+    do {
+        while (n % p) {
+            if (p == 4) p = 2;
+            else if (p == 2) p = 3;
+            else p += 2;
+            if (p > root) p = n;
+        }
+        n /= p;
+        if (ns >= KFCU_MAXSTAGES) return -1;
+        facbuf[2 * ns] = p;
+        facbuf[2 * ns + 1] = n;
+        ++ns;
+    } while (n > 1);
+    return ns;
+}
+
+kiss_fft_cfg kiss_fft_alloc(int nfft, int inverse_fft, void *mem, size_t *lenmem)
+{
+    kiss_fft_cfg st = NULL;
+    if (nfft <= 0) return NULL;
+    if ((size_t)nfft >= (SIZE_MAX - 2 * sizeof(struct kiss_fft_state)) / sizeof(kiss_fft_cpx)) return NULL;
+    const size_t memneeded = sizeof(struct kiss_fft_state) + sizeof(kiss_fft_cpx) * (size_t)(nfft - 1);
+
+    if (lenmem == NULL) {
+        st = (kiss_fft_cfg)KISS_FFT_MALLOC(memneeded);
+    } else {
+        if (mem != NULL && *lenmem >= memneeded) st = (kiss_fft_cfg)mem;
+        *lenmem = memneeded;
+    }
+    if (!st) return NULL;
+
+    st->magic = KF_MAGIC_1D;
+    st->nfft = nfft;
+    st->inverse = inverse_fft ? 1 : 0;
+    memset(st->factors, 0, sizeof(st->factors));
+    st->nstages = kf_plan_radices(nfft, st->factors);
+    {
+        const double pi = 3.141592653589793238462643383279502884197169399375105820974944;
+        for (int i = 0; i < nfft; ++i) {
+            double phase = -2 * pi * i / nfft;
+            if (st->inverse) phase *= -1;
+            st->twiddles[i].r = kf_scalar_from(cos(phase));
+            st->twiddles[i].i = kf_scalar_from(sin(phase));
+        }
+    }
+    return st;
+}
+
+int kiss_fft_next_fast_size(int n)
+{
+    for (;; ++n) {
+        int m = n;
+        while ((m % 2) == 0) m /= 2;
+        while ((m % 3) == 0) m /= 3;
+        while ((m % 5) == 0) m /= 5;
+        if (m <= 1) return n;
+    }
+}
+
+kiss_fftr_cfg kiss_fftr_alloc(int nfft, int inverse_fft, void *mem, size_t *lenmem)
+{
+    kiss_fftr_cfg st = NULL;
+    size_t subsize = 0;
+    if (nfft & 1) {
+        KF_ERROR("Real FFT optimization must be even.");
+        return NULL;
+    }
+    if (nfft <= 0) return NULL;
+    const int nc = nfft >> 1;
+    kiss_fft_alloc(nc, inverse_fft, NULL, &subsize);
+    subsize = (subsize + 15u) & ~(size_t)15u;
+    const size_t hdr = (sizeof(struct kiss_fftr_state) + 15u) & ~(size_t)15u;
+    const size_t memneeded = hdr + subsize + sizeof(kiss_fft_cpx) * (size_t)(nc / 2 + 1);
+
+    if (lenmem == NULL) {
+        st = (kiss_fftr_cfg)KISS_FFT_MALLOC(memneeded);
+    } else {
+        if (mem != NULL && *lenmem >= memneeded) st = (kiss_fftr_cfg)mem;
+        *lenmem = memneeded;
+    }
+    if (!st) return NULL;
+
+    st->magic = KF_MAGIC_R;
+    st->nfft = nfft;
+    st->substate = (kiss_fft_cfg)((char *)st + hdr);
+    st->super_twiddles = (kiss_fft_cpx *)((char *)st->substate + subsize);
+    kiss_fft_alloc(nc, inverse_fft, st->substate, &subsize);
+    for (int i = 0; i < nc / 2; ++i) {
+        double phase = -3.14159265358979323846264338327 * ((double)(i + 1) / nc + .5);
+        if (inverse_fft) phase *= -1;
+        st->super_twiddles[i].r = kf_scalar_from(cos(phase));
+        st->super_twiddles[i].i = kf_scalar_from(sin(phase));
+    }
+    return st;
+}
+
+kiss_fftnd_cfg kiss_fftnd_alloc(const int *dims, int ndims, int inverse_fft, void *mem, size_t *lenmem)
+{
+    kiss_fftnd_cfg st = NULL;
+    if (ndims < 0 || (ndims > 0 && !dims)) return NULL;
+    size_t memneeded = (sizeof(struct kiss_fftnd_state) + 15u) & ~(size_t)15u;
+    const size_t off_dims = memneeded;
+    memneeded += (sizeof(int) * (size_t)ndims + 15u) & ~(size_t)15u;
+    const size_t off_states = memneeded;
+    memneeded += (sizeof(void *) * (size_t)ndims + 15u) & ~(size_t)15u;
+    const size_t off_cfgs = memneeded;
+    long long dimprod = 1;
+    for (int i = 0; i < ndims; ++i) {
+        size_t sublen = 0;
+        if (dims[i] <= 0) return NULL;
+        kiss_fft_alloc(dims[i], inverse_fft, NULL, &sublen);
+        memneeded += (sublen + 15u) & ~(size_t)15u;
+        dimprod *= dims[i];
+    }
+    if (lenmem == NULL) {
+        st = (kiss_fftnd_cfg)KISS_FFT_MALLOC(memneeded);
+    } else {
+        if (mem != NULL && *lenmem >= memneeded) st = (kiss_fftnd_cfg)mem;
+        *lenmem = memneeded;
+    }
+    if (!st) return NULL;
+    st->magic = KF_MAGIC_ND;
+    st->ndims = ndims;
+    st->inverse = inverse_fft ? 1 : 0;
+    st->dimprod = dimprod;
+    st->dims = (int *)((char *)st + off_dims);
+    st->states = (kiss_fft_cfg *)((char *)st + off_states);
+    char *ptr = (char *)st + off_cfgs;
+    for (int i = 0; i < ndims; ++i) {
+        size_t len = 0;
+        st->dims[i] = dims[i];
+        kiss_fft_alloc(dims[i], inverse_fft, NULL, &len);
+        st->states[i] = kiss_fft_alloc(dims[i], inverse_fft, ptr, &len);
+        ptr += (len + 15u) & ~(size_t)15u;
+    }
+    return st;
+}
+
+kiss_fftndr_cfg kiss_fftndr_alloc(const int *dims, int ndims, int inverse_fft, void *mem, size_t *lenmem)
+{
+    kiss_fftndr_cfg st = NULL;
+    size_t nr = 0, nd = 0;
+    if (ndims < 1 || !dims) return NULL;
+    const int dimReal = dims[ndims - 1];
+    if (dimReal <= 0 || (dimReal & 1)) {
+        KF_ERROR("Real FFT optimization must be even.");
+        return NULL;
+    }
+    long long dimOther = 1;
+    for (int i = 0; i < ndims - 1; ++i) {
+        if (dims[i] <= 0) return NULL;
+        dimOther *= dims[i];
+    }
+    (void)kiss_fftr_alloc(dimReal, inverse_fft, NULL, &nr);
+    if (ndims > 1) (void)kiss_fftnd_alloc(dims, ndims - 1, inverse_fft, NULL, &nd);
+    const size_t hdr = (sizeof(struct kiss_fftndr_state) + 15u) & ~(size_t)15u;
+    nr = (nr + 15u) & ~(size_t)15u;
+    nd = (nd + 15u) & ~(size_t)15u;
+    const size_t memneeded = hdr + nr + nd;
+    if (lenmem == NULL) {
+        st = (kiss_fftndr_cfg)malloc(memneeded);
+    } else {
+        if (mem != NULL && *lenmem >= memneeded) st = (kiss_fftndr_cfg)mem;
+        *lenmem = memneeded;
+    }
+    if (!st) return NULL;
+    memset(st, 0, memneeded);
+    st->magic = KF_MAGIC_NDR;
+    st->dimReal = dimReal;
+    st->dimOther = dimOther;
+    st->ndims = ndims;
+    st->inverse = inverse_fft ? 1 : 0;
+    char *ptr = (char *)st + hdr;
+    st->cfg_r = kiss_fftr_alloc(dimReal, inverse_fft, ptr, &nr);
+    ptr += nr;
+    st->cfg_nd = (ndims > 1) ? kiss_fftnd_alloc(dims, ndims - 1, inverse_fft, ptr, &nd) : NULL;
+    return st;
+}
+
+/* ---- device plan cache ---------------------------------------------------------------------------------- */
+typedef struct kf_devplan {
+    int device, nfft, inverse, has_stw;
+    kfcu_plan plan;
+    kiss_fft_cpx *h_tw; /* private host copy (the cfg may be freed by the caller at any time) */
+    struct kf_devplan *next;
+} kf_devplan;
+
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static kf_devplan *g_plans = NULL;
+
+/* scratch pool (per process, used under g_stage_lock by the host-pointer entry points) */
+static pthread_mutex_t g_stage_lock = PTHREAD_MUTEX_INITIALIZER;
+typedef struct { void *ptr; size_t bytes; int device; } kf_buf;
+#define KF_NSLOTS 8
+static kf_buf g_dev_bufs[KF_NSLOTS];
+static cudaStream_t g_streams[4];
+static int g_streams_dev = -1;
+
+static int kf_get_devplan(const struct kiss_fft_state *cfg, const kiss_fft_cpx *stw, const kf_devplan **out)
+{
+    int dev = 0;
+    KF_CHECK(cudaGetDevice(&dev));
+    pthread_mutex_lock(&g_lock);
+    kf_devplan *e;
+    for (e = g_plans; e; e = e->next)
+        if (e->device == dev && e->nfft == cfg->nfft && e->inverse == cfg->inverse && (!stw || e->has_stw)) break;
+    if (!e) {
+        e = (kf_devplan *)calloc(1, sizeof(*e));
+        int rc = e ? 0 : KISS_FFT_CUDA_ENOMEM;
+        void *d_tw = NULL, *d_stw = NULL;
+        const size_t twbytes = sizeof(kiss_fft_cpx) * (size_t)cfg->nfft;
+        const size_t stwn = (size_t)(cfg->nfft / 2);
+        if (!rc) {
+            e->h_tw = (kiss_fft_cpx *)malloc(twbytes);
+            if (!e->h_tw) rc = KISS_FFT_CUDA_ENOMEM;
+        }
+        if (!rc) rc = (int)cudaMalloc(&d_tw, twbytes);
+        if (!rc) rc = (int)cudaMemcpy(d_tw, cfg->twiddles, twbytes, cudaMemcpyHostToDevice);
+        if (!rc && stw && stwn) {
+            rc = (int)cudaMalloc(&d_stw, sizeof(kiss_fft_cpx) * stwn);
+            if (!rc) rc = (int)cudaMemcpy(d_stw, stw, sizeof(kiss_fft_cpx) * stwn, cudaMemcpyHostToDevice);
+        }
+        if (rc) {
+            if (d_tw) cudaFree(d_tw);
+            if (d_stw) cudaFree(d_stw);
+            if (e) { free(e->h_tw); free(e); }
+            pthread_mutex_unlock(&g_lock);
+            return kf_cuda_fail(__FILE__, __LINE__, "device plan creation", rc);
+        }
+        memcpy(e->h_tw, cfg->twiddles, twbytes);
+        e->device = dev;
+        e->nfft = cfg->nfft;
+        e->inverse = cfg->inverse;
+        e->has_stw = (stw != NULL);
+        e->plan.nfft = cfg->nfft;
+        e->plan.inverse = cfg->inverse;
+        e->plan.nstages = cfg->nstages;
+        for (int s = 0; s < cfg->nstages; ++s) {
+            e->plan.p[s] = cfg->factors[2 * s];
+            e->plan.m[s] = cfg->factors[2 * s + 1];
+        }
+        e->plan.d_tw = d_tw;
+        e->plan.d_stw = d_stw;
+        e->plan.h_tw = e->h_tw;
+        e->next = g_plans;
+        g_plans = e;
+    }
+    pthread_mutex_unlock(&g_lock);
+    *out = e;
+    return 0;
+}
+
+void kiss_fft_cleanup(void)
+{
+    int cur = 0;
+    cudaGetDevice(&cur);
+    pthread_mutex_lock(&g_stage_lock);
+    pthread_mutex_lock(&g_lock);
+    for (kf_devplan *e = g_plans; e;) {
+        kf_devplan *n = e->next;
+        cudaSetDevice(e->device);
+        cudaFree((void *)e->plan.d_tw);
+        if (e->plan.d_stw) cudaFree((void *)e->plan.d_stw);
+        free(e->h_tw);
+        free(e);
+        e = n;
+    }
+    g_plans = NULL;
+    for (int i = 0; i < KF_NSLOTS; ++i) {
+        if (g_dev_bufs[i].ptr) {
+            cudaSetDevice(g_dev_bufs[i].device);
+            cudaFree(g_dev_bufs[i].ptr);
+        }
+        g_dev_bufs[i].ptr = NULL;
+        g_dev_bufs[i].bytes = 0;
+    }
+    if (g_streams_dev >= 0) {
+        cudaSetDevice(g_streams_dev);
+        for (int i = 0; i < 4; ++i) cudaStreamDestroy(g_streams[i]);
+        g_streams_dev = -1;
+    }
+    cudaSetDevice(cur);
+    pthread_mutex_unlock(&g_lock);
+    pthread_mutex_unlock(&g_stage_lock);
+}
+
+/* scratch slot `i`, at least `bytes` large, on the current device (caller holds g_stage_lock) */
+static int kf_scratch(int i, size_t bytes, void **out)
+{
+    int dev = 0;
+    KF_CHECK(cudaGetDevice(&dev));
+    kf_buf *b = &g_dev_bufs[i];
+    if (b->ptr && (b->bytes < bytes || b->device != dev)) {
+        cudaSetDevice(b->device);
+        cudaFree(b->ptr);
+        cudaSetDevice(dev);
+        b->ptr = NULL;
+        b->bytes = 0;
+    }
+    if (!b->ptr) {
+        KF_CHECK(cudaMalloc(&b->ptr, bytes ? bytes : 1));
+        b->bytes = bytes;
+        b->device = dev;
+    }
+    *out = b->ptr;
+    return 0;
+}
+
+static int kf_get_streams(void)
+{
+    int dev = 0;
+    KF_CHECK(cudaGetDevice(&dev));
+    if (g_streams_dev != dev) {
+        if (g_streams_dev >= 0) {
+            cudaSetDevice(g_streams_dev);
+            for (int i = 0; i < 4; ++i) cudaStreamDestroy(g_streams[i]);
+            cudaSetDevice(dev);
+            g_streams_dev = -1;
+        }
+        for (int i = 0; i < 4; ++i) KF_CHECK(cudaStreamCreateWithFlags(&g_streams[i], cudaStreamNonBlocking));
+        g_streams_dev = dev;
+    }
+    return 0;
+}
+
+static int kf_is_device_ptr(const void *p)
+{
+    struct cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+/* ---- device-pointer batched entry points ---------------------------------------------------------------- */
+
+int kiss_fft_batch_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, size_t howmany, size_t in_dist,
+                       size_t out_dist, int in_stride, void *stream)
+{
+    if (!cfg || cfg->magic != KF_MAGIC_1D || !d_in || !d_out || in_stride < 1) {
+        KF_ERROR("kiss_fft_batch_dev: bad argument");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    const kf_devplan *dp;
+    KF_CHECK(kf_get_devplan(cfg, NULL, &dp));
+    KF_CHECK(kfcu_exec(KFCU_C2C, &dp->plan, d_in, d_out, (long long)howmany, (long long)in_dist, (long long)out_dist,
+                       (long long)in_stride, stream));
+    return 0;
+}
+
+int kiss_fft_axis_pass_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, size_t ncols, size_t col_stride,
+                           void *stream)
+{
+    if (!cfg || cfg->magic != KF_MAGIC_1D || !d_in || !d_out || col_stride < 1) {
+        KF_ERROR("kiss_fft_axis_pass_dev: bad argument");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    const kf_devplan *dp;
+    KF_CHECK(kf_get_devplan(cfg, NULL, &dp));
+    /* column i: elements d_in[i + j*col_stride]; written as row i: d_out[i*nfft + k]  (kiss_fftnd.c:176-177) */
+    const int mode = (col_stride == 1 && ncols == 1) ? KFCU_C2C : KFCU_C2C_COL;
+    KF_CHECK(kfcu_exec(mode, &dp->plan, d_in, d_out, (long long)ncols, 1, (long long)cfg->nfft, (long long)col_stride, stream));
+    return 0;
+}
+
+static int kf_real_args_ok(const void *d_real, size_t real_dist)
+{
+    return ((uintptr_t)d_real % (2 * sizeof(kiss_fft_scalar))) == 0 && (real_dist % 2) == 0;
+}
+
+int kiss_fftr_batch_dev(kiss_fftr_cfg cfg, const kiss_fft_scalar *d_time, kiss_fft_cpx *d_freq, size_t howmany,
+                        size_t time_dist, size_t freq_dist, void *stream)
+{
+    if (!cfg || cfg->magic != KF_MAGIC_R || !d_time || !d_freq) {
+        KF_ERROR("kiss_fftr_batch_dev: bad argument");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    if (cfg->substate->inverse) {
+        KF_ERROR("kiss fft usage error: improper alloc"); /* kiss_fftr.c:69-72 */
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    if (!kf_real_args_ok(d_time, time_dist)) {
+        KF_ERROR("kiss_fftr_batch_dev: real rows must be 2*sizeof(scalar) aligned and an even distance apart");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    const kf_devplan *dp;
+    KF_CHECK(kf_get_devplan(cfg->substate, cfg->super_twiddles, &dp));
+    KF_CHECK(kfcu_exec(KFCU_R2C, &dp->plan, d_time, d_freq, (long long)howmany, (long long)(time_dist / 2),
+                       (long long)freq_dist, 1, stream));
+    return 0;
+}
+
+int kiss_fftri_batch_dev(kiss_fftr_cfg cfg, const kiss_fft_cpx *d_freq, kiss_fft_scalar *d_time, size_t howmany,
+                         size_t freq_dist, size_t time_dist, void *stream)
+{
+    if (!cfg || cfg->magic != KF_MAGIC_R || !d_time || !d_freq) {
+        KF_ERROR("kiss_fftri_batch_dev: bad argument");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    if (cfg->substate->inverse == 0) {
+        KF_ERROR("kiss fft usage error: improper alloc"); /* kiss_fftr.c:124-127 */
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    if (!kf_real_args_ok(d_time, time_dist)) {
+        KF_ERROR("kiss_fftri_batch_dev: real rows must be 2*sizeof(scalar) aligned and an even distance apart");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    const kf_devplan *dp;
+    KF_CHECK(kf_get_devplan(cfg->substate, cfg->super_twiddles, &dp));
+    KF_CHECK(kfcu_exec(KFCU_C2R, &dp->plan, d_freq, d_time, (long long)howmany, (long long)freq_dist,
+                       (long long)(time_dist / 2), 1, stream));
+    return 0;
+}
+
+/* kiss_fftnd.c:156-188 on device buffers.  Pass k views the current buffer as dims[k] x stride, transforms
+ * every column and stores it as a row, ping-ponging so that the last pass lands in d_out. */
+static int kf_fftnd_dev_locked(kiss_fftnd_cfg st, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, kiss_fft_cpx *d_work,
+                               void *stream)
+{
+    const size_t bytes = sizeof(kiss_fft_cpx) * (size_t)st->dimprod;
+    const kiss_fft_cpx *bufin = d_in;
+    kiss_fft_cpx *bufout;
+    if (st->ndims == 0) return 0;
+    if (st->ndims & 1) {
+        bufout = d_out;
+        if (d_in == d_out) {
+            KF_CHECK(cudaMemcpyAsync(d_work, d_in, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+            bufin = d_work;
+        }
+    } else {
+        bufout = d_work;
+    }
+    for (int k = 0; k < st->ndims; ++k) {
+        const int curdim = st->dims[k];
+        const long long stride = st->dimprod / curdim;
+        KF_CHECK(kiss_fft_axis_pass_dev(st->states[k], bufin, bufout, (size_t)stride, (size_t)stride, stream));
+        if (bufout == d_work) {
+            bufout = d_out;
+            bufin = d_work;
+        } else {
+            bufout = d_work;
+            bufin = d_out;
+        }
+    }
+    return 0;
+}
+
+int kiss_fftnd_dev(kiss_fftnd_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, kiss_fft_cpx *d_work, void *stream)
+{
+    if (!cfg || cfg->magic != KF_MAGIC_ND || !d_in || !d_out) {
+        KF_ERROR("kiss_fftnd_dev: bad argument");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    if (d_work) return kf_fftnd_dev_locked(cfg, d_in, d_out, d_work, stream);
+    /* internal scratch: serialise users of the shared slot and wait for completion before releasing it */
+    pthread_mutex_lock(&g_stage_lock);
+    void *w = NULL;
+    int rc = kf_scratch(2, sizeof(kiss_fft_cpx) * (size_t)cfg->dimprod, &w);
+    if (!rc) rc = kf_fftnd_dev_locked(cfg, d_in, d_out, (kiss_fft_cpx *)w, stream);
+    if (!rc) rc = (int)cudaStreamSynchronize((cudaStream_t)stream);
+    pthread_mutex_unlock(&g_stage_lock);
+    return rc;
+}
+
+/* kiss_fftndr.c:86-110 and :112-132 on device buffers.
+ *
+ * The reference gathers every frequency bin into its own contiguous array, runs kiss_fftnd on it and scatters
+ * the result back.  Here the bins stay interleaved: with B = dimReal/2+1 the half spectra form the array
+ * [d0][d1]..[d(n-2)][B]; a transposing axis pass (kiss_fftnd.c:172-178) over the leading axis turns it into
+ * [d1]..[d(n-2)][B][d0], and after all n-1 leading axes it is [B][d0]..[d(n-2)], i.e. exactly the reference's
+ * bin-major tmp2 (kiss_fftndr.c:101-102) already transformed.  One transpose brings it to [dimOther][B].
+ * Every 1-D transform sees the reference's operands and the axes run in the reference's order 0,1,..., so the
+ * fixed-point results are bit-identical. */
+static int kf_leading_axes_dev(kiss_fftnd_cfg nd, size_t total, kiss_fft_cpx **a, kiss_fft_cpx **b, void *stream)
+{
+    for (int k = 0; k < nd->ndims; ++k) {
+        const size_t cols = total / (size_t)nd->dims[k];
+        KF_CHECK(kiss_fft_axis_pass_dev(nd->states[k], *a, *b, cols, cols, stream));
+        kiss_fft_cpx *t = *a;
+        *a = *b;
+        *b = t;
+    }
+    return 0;
+}
+
+int kiss_fftndr_dev(kiss_fftndr_cfg cfg, const kiss_fft_scalar *d_time, kiss_fft_cpx *d_freq, void *stream)
+{
+    if (!cfg || cfg->magic != KF_MAGIC_NDR || !d_time || !d_freq) {
+        KF_ERROR("kiss_fftndr_dev: bad argument");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    if (cfg->inverse) {
+        KF_ERROR("kiss fft usage error: improper alloc");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    const size_t nrbins = (size_t)cfg->dimReal / 2 + 1;
+    const size_t total = (size_t)cfg->dimOther * nrbins;
+    if (cfg->ndims == 1) return kiss_fftr_batch_dev(cfg->cfg_r, d_time, d_freq, 1, (size_t)cfg->dimReal, nrbins, stream);
+    pthread_mutex_lock(&g_stage_lock);
+    void *w0 = NULL, *w1 = NULL;
+    int rc = kf_scratch(3, sizeof(kiss_fft_cpx) * total, &w0);
+    if (!rc) rc = kf_scratch(4, sizeof(kiss_fft_cpx) * total, &w1);
+    kiss_fft_cpx *a = (kiss_fft_cpx *)w0, *b = (kiss_fft_cpx *)w1;
+    if (!rc) rc = kiss_fftr_batch_dev(cfg->cfg_r, d_time, a, (size_t)cfg->dimOther, (size_t)cfg->dimReal, nrbins, stream);
+    if (!rc) rc = kf_leading_axes_dev(cfg->cfg_nd, total, &a, &b, stream);
+    /* a: [B][dimOther] -> d_freq: [dimOther][B] */
+    if (!rc) rc = kfcu_transpose(a, d_freq, (long long)nrbins, (long long)cfg->dimOther, stream);
+    if (!rc) rc = (int)cudaStreamSynchronize((cudaStream_t)stream);
+    pthread_mutex_unlock(&g_stage_lock);
+    if (rc) return kf_cuda_fail(__FILE__, __LINE__, "kiss_fftndr_dev", rc);
+    return 0;
+}
+
+int kiss_fftndri_dev(kiss_fftndr_cfg cfg, const kiss_fft_cpx *d_freq, kiss_fft_scalar *d_time, void *stream)
+{
+    if (!cfg || cfg->magic != KF_MAGIC_NDR || !d_time || !d_freq) {
+        KF_ERROR("kiss_fftndri_dev: bad argument");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    if (!cfg->inverse) {
+        KF_ERROR("kiss fft usage error: improper alloc");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    const size_t nrbins = (size_t)cfg->dimReal / 2 + 1;
+    const size_t total = (size_t)cfg->dimOther * nrbins;
+    if (cfg->ndims == 1) return kiss_fftri_batch_dev(cfg->cfg_r, d_freq, d_time, 1, nrbins, (size_t)cfg->dimReal, stream);
+    pthread_mutex_lock(&g_stage_lock);
+    void *w0 = NULL, *w1 = NULL;
+    int rc = kf_scratch(3, sizeof(kiss_fft_cpx) * total, &w0);
+    if (!rc) rc = kf_scratch(4, sizeof(kiss_fft_cpx) * total, &w1);
+    kiss_fft_cpx *a = (kiss_fft_cpx *)w0, *b = (kiss_fft_cpx *)w1;
+    /* first leading-axis pass reads the caller's buffer directly ([d0].. [B] has d0 leading already) */
+    kiss_fftnd_cfg nd = cfg->cfg_nd;
+    if (!rc) {
+        const size_t cols = total / (size_t)nd->dims[0];
+        rc = kiss_fft_axis_pass_dev(nd->states[0], d_freq, a, cols, cols, stream);
+    }
+    for (int k = 1; !rc && k < nd->ndims; ++k) {
+        const size_t cols = total / (size_t)nd->dims[k];
+        rc = kiss_fft_axis_pass_dev(nd->states[k], a, b, cols, cols, stream);
+        kiss_fft_cpx *t = a; a = b; b = t;
+    }
+    /* a: [B][dimOther] -> b: [dimOther][B], then the real inverse of every row (kiss_fftndr.c:127-131) */
+    if (!rc) rc = kfcu_transpose(a, b, (long long)nrbins, (long long)cfg->dimOther, stream);
+    if (!rc) rc = kiss_fftri_batch_dev(cfg->cfg_r, b, d_time, (size_t)cfg->dimOther, nrbins, (size_t)cfg->dimReal, stream);
+    if (!rc) rc = (int)cudaStreamSynchronize((cudaStream_t)stream);
+    pthread_mutex_unlock(&g_stage_lock);
+    if (rc) return kf_cuda_fail(__FILE__, __LINE__, "kiss_fftndri_dev", rc);
+    return 0;
+}
+
+/* ---- host-pointer batched entry points: chunked H2D / kernel / D2H pipeline over 3 streams ---------------- */
+typedef int (*kf_chunk_fn)(void *cfg, const void *d_in, void *d_out, size_t howmany, void *stream);
+
+static int kf_chunk_c2c(void *cfg, const void *d_in, void *d_out, size_t n, void *stream)
+{
+    kiss_fft_cfg c = (kiss_fft_cfg)cfg;
+    return kiss_fft_batch_dev(c, (const kiss_fft_cpx *)d_in, (kiss_fft_cpx *)d_out, n, (size_t)c->nfft, (size_t)c->nfft, 1, stream);
+}
+static int kf_chunk_r2c(void *cfg, const void *d_in, void *d_out, size_t n, void *stream)
+{
+    kiss_fftr_cfg c = (kiss_fftr_cfg)cfg;
+    return kiss_fftr_batch_dev(c, (const kiss_fft_scalar *)d_in, (kiss_fft_cpx *)d_out, n, (size_t)c->nfft,
+                               (size_t)c->nfft / 2 + 1, stream);
+}
+static int kf_chunk_c2r(void *cfg, const void *d_in, void *d_out, size_t n, void *stream)
+{
+    kiss_fftr_cfg c = (kiss_fftr_cfg)cfg;
+    return kiss_fftri_batch_dev(c, (const kiss_fft_cpx *)d_in, (kiss_fft_scalar *)d_out, n, (size_t)c->nfft / 2 + 1,
+                                (size_t)c->nfft, stream);
+}
+
+static int kf_host_pipeline(kf_chunk_fn fn, void *cfg, const void *in, void *out, size_t howmany, size_t in_row_bytes,
+                            size_t out_row_bytes)
+{
+    enum { NS = 3 };
+    if (howmany == 0) return 0;
+    pthread_mutex_lock(&g_stage_lock);
+    int rc = kf_get_streams();
+    /* chunk so that one chunk moves ~32 MiB each way (PCIe-efficient, still >= 6 chunks for the big batches) */
+    size_t rows = (size_t)(32u << 20) / (in_row_bytes > out_row_bytes ? in_row_bytes : out_row_bytes);
+    if (rows < 1) rows = 1;
+    if (rows > howmany) rows = howmany;
+    void *din[NS], *dout[NS];
+    for (int s = 0; s < NS && !rc; ++s) {
+        /* one allocation per slot: input chunk followed by output chunk (256-B aligned) */
+        const size_t inb = (rows * in_row_bytes + 255u) & ~(size_t)255u;
+        void *base = NULL;
+        rc = kf_scratch(5 + s, inb + rows * out_row_bytes, &base);
+        din[s] = base;
+        dout[s] = (char *)base + inb;
+    }
+    size_t done = 0;
+    int c = 0;
+    while (!rc && done < howmany) {
+        const size_t n = (howmany - done < rows) ? howmany - done : rows;
+        const int s = c % NS;
+        cudaStream_t st = g_streams[s];
+        rc = (int)cudaMemcpyAsync(din[s], (const char *)in + done * in_row_bytes, n * in_row_bytes, cudaMemcpyHostToDevice, st);
+        if (!rc) rc = fn(cfg, din[s], dout[s], n, st);
+        if (!rc) rc = (int)cudaMemcpyAsync((char *)out + done * out_row_bytes, dout[s], n * out_row_bytes, cudaMemcpyDeviceToHost, st);
+        done += n;
+        ++c;
+    }
+    for (int s = 0; s < NS; ++s) {
+        int e = (g_streams_dev >= 0) ? (int)cudaStreamSynchronize(g_streams[s]) : 0;
+        if (!rc) rc = e;
+    }
+    pthread_mutex_unlock(&g_stage_lock);
+    if (rc) return kf_cuda_fail(__FILE__, __LINE__, "host batch pipeline", rc);
+    return 0;
+}
+
+int kiss_fft_batch(kiss_fft_cfg cfg, const kiss_fft_cpx *in, kiss_fft_cpx *out, size_t howmany)
+{
+    if (!cfg || cfg->magic != KF_MAGIC_1D || !in || !out) {
+        KF_ERROR("kiss_fft_batch: bad argument");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    const size_t rb = sizeof(kiss_fft_cpx) * (size_t)cfg->nfft;
+    return kf_host_pipeline(kf_chunk_c2c, cfg, in, out, howmany, rb, rb);
+}
+
+int kiss_fftr_batch(kiss_fftr_cfg cfg, const kiss_fft_scalar *timedata, kiss_fft_cpx *freqdata, size_t howmany)
+{
+    if (!cfg || cfg->magic != KF_MAGIC_R || !timedata || !freqdata || cfg->substate->inverse) {
+        KF_ERROR("kiss_fftr_batch: bad argument");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    return kf_host_pipeline(kf_chunk_r2c, cfg, timedata, freqdata, howmany, sizeof(kiss_fft_scalar) * (size_t)cfg->nfft,
+                            sizeof(kiss_fft_cpx) * ((size_t)cfg->nfft / 2 + 1));
+}
+
+int kiss_fftri_batch(kiss_fftr_cfg cfg, const kiss_fft_cpx *freqdata, kiss_fft_scalar *timedata, size_t howmany)
+{
+    if (!cfg || cfg->magic != KF_MAGIC_R || !timedata || !freqdata || !cfg->substate->inverse) {
+        KF_ERROR("kiss_fftri_batch: bad argument");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    return kf_host_pipeline(kf_chunk_c2r, cfg, freqdata, timedata, howmany, sizeof(kiss_fft_cpx) * ((size_t)cfg->nfft / 2 + 1),
+                            sizeof(kiss_fft_scalar) * (size_t)cfg->nfft);
+}
+
+/* ---- the reference's transform calls -------------------------------------------------------------------- */
+
+/* run `body` on device copies of host buffers: in (in_bytes) -> out (out_bytes) */
+typedef int (*kf_dev_body)(void *cfg, const void *d_in, void *d_out, void *d_work, long long arg);
+
+static int kf_stage_through_device(kf_dev_body body, void *cfg, const void *in, size_t in_bytes, void *out, size_t out_bytes,
+                                   size_t work_bytes, long long arg)
+{
+    pthread_mutex_lock(&g_stage_lock);
+    void *din = NULL, *dout = NULL, *dwork = NULL;
+    int rc = kf_scratch(0, in_bytes, &din);
+    if (!rc) rc = kf_scratch(1, out_bytes, &dout);
+    if (!rc && work_bytes) rc = kf_scratch(2, work_bytes, &dwork);
+    if (!rc) rc = (int)cudaMemcpy(din, in, in_bytes, cudaMemcpyHostToDevice);
+    if (!rc) rc = body(cfg, din, dout, dwork, arg);
+    if (!rc) rc = (int)cudaMemcpy(out, dout, out_bytes, cudaMemcpyDeviceToHost); /* synchronises with the kernel */
+    pthread_mutex_unlock(&g_stage_lock);
+    return rc;
+}
+
+static int kf_body_stride(void *cfg, const void *d_in, void *d_out, void *d_work, long long stride)
+{
+    (void)d_work;
+    kiss_fft_cfg c = (kiss_fft_cfg)cfg;
+    return kiss_fft_batch_dev(c, (const kiss_fft_cpx *)d_in, (kiss_fft_cpx *)d_out, 1, 0, 0, (int)stride, NULL);
+}
+
+void kiss_fft_stride(kiss_fft_cfg st, const kiss_fft_cpx *fin, kiss_fft_cpx *fout, int in_stride)
+{
+    if (!st || st->magic != KF_MAGIC_1D) {
+        KF_ERROR("kiss_fft: bad cfg");
+        return;
+    }
+    if (fout == NULL || fin == NULL) {
+        KF_ERROR("fout buffer NULL."); /* kiss_fft.c:380-383 */
+        return;
+    }
+    if (in_stride < 1) in_stride = 1;
+    if (kf_is_device_ptr(fin) || kf_is_device_ptr(fout)) {
+        /* device pointers: in place on the device, stream-ordered on the default stream; the kernel reads a
+         * whole transform into registers/shared memory before writing it, so fin == fout is fine */
+        (void)kiss_fft_batch_dev(st, fin, fout, 1, 0, 0, in_stride, NULL);
+        return;
+    }
+    const size_t n = (size_t)st->nfft;
+    const size_t in_bytes = sizeof(kiss_fft_cpx) * ((n - 1) * (size_t)in_stride + 1);
+    int rc = kf_stage_through_device(kf_body_stride, st, fin, in_bytes, fout, sizeof(kiss_fft_cpx) * n, 0, in_stride);
+    if (rc) kf_cuda_fail(__FILE__, __LINE__, "kiss_fft_stride", rc);
+}
+
+void kiss_fft(kiss_fft_cfg cfg, const kiss_fft_cpx *fin, kiss_fft_cpx *fout) { kiss_fft_stride(cfg, fin, fout, 1); }
+
+static int kf_body_r2c(void *cfg, const void *d_in, void *d_out, void *d_work, long long arg)
+{
+    (void)d_work; (void)arg;
+    kiss_fftr_cfg c = (kiss_fftr_cfg)cfg;
+    return kiss_fftr_batch_dev(c, (const kiss_fft_scalar *)d_in, (kiss_fft_cpx *)d_out, 1, 0, 0, NULL);
+}
+static int kf_body_c2r(void *cfg, const void *d_in, void *d_out, void *d_work, long long arg)
+{
+    (void)d_work; (void)arg;
+    kiss_fftr_cfg c = (kiss_fftr_cfg)cfg;
+    return kiss_fftri_batch_dev(c, (const kiss_fft_cpx *)d_in, (kiss_fft_scalar *)d_out, 1, 0, 0, NULL);
+}
+
+void kiss_fftr(kiss_fftr_cfg st, const kiss_fft_scalar *timedata, kiss_fft_cpx *freqdata)
+{
+    if (!st || st->magic != KF_MAGIC_R || !timedata || !freqdata) {
+        KF_ERROR("kiss_fftr: bad argument");
+        return;
+    }
+    if (st->substate->inverse) {
+        KF_ERROR("kiss fft usage error: improper alloc"); /* kiss_fftr.c:69-72: logged no-op */
+        return;
+    }
+    if (kf_is_device_ptr(timedata) || kf_is_device_ptr(freqdata)) {
+        (void)kiss_fftr_batch_dev(st, timedata, freqdata, 1, 0, 0, NULL);
+        return;
+    }
+    const size_t n = (size_t)st->nfft;
+    int rc = kf_stage_through_device(kf_body_r2c, st, timedata, sizeof(kiss_fft_scalar) * n, freqdata,
+                                     sizeof(kiss_fft_cpx) * (n / 2 + 1), 0, 0);
+    if (rc) kf_cuda_fail(__FILE__, __LINE__, "kiss_fftr", rc);
+}
+
+void kiss_fftri(kiss_fftr_cfg st, const kiss_fft_cpx *freqdata, kiss_fft_scalar *timedata)
+{
+    if (!st || st->magic != KF_MAGIC_R || !timedata || !freqdata) {
+        KF_ERROR("kiss_fftri: bad argument");
+        return;
+    }
+    if (st->substate->inverse == 0) {
+        KF_ERROR("kiss fft usage error: improper alloc"); /* kiss_fftr.c:124-127 */
+        return;
+    }
+    if (kf_is_device_ptr(timedata) || kf_is_device_ptr(freqdata)) {
+        (void)kiss_fftri_batch_dev(st, freqdata, timedata, 1, 0, 0, NULL);
+        return;
+    }
+    const size_t n = (size_t)st->nfft;
+    int rc = kf_stage_through_device(kf_body_c2r, st, freqdata, sizeof(kiss_fft_cpx) * (n / 2 + 1), timedata,
+                                     sizeof(kiss_fft_scalar) * n, 0, 0);
+    if (rc) kf_cuda_fail(__FILE__, __LINE__, "kiss_fftri", rc);
+}
+
+static int kf_body_nd(void *cfg, const void *d_in, void *d_out, void *d_work, long long arg)
+{
+    (void)arg;
+    return kf_fftnd_dev_locked((kiss_fftnd_cfg)cfg, (const kiss_fft_cpx *)d_in, (kiss_fft_cpx *)d_out, (kiss_fft_cpx *)d_work, NULL);
+}
+
+void kiss_fftnd(kiss_fftnd_cfg st, const kiss_fft_cpx *fin, kiss_fft_cpx *fout)
+{
+    if (!st || st->magic != KF_MAGIC_ND || !fin || !fout) {
+        KF_ERROR("kiss_fftnd: bad argument");
+        return;
+    }
+    if (kf_is_device_ptr(fin) || kf_is_device_ptr(fout)) {
+        (void)kiss_fftnd_dev(st, fin, fout, NULL, NULL);
+        return;
+    }
+    const size_t bytes = sizeof(kiss_fft_cpx) * (size_t)st->dimprod;
+    int rc = kf_stage_through_device(kf_body_nd, st, fin, bytes, fout, bytes, bytes, 0);
+    if (rc) kf_cuda_fail(__FILE__, __LINE__, "kiss_fftnd", rc);
+}
+
+void kiss_fftndr(kiss_fftndr_cfg st, const kiss_fft_scalar *timedata, kiss_fft_cpx *freqdata)
+{
+    if (!st || st->magic != KF_MAGIC_NDR || !timedata || !freqdata) {
+        KF_ERROR("kiss_fftndr: bad argument");
+        return;
+    }
+    if (kf_is_device_ptr(timedata) || kf_is_device_ptr(freqdata)) {
+        (void)kiss_fftndr_dev(st, timedata, freqdata, NULL);
+        return;
+    }
+    const size_t nrbins = (size_t)st->dimReal / 2 + 1;
+    const size_t in_bytes = sizeof(kiss_fft_scalar) * (size_t)st->dimOther * (size_t)st->dimReal;
+    const size_t out_bytes = sizeof(kiss_fft_cpx) * (size_t)st->dimOther * nrbins;
+    void *din = NULL, *dout = NULL;
+    int rc = (int)cudaMalloc(&din, in_bytes);
+    if (!rc) rc = (int)cudaMalloc(&dout, out_bytes);
+    if (!rc) rc = (int)cudaMemcpy(din, timedata, in_bytes, cudaMemcpyHostToDevice);
+    if (!rc) rc = kiss_fftndr_dev(st, (const kiss_fft_scalar *)din, (kiss_fft_cpx *)dout, NULL);
+    if (!rc) rc = (int)cudaMemcpy(freqdata, dout, out_bytes, cudaMemcpyDeviceToHost);
+    cudaFree(din);
+    cudaFree(dout);
+    if (rc) kf_cuda_fail(__FILE__, __LINE__, "kiss_fftndr", rc);
+}
+
+void kiss_fftndri(kiss_fftndr_cfg st, const kiss_fft_cpx *freqdata, kiss_fft_scalar *timedata)
+{
+    if (!st || st->magic != KF_MAGIC_NDR || !timedata || !freqdata) {
+        KF_ERROR("kiss_fftndri: bad argument");
+        return;
+    }
+    if (kf_is_device_ptr(timedata) || kf_is_device_ptr(freqdata)) {
+        (void)kiss_fftndri_dev(st, freqdata, timedata, NULL);
+        return;
+    }
+    const size_t nrbins = (size_t)st->dimReal / 2 + 1;
+    const size_t out_bytes = sizeof(kiss_fft_scalar) * (size_t)st->dimOther * (size_t)st->dimReal;
+    const size_t in_bytes = sizeof(kiss_fft_cpx) * (size_t)st->dimOther * nrbins;
+    void *din = NULL, *dout = NULL;
+    int rc = (int)cudaMalloc(&din, in_bytes);
+    if (!rc) rc = (int)cudaMalloc(&dout, out_bytes);
+    if (!rc) rc = (int)cudaMemcpy(din, freqdata, in_bytes, cudaMemcpyHostToDevice);
+    if (!rc) rc = kiss_fftndri_dev(st, (const kiss_fft_cpx *)din, (kiss_fft_scalar *)dout, NULL);
+    if (!rc) rc = (int)cudaMemcpy(timedata, dout, out_bytes, cudaMemcpyDeviceToHost);
+    cudaFree(din);
+    cudaFree(dout);
+    if (rc) kf_cuda_fail(__FILE__, __LINE__, "kiss_fftndri", rc);
+}
+
+void kiss_fft_cuda_force_generic(int on) { kfcu_force_generic(on); }
+
+int kiss_fft_cuda_plan_kind(int nfft)
+{
+    if (nfft <= 0) return -1;
+    if (kfcu_has_fused(nfft, KFCU_C2C)) return 1;
+    return nfft <= kfcu_generic_max_nfft() ? 0 : -1;
+}

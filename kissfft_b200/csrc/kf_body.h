@@ -1,0 +1,329 @@
+// kf_body.h -- bodies of the batched transform kernels, written against an execution-environment concept.
+//
+//   fused_body<A, PT, MODE>   compile-time plan PT::D (kf_plan.h): every transform is read from HBM once and
+//                             written once; the radix stages of kf_work/kf_bfly* (kiss_fft.c:15-300) run as
+//                             register groups that exchange through shared memory.  Persistent CTAs
+//                             (grid = resident CTAs), `tpc` transforms per CTA iteration.
+//   generic_body<A>           run-time plan for any nfft whose two exchange buffers fit in shared memory:
+//                             one radix stage per pass over shared memory.
+//
+// MODE selects what surrounds the complex transform:
+//   kC2C      kiss_fft / kiss_fft_stride with unit or small input stride             (kiss_fft.c:375-404)
+//   kC2CCol   kiss_fftnd axis pass: `tpc` adjacent columns are loaded together so that HBM reads are
+//             tpc*sizeof(cpx)-byte segments, each column is written as a contiguous row (kiss_fftnd.c:172-178)
+//   kR2C      kiss_fftr: packed complex transform + split-twiddle post pass fused     (kiss_fftr.c:63-117)
+//   kC2R      kiss_fftri: split pre pass fused + inverse complex transform            (kiss_fftr.c:119-155)
+#pragma once
+#include "kf_engine.h"
+
+namespace kf {
+
+enum Mode { kC2C = 0, kC2CCol = 1, kR2C = 2, kC2R = 3 };
+
+template <class A>
+struct KParams {
+    const typename A::C* in;     // complex view of the input (kR2C: the real rows, 2 scalars per element)
+    typename A::C* out;          // complex view of the output (kC2R: the real rows)
+    long long howmany;
+    long long in_dist, out_dist; // distance between consecutive transforms, in complex elements of each side
+    long long in_stride;         // element stride of the input (kiss_fft_stride's in_stride)
+    const typename A::C* tw;     // N twiddles (kR2C/kC2R: of the ncfft-point sub-transform)
+    const typename A::C* stw;    // ncfft/2 split twiddles (kiss_fftr.c:53-59), real modes only
+    PlanConsts<A> pc;
+    int inverse;
+};
+
+template <class C>
+KF_HD C ld_stream(const C* p)
+{
+#if !defined(__CUDA_ARCH__)
+    return *p;
+#else
+    // input rows are read exactly once: bypass L1 allocation
+    if constexpr (sizeof(C) == 4) {
+        unsigned u;
+        asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(u) : "l"(p));
+        return *reinterpret_cast<C*>(&u);
+    } else if constexpr (sizeof(C) == 8) {
+        unsigned long long u;
+        asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(u) : "l"(p));
+        return *reinterpret_cast<C*>(&u);
+    } else {
+        unsigned long long u0, u1;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(u0), "=l"(u1) : "l"(p));
+        struct alignas(16) U2 { unsigned long long a, b; } u{u0, u1};
+        return *reinterpret_cast<C*>(&u);
+    }
+#endif
+}
+
+template <class A>
+struct SrcGlobal {
+    const typename A::C* base;
+    long long stride;
+    KF_HD cx<typename A::R> load(int i) const { return A::load(ld_stream(base + (long long)i * stride)); }
+};
+template <class A>
+struct SrcShared {
+    const typename A::C* base;   // natural order, unpadded
+    KF_HD cx<typename A::R> load(int i) const { return A::load(base[i]); }
+};
+template <class A>
+struct DstGlobal {
+    typename A::C* base;
+    KF_HD void store(int k, const cx<typename A::R>& v) const { base[k] = A::store(v); }
+};
+template <class A>
+struct DstShared {
+    typename A::C* base;         // natural order, unpadded
+    KF_HD void store(int k, const cx<typename A::R>& v) const { base[k] = A::store(v); }
+};
+struct NoSrc {
+    template <class T = int>
+    KF_HD cx<int> load(int) const { return cx<int>{0, 0}; }
+};
+
+// ---- group sequencing: group g reads exchange buffer (x0+g-1)&1 and writes (x0+g)&1; one barrier per exchange ----
+template <class A, PlanDesc D, int g, class Src, class Dst, class Env>
+KF_HD void run_groups(Env& env, int t, bool active, const Src& src, const Dst& dst, typename A::C* buf0,
+                      typename A::C* buf1, const TwTab<A>& tw, const PlanConsts<A>& pc, int inverse)
+{
+    // buf0 is read by this group (unused for g == 0), buf1 is written (unused for the last group)
+    run_group<A, D, g, Src, Dst>(t, active, src, dst, buf0, buf1, tw, pc, inverse);
+    if constexpr (g + 1 < D.G) {
+        env.sync();
+        run_groups<A, D, g + 1, Src, Dst>(env, t, active, src, dst, buf1, buf0, tw, pc, inverse);
+    }
+}
+
+// PT is a tag type carrying the plan as `static constexpr PlanDesc D`.
+// Env abstracts the execution environment (thread/block ids, CTA barrier, dynamic shared memory) so that the
+// identical body runs as a CUDA kernel (DeviceEnv, kf_kernels.cuh) and, for index-math tests without a GPU,
+// under tests/emul's thread-per-CUDA-thread emulator.
+template <class A, class PT, int MODE, class Env>
+KF_HD void fused_body(const KParams<A>& P, Env& env)
+{
+    constexpr PlanDesc D = PT::D;
+    typedef typename A::C C;
+    typedef cx<typename A::R> X;
+    static_assert(D.valid(), "inconsistent plan descriptor");
+    C* const smem = reinterpret_cast<C*>(env.smem());
+    constexpr int kPitch = D.pitch();
+    // two exchange buffers of tpc * pitch elements each
+    C* const bufA = smem;
+    C* const bufB = smem + D.tpc * kPitch;
+
+    const int tid = env.tid();
+    const int team = tid / D.team, t = tid % D.team;              // standard mapping: a team owns a transform
+    const TwTab<A> tw{P.tw};
+    const long long ntiles = (P.howmany + D.tpc - 1) / D.tpc;
+    int par = 0;   // parity of the exchange buffer sequence, carried across tiles (see run_groups)
+
+    for (long long tile = env.bid(); tile < ntiles; tile += env.nblocks()) {
+        const long long b = tile * D.tpc + team;
+        const bool active = b < P.howmany;
+        C* b0 = (par ? bufB : bufA) + team * kPitch;
+        C* b1 = (par ? bufA : bufB) + team * kPitch;
+
+        if constexpr (MODE == kC2C) {
+            SrcGlobal<A> src{P.in + b * P.in_dist, P.in_stride};
+            DstGlobal<A> dst{P.out + b * P.out_dist};
+            // group 0 writes b1... sequence: g0 -> W(b1); g1: R(b1) W(b0); g2: R(b0) W(b1) ...
+            run_groups<A, D, 0>(env, t, active, src, dst, b0, b1, tw, P.pc, P.inverse);
+            if constexpr (D.G >= 2) par ^= (D.G - 1) & 1;
+        } else if constexpr (MODE == kC2CCol) {
+            // group 0 uses the transposed mapping: consecutive lanes take consecutive transforms (columns)
+            static_assert(D.G >= 2, "column mode needs a shared-memory exchange");
+            const int cteam = tid % D.tpc, ct = tid / D.tpc;
+            const long long cb = tile * D.tpc + cteam;
+            SrcGlobal<A> src{P.in + cb * P.in_dist, P.in_stride};
+            DstGlobal<A> dst{P.out + b * P.out_dist};
+            C* cb1 = (par ? bufA : bufB) + cteam * kPitch;
+            run_group<A, D, 0, SrcGlobal<A>, DstGlobal<A>>(ct, cb < P.howmany, src, dst, nullptr, cb1, tw, P.pc, P.inverse);
+            env.sync();
+            run_groups<A, D, 1>(env, t, active, src, dst, b1, b0, tw, P.pc, P.inverse);
+            par ^= (D.G - 1) & 1;
+        } else if constexpr (MODE == kR2C) {
+            // packed complex transform, last group leaves T[] in natural order in shared memory
+            SrcGlobal<A> src{P.in + b * P.in_dist, 1};
+            // buffer written by the last group: after G-1 exchanges the "next write" buffer
+            C* tb = (((D.G - 1) & 1) ? b0 : b1);
+            DstShared<A> dst{tb};
+            run_groups<A, D, 0>(env, t, active, src, dst, b0, b1, tw, P.pc, P.inverse);
+            env.sync();
+            if (active) {
+                constexpr int nc = D.N;
+                C* out = P.out + b * P.out_dist;
+                for (int k = t; k <= nc / 2; k += D.team) {
+                    X Tk = A::load(tb[k]);
+                    X Tnk = (k == 0) ? Tk : A::load(tb[nc - k]);
+                    X st = (k == 0) ? Tk : A::load(TwTab<A>::ro_load_c(P.stw + (k - 1)));
+                    X ok, onk;
+                    fftr_post_pair<A>(k, nc, Tk, Tnk, st, ok, onk);
+                    out[k] = A::store(ok);
+                    out[nc - k] = A::store(onk);
+                }
+            }
+            par ^= D.G & 1;   // G exchanges were used (G-1 between groups + the T[] buffer)
+        } else {   // kC2R
+            constexpr int nc = D.N;
+            // split pre pass writes T[] (natural order) into b1, group 0 then reads it from shared memory
+            if (active) {
+                const C* in = P.in + b * P.in_dist;
+                for (int k = t; k <= nc / 2; k += D.team) {
+                    X Fk = A::load(ld_stream(in + k));
+                    X Fnk = A::load(ld_stream(in + (nc - k)));
+                    X st = (k == 0) ? Fk : A::load(TwTab<A>::ro_load_c(P.stw + (k - 1)));
+                    X Tk, Tnk;
+                    fftri_pre_pair<A>(k, Fk, Fnk, st, Tk, Tnk);
+                    b1[k] = A::store(Tk);
+                    if (k != 0) b1[nc - k] = A::store(Tnk);
+                }
+            }
+            env.sync();
+            SrcShared<A> src{b1};
+            DstGlobal<A> dst{P.out + b * P.out_dist};
+            // group 0 reads b1 (via src) and writes b0; g1 reads b0 writes b1 ...
+            run_groups<A, D, 0>(env, t, active, src, dst, b1, b0, tw, P.pc, P.inverse);
+            par ^= D.G & 1;
+        }
+    }
+}
+
+// =========================================================================================================
+// Run-time plan kernel: any radix schedule, one stage per shared-memory pass.
+// =========================================================================================================
+struct GenericPlan {
+    int N, L;
+    int p[32], m[32];   // kf_factor order (kiss_fft.c:306-328), MAXFACTORS == 32 (_kiss_fft_guts.h:21)
+};
+
+template <class A>
+struct GParams {
+    KParams<A> k;
+    GenericPlan plan;
+    int mode;   // Mode
+    int tpc;    // transforms per CTA (kC2CCol: adjacent columns)
+};
+
+// One output element of the generic radix (kiss_fft.c:192-233) -- every thread owns one output so that even a
+// prime nfft (single stage p == nfft) is spread over the whole CTA.
+template <class A>
+KF_HD cx<typename A::R> generic_output(const typename A::C* rd, int u, int off, int q1, int p, int m,
+                                                            int F, int N, const TwTab<A>& tw)
+{
+    typedef cx<typename A::R> X;
+    const int k = u + q1 * m;
+    const int step = (int)(((long long)F * k) % N);
+    int twidx = 0;
+    X s0 = A::load(rd[(u * p) * F + off]);
+    X acc{A::divk_rt(s0.r, p), A::divk_rt(s0.i, p)};
+    for (int q = 1; q < p; ++q) {
+        twidx += step;
+        if (twidx >= N) twidx -= N;
+        X sq = A::load(rd[(u * p + q) * F + off]);
+        sq = X{A::divk_rt(sq.r, p), A::divk_rt(sq.i, p)};
+        acc = cadd<A>(acc, A::cmul(sq, tw.get(twidx)));
+    }
+    return cwrap<A>(acc);
+}
+
+template <class A, class Env>
+KF_HD void generic_body(const GParams<A>& G, Env& env)
+{
+    typedef typename A::C C;
+    typedef cx<typename A::R> X;
+    const KParams<A>& P = G.k;
+    const int N = G.plan.N, L = G.plan.L, tpc = G.tpc, mode = G.mode;
+    C* const buf0 = reinterpret_cast<C*>(env.smem());
+    C* const buf1 = buf0 + (size_t)tpc * N;
+    const TwTab<A> tw{P.tw};
+    const int nthr = env.nthreads(), tid = env.tid();
+    const long long ntiles = (P.howmany + tpc - 1) / tpc;
+
+    for (long long tile = env.bid(); tile < ntiles; tile += env.nblocks()) {
+        const long long bbase = tile * tpc;
+        const int nb = (int)((P.howmany - bbase) < tpc ? (P.howmany - bbase) : tpc);
+        // ---- load (level L, natural order) ----
+        if (mode == kC2R) {
+            for (int i = tid; i < nb * (N / 2 + 1); i += nthr) {
+                const int bl = i / (N / 2 + 1), k = i % (N / 2 + 1);
+                const C* in = P.in + (bbase + bl) * P.in_dist;
+                X Fk = A::load(in[k]), Fnk = A::load(in[N - k]);
+                X st = (k == 0) ? Fk : A::load(P.stw[k - 1]);
+                X Tk, Tnk;
+                fftri_pre_pair<A>(k, Fk, Fnk, st, Tk, Tnk);
+                // k == N-k (N even, k == N/2): the reference's second assignment wins (kiss_fftr.c:147-153)
+                if (k != N - k) buf0[bl * N + k] = A::store(Tk);
+                if (k != 0) buf0[bl * N + (N - k)] = A::store(Tnk);
+            }
+        } else if (mode == kC2CCol) {
+            for (int i = tid; i < tpc * N; i += nthr) {
+                const int bl = i % tpc, n = i / tpc;
+                if (bl < nb) buf0[bl * N + n] = P.in[(bbase + bl) * P.in_dist + (long long)n * P.in_stride];
+            }
+        } else {
+            for (int i = tid; i < nb * N; i += nthr) {
+                const int bl = i / N, n = i % N;
+                buf0[i] = P.in[(bbase + bl) * P.in_dist + (long long)n * P.in_stride];
+            }
+        }
+        env.sync();
+        // ---- radix stages, innermost first ----
+        C* rd = buf0;
+        C* wr = buf1;
+        int F = N;
+        for (int s = L - 1; s >= 0; --s) {
+            const int p = G.plan.p[s], m = G.plan.m[s];
+            F /= p;
+            if (p == 2 || p == 3 || p == 4 || p == 5) {
+                const int nbf = N / p;
+                for (int i = tid; i < nb * nbf; i += nthr) {
+                    const int bl = i / nbf, j = i % nbf;
+                    const int k = j / F, off = j % F;
+                    const C* r = rd + bl * N;
+                    C* w = wr + bl * N;
+                    X v[5];
+                    for (int q = 0; q < p; ++q) v[q] = A::load(r[(k * p + q) * F + off]);
+                    if (p == 2) bfly2<A, false>(v, tw.get(F * k));
+                    else if (p == 4) bfly4<A, false>(v, tw.get(F * k), tw.get(2 * F * k), tw.get(3 * F * k), P.inverse);
+                    else if (p == 3) bfly3<A, false>(v, tw.get(F * k), tw.get(2 * F * k), P.pc.epi3.i);
+                    else bfly5<A, false>(v, tw.get(F * k), tw.get(2 * F * k), tw.get(3 * F * k), tw.get(4 * F * k), P.pc.ya, P.pc.yb);
+                    for (int q = 0; q < p; ++q) w[(k + q * m) * F + off] = A::store(v[q]);
+                }
+            } else {
+                for (int i = tid; i < nb * N; i += nthr) {
+                    const int bl = i / N, o = i % N;          // o = output address (k*F + off)
+                    const int k = o / F, off = o % F;
+                    const int q1 = k / m, u = k % m;
+                    wr[bl * N + o] = A::store(generic_output<A>(rd + bl * N, u, off, q1, p, m, F, N, tw));
+                }
+            }
+            env.sync();
+            C* tsw = rd; rd = wr; wr = tsw;
+        }
+        // ---- store (level 0, natural order, in rd) ----
+        if (mode == kR2C) {
+            for (int i = tid; i < nb * (N / 2 + 1); i += nthr) {
+                const int bl = i / (N / 2 + 1), k = i % (N / 2 + 1);
+                const C* T = rd + bl * N;
+                C* out = P.out + (bbase + bl) * P.out_dist;
+                X Tk = A::load(T[k]);
+                X Tnk = (k == 0) ? Tk : A::load(T[N - k]);
+                X st = (k == 0) ? Tk : A::load(P.stw[k - 1]);
+                X ok, onk;
+                fftr_post_pair<A>(k, N, Tk, Tnk, st, ok, onk);
+                if (k != N - k) out[k] = A::store(ok);
+                out[N - k] = A::store(onk);
+            }
+        } else {
+            for (int i = tid; i < nb * N; i += nthr) {
+                const int bl = i / N, k = i % N;
+                P.out[(bbase + bl) * P.out_dist + k] = rd[i];
+            }
+        }
+        env.sync();
+    }
+}
+
+}   // namespace kf

@@ -1,0 +1,280 @@
+// kf_engine.h -- register-group executor of a compile-time Stockham plan (see kf_plan.h for the math).
+//
+// Replaces kf_work's depth-first recursion (kiss_fft.c:235-300): one "work item" of group g is the set of
+// R(g) elements that the fused stages s_hi(g)..s_lo(g) combine; a thread loads them (from HBM for the first
+// group, from the shared-memory exchange buffer otherwise), runs the fused radix stages in registers with the
+// butterflies of kf_math.h, and stores them (to HBM for the last group).  All index arithmetic that depends
+// only on the plan is resolved at compile time (static_for + constexpr PlanDesc members).
+//
+// Host-compilable (KF_HD) so tests/emul can execute the same index math thread-by-thread on the CPU.
+#pragma once
+#include <type_traits>
+#include <utility>
+
+#include "kf_plan.h"
+
+namespace kf {
+
+template <class F, int... I>
+KF_HD void static_for_impl(F&& f, std::integer_sequence<int, I...>)
+{
+    (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+KF_HD void static_for(F&& f)
+{
+    static_for_impl(f, std::make_integer_sequence<int, N>{});
+}
+
+// read-only table fetch (twiddles live in HBM but are L1/L2 resident: <= 32 KiB per plan)
+template <class T>
+KF_HD T ro_load(const T* p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+template <class A>
+struct TwTab {
+    typedef typename A::C C;
+    typedef cx<typename A::R> X;
+    const C* tw;   // N entries, tw[i] = exp(-+2 pi j i/N) generated on the host exactly like kiss_fft.c:361-367
+    KF_HD X get(int idx) const
+    {
+        // all storage complexes are plain {S r, i}; load as one vector
+        C c = ro_load_c(tw + idx);
+        return A::load(c);
+    }
+    static KF_HD C ro_load_c(const C* p)
+    {
+#if defined(__CUDA_ARCH__)
+        if constexpr (sizeof(C) == 4) {
+            unsigned u = __ldg(reinterpret_cast<const unsigned*>(p));
+            return *reinterpret_cast<C*>(&u);
+        } else if constexpr (sizeof(C) == 8) {
+            float2 u = __ldg(reinterpret_cast<const float2*>(p));
+            return *reinterpret_cast<C*>(&u);
+        } else {
+            double2 u = __ldg(reinterpret_cast<const double2*>(p));
+            return *reinterpret_cast<C*>(&u);
+        }
+#else
+        return *p;
+#endif
+    }
+};
+
+// per-plan constants used by the radix-3 and radix-5 butterflies (kiss_fft.c:99, 143-144)
+template <class A>
+struct PlanConsts {
+    cx<typename A::R> epi3;   // tw[N/3]
+    cx<typename A::R> ya;     // tw[N/5]
+    cx<typename A::R> yb;     // tw[2N/5]
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// generic radix p (kf_bfly_generic, kiss_fft.c:192-233)
+// ---------------------------------------------------------------------------------------------------------
+// Fixed point: literal restatement -- scratch pre-scaled by 1/p, twiddle index walked modulo N, products
+// rounded one by one and accumulated in the order q = 1..p-1, so the result is bit-identical.
+template <class A, int N, int p, int Fs, int ms>
+KF_HD void bfly_generic_fixed(cx<typename A::R>* v, int ks, const TwTab<A>& tw)
+{
+    typedef cx<typename A::R> X;
+    X sc[p];
+    static_for<p>([&](auto Q) { constexpr int q = decltype(Q)::value; sc[q] = cfixdiv<A, p>(v[q]); });
+    static_for<p>([&](auto Q1) {
+        constexpr int q1 = decltype(Q1)::value;
+        const int k = ks + q1 * ms;
+        int twidx = 0;
+        X acc = sc[0];
+        static_for<p - 1>([&](auto Qm1) {
+            twidx += Fs * k;
+            if (twidx >= N) twidx -= N;
+            acc = cadd<A>(acc, A::cmul(sc[decltype(Qm1)::value + 1], tw.get(twidx)));
+        });
+        v[q1] = cwrap<A>(acc);
+    });
+}
+
+// Floating point: tw[(q*(ks+q1*ms)*Fs) mod N] = tw[q*ks*Fs] * W_p^(q*q1) with W_p^j = tw[j*N/p], so the stage
+// twiddles are applied first (p-1 products, as the radix-2..5 butterflies do) and the remaining constant
+// p-point DFT uses the conjugate symmetry W_p^(p-j) = conj(W_p^j): outputs q1 and p-q1 share their sums.
+// Same operands, different association => equal up to rounding (parity is relative-RMS for float/double).
+template <class A, int N, int p, int Fs, int ms, bool TW1>
+KF_HD void bfly_generic_float(cx<typename A::R>* v, int ks, const TwTab<A>& tw)
+{
+    typedef typename A::R R;
+    typedef cx<R> X;
+    static_assert(p % 2 == 1, "generic radices are odd (kf_factor emits 4, 2, then odd numbers)");
+    constexpr int h = (p - 1) / 2;
+    X y[p];
+    y[0] = v[0];
+    static_for<p - 1>([&](auto Qm1) {
+        constexpr int q = decltype(Qm1)::value + 1;
+        y[q] = TW1 ? v[q] : A::cmul(v[q], tw.get(q * Fs * ks));
+    });
+    X a[h + 1], b[h + 1];
+    X sum = y[0];
+    static_for<h>([&](auto Qm1) {
+        constexpr int q = decltype(Qm1)::value + 1;
+        a[q] = X{y[q].r + y[p - q].r, y[q].i + y[p - q].i};
+        b[q] = X{y[q].r - y[p - q].r, y[q].i - y[p - q].i};
+        sum.r += a[q].r;
+        sum.i += a[q].i;
+    });
+    v[0] = sum;
+    static_for<h>([&](auto Q1m1) {
+        constexpr int q1 = decltype(Q1m1)::value + 1;
+        X P = y[0], Qv{(R)0, (R)0};
+        static_for<h>([&](auto Qm1) {
+            constexpr int q = decltype(Qm1)::value + 1;
+            constexpr int j = (q * q1) % p;
+            const X w = tw.get(j * (N / p));   // compile-time index: uniform, cache resident
+            P.r += a[q].r * w.r;
+            P.i += a[q].i * w.r;
+            Qv.r -= b[q].i * w.i;
+            Qv.i += b[q].r * w.i;
+        });
+        v[q1] = X{P.r + Qv.r, P.i + Qv.i};
+        v[p - q1] = X{P.r - Qv.r, P.i - Qv.i};
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// one radix stage s of group g applied to the R(g) registers of a work item whose k' is `kp`
+// ---------------------------------------------------------------------------------------------------------
+template <class A, PlanDesc D, int g, int s>
+KF_HD void run_stage(cx<typename A::R>* v, int kp, const TwTab<A>& tw, const PlanConsts<A>& pc, int inverse)
+{
+    typedef cx<typename A::R> X;
+    constexpr int p = D.p[s], Ws = D.W(g, s), Fs = D.F(s), ms = D.m(s), R = D.R(g);
+    static_for<R>([&](auto E) {
+        constexpr int e = decltype(E)::value;
+        if constexpr (D.digit(g, s, e) == 0) {
+            constexpr int kab = D.kabove(g, s, e);
+            // group 0 has k' == 0 (m_{L-1} == 1), so its twiddle indices are compile-time constants and the
+            // all-ones case can be dropped for float/double
+            constexpr bool kTw1 = !A::kFixed && g == 0 && kab == 0;
+            const int ks = (g == 0 ? 0 : kp) + kab;
+            X x[p];
+            static_for<p>([&](auto Q) { constexpr int q = decltype(Q)::value; x[q] = v[e + q * Ws]; });
+            if constexpr (p == 2) {
+                bfly2<A, kTw1>(x, kTw1 ? X{} : tw.get(Fs * ks));
+            } else if constexpr (p == 4) {
+                bfly4<A, kTw1>(x, kTw1 ? X{} : tw.get(Fs * ks), kTw1 ? X{} : tw.get(2 * Fs * ks),
+                               kTw1 ? X{} : tw.get(3 * Fs * ks), inverse);
+            } else if constexpr (p == 3) {
+                bfly3<A, kTw1>(x, kTw1 ? X{} : tw.get(Fs * ks), kTw1 ? X{} : tw.get(2 * Fs * ks), pc.epi3.i);
+            } else if constexpr (p == 5) {
+                bfly5<A, kTw1>(x, kTw1 ? X{} : tw.get(Fs * ks), kTw1 ? X{} : tw.get(2 * Fs * ks),
+                               kTw1 ? X{} : tw.get(3 * Fs * ks), kTw1 ? X{} : tw.get(4 * Fs * ks), pc.ya, pc.yb);
+            } else if constexpr (A::kFixed) {
+                bfly_generic_fixed<A, D.N, p, Fs, ms>(x, ks, tw);
+            } else {
+                bfly_generic_float<A, D.N, p, Fs, ms, kTw1>(x, ks, tw);
+            }
+            static_for<p>([&](auto Q) { constexpr int q = decltype(Q)::value; v[e + q * Ws] = x[q]; });
+        }
+    });
+}
+
+template <class A, PlanDesc D, int g, int s>
+KF_HD void run_stages_from(cx<typename A::R>* v, int kp, const TwTab<A>& tw, const PlanConsts<A>& pc, int inverse)
+{
+    run_stage<A, D, g, s>(v, kp, tw, pc, inverse);
+    if constexpr (s > D.s_lo(g)) run_stages_from<A, D, g, s - 1>(v, kp, tw, pc, inverse);
+}
+
+KF_HD int phys_rt(int a, int logpad) { return logpad >= 31 ? a : a + (a >> logpad); }
+
+// ---------------------------------------------------------------------------------------------------------
+// one group for one thread.  t = thread index inside the team, `active` = this team has a transform.
+//   Src::load(i)      element i of the level-L (natural order) input of this transform   [group 0 only]
+//   Dst::store(k, v)  element k of the natural-order output                               [last group only]
+//   rd / wr           this transform's exchange buffers (already offset by team * pitch)
+// ---------------------------------------------------------------------------------------------------------
+template <class A, PlanDesc D, int g, class Src, class Dst>
+KF_HD void run_group(int t, bool active, const Src& src, const Dst& dst, const typename A::C* rd, typename A::C* wr,
+                     const TwTab<A>& tw, const PlanConsts<A>& pc, int inverse)
+{
+    typedef cx<typename A::R> X;
+    constexpr int R = D.R(g), WI = D.items(g), IT = D.iters(g), Flo = D.Flo(g);
+    constexpr bool kFirst = (g == 0), kLast = (g == D.G - 1);
+    static_for<IT>([&](auto ITER) {
+        constexpr int it = decltype(ITER)::value;
+        const int w = t + it * D.team;
+        const bool on = active && ((it + 1) * D.team <= WI || w < WI);
+        if (on) {
+            const int off = w % Flo, kp = w / Flo;
+            X v[R];
+            static_for<R>([&](auto E) {
+                constexpr int e = decltype(E)::value;
+                if constexpr (kFirst) v[e] = src.load(off + e * Flo);
+                else v[e] = A::load(rd[phys_rt(kp * (Flo * R) + off + e * Flo, D.logpad)]);
+            });
+            run_stages_from<A, D, g, D.s_hi(g)>(v, kp, tw, pc, inverse);
+            static_for<R>([&](auto E) {
+                constexpr int e = decltype(E)::value;
+                const int k = kp + D.kout(g, e);
+                if constexpr (kLast) dst.store(k, v[e]);
+                else wr[phys_rt(k * Flo + off, D.logpad)] = A::store(v[e]);
+            });
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// real-transform split passes (kiss_fftr.c:88-116 and :131-153) on one bin pair k / ncfft-k
+// ---------------------------------------------------------------------------------------------------------
+// forward: T = FFT_ncfft(packed input); produces out[k] and out[nc-k] (k >= 1), or out[0] / out[nc] (k == 0)
+template <class A>
+KF_HD void fftr_post_pair(int k, int nc, const cx<typename A::R>& Tk, const cx<typename A::R>& Tnk,
+                          const cx<typename A::R>& st_km1, cx<typename A::R>& outk, cx<typename A::R>& outnk)
+{
+    typedef typename A::R R;
+    typedef cx<R> X;
+    if (k == 0) {
+        X tdc = cfixdiv<A, 2>(Tk);
+        outk = X{A::wrap(A::add(tdc.r, tdc.i)), (R)0};
+        outnk = X{A::wrap(A::sub(tdc.r, tdc.i)), (R)0};
+        return;
+    }
+    X fpk = cfixdiv<A, 2>(Tk);
+    X fpnk = cfixdiv<A, 2>(X{Tnk.r, A::wrap(A::neg(Tnk.i))});
+    X f1k = cwrap<A>(cadd<A>(fpk, fpnk));
+    X f2k = cwrap<A>(csub<A>(fpk, fpnk));
+    X tw = A::cmul(f2k, st_km1);
+    // HALF_OF(sum): the sum is formed in int before the shift (kiss_fftr.c:112-115)
+    outk = X{A::half(A::add(f1k.r, tw.r)), A::half(A::add(f1k.i, tw.i))};
+    outnk = X{A::half(A::sub(f1k.r, tw.r)), A::half(A::sub(tw.i, f1k.i))};
+    (void)nc;
+}
+
+// inverse: consumes F[k], F[nc-k]; produces T[k], T[nc-k] (k >= 1) or T[0] (k == 0, Tnk_out unused)
+template <class A>
+KF_HD void fftri_pre_pair(int k, const cx<typename A::R>& Fk, const cx<typename A::R>& Fnk,
+                          const cx<typename A::R>& st_km1, cx<typename A::R>& Tk, cx<typename A::R>& Tnk)
+{
+    typedef cx<typename A::R> X;
+    if (k == 0) {
+        // Fnk is F[nc] here
+        X t{A::wrap(A::add(Fk.r, Fnk.r)), A::wrap(A::sub(Fk.r, Fnk.r))};
+        Tk = cfixdiv<A, 2>(t);
+        Tnk = Tk;
+        return;
+    }
+    X fk = cfixdiv<A, 2>(Fk);
+    X fnkc = cfixdiv<A, 2>(X{Fnk.r, A::wrap(A::neg(Fnk.i))});
+    X fek = cwrap<A>(cadd<A>(fk, fnkc));
+    X tmp = cwrap<A>(csub<A>(fk, fnkc));
+    X fok = A::cmul(tmp, st_km1);
+    Tk = cwrap<A>(cadd<A>(fek, fok));
+    X d = csub<A>(fek, fok);
+    Tnk = cwrap<A>(X{d.r, A::neg(d.i)});
+}
+
+}   // namespace kf

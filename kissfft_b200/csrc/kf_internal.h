@@ -1,0 +1,55 @@
+/* kf_internal.h -- private C interface between the C host layer (kf_api.c) and the CUDA launchers
+ * (kf_launch.cu).  One library is built per datatype, exactly like the reference builds one
+ * libkissfft-<type>.so per datatype (reference Makefile:89-137); the datatype is fixed by the same macros the
+ * reference uses (FIXED_POINT=16|32, kiss_fft_scalar=float|double). */
+#ifndef KF_INTERNAL_H
+#define KF_INTERNAL_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KFCU_MAXSTAGES 32 /* MAXFACTORS, _kiss_fft_guts.h:21 */
+
+enum { KFCU_C2C = 0, KFCU_C2C_COL = 1, KFCU_R2C = 2, KFCU_C2R = 3 };
+
+/* device-side view of one 1-D plan (one per (device, nfft, inverse)) */
+typedef struct kfcu_plan {
+    int nfft; /* length of the complex transform (ncfft for the real modes) */
+    int inverse;
+    int nstages;
+    int p[KFCU_MAXSTAGES]; /* kf_factor order: p[0] outermost */
+    int m[KFCU_MAXSTAGES];
+    const void *d_tw;  /* nfft complex twiddles in device memory */
+    const void *d_stw; /* nfft/2 split twiddles (real modes) or NULL */
+    const void *h_tw;  /* the same twiddles on the host (for the butterfly constants) */
+} kfcu_plan;
+
+/* Runs `howmany` transforms. Distances are in complex elements of the respective side (for KFCU_R2C the input
+ * side and for KFCU_C2R the output side are real rows viewed as packed complex, i.e. scalars/2).
+ * Returns 0 or a cudaError_t value; KFCU_E* (negative) for argument errors. */
+int kfcu_exec(int mode, const kfcu_plan *plan, const void *d_in, void *d_out, long long howmany, long long in_dist,
+              long long out_dist, long long in_stride, void *stream);
+
+/* out[c][r] = in[r][c] for a rows x cols array of complex elements (kiss_fftndr's bin-major <-> row-major
+ * scatter loops, kiss_fftndr.c:101-102, 107-108) */
+int kfcu_transpose(const void *d_in, void *d_out, long long rows, long long cols, void *stream);
+
+/* 1 if a compile-time (fused, register-group) plan exists for this length/mode in this datatype build */
+int kfcu_has_fused(int nfft, int mode);
+/* largest nfft the run-time (generic shared-memory) kernel accepts */
+int kfcu_generic_max_nfft(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+long long kfcu_launch_count(void);
+/* force the generic kernel even when a fused plan exists (testing aid; 0 = default) */
+void kfcu_force_generic(int on);
+
+#define KFCU_EINVAL (-1)
+#define KFCU_ETOOBIG (-2)
+
+#ifdef __cplusplus
+}
+#endif
+#endif

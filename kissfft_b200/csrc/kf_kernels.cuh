@@ -1,0 +1,57 @@
+// kf_kernels.cuh -- sm_100a __global__ entry points: thin wrappers that bind the kernel bodies of kf_body.h
+// to the CUDA execution environment.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kf_body.h"
+
+namespace kf {
+
+struct DeviceEnv {
+    unsigned char* smem_;
+    __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
+    __device__ __forceinline__ int nthreads() const { return (int)blockDim.x; }
+    __device__ __forceinline__ long long bid() const { return (long long)blockIdx.x; }
+    __device__ __forceinline__ long long nblocks() const { return (long long)gridDim.x; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ unsigned char* smem() const { return smem_; }
+};
+
+// PT is a tag type carrying the plan as `static constexpr PlanDesc D` (a class-type non-type template argument
+// cannot appear in a __global__ signature: nvcc's host stub cannot spell it).
+template <class A, class PT, int MODE>
+__global__ void __launch_bounds__(PT::D.threads(), PT::D.minblocks) kf_fused_kernel(const __grid_constant__ KParams<A> P)
+{
+    extern __shared__ __align__(16) unsigned char kf_smem_raw[];
+    DeviceEnv env{kf_smem_raw};
+    fused_body<A, PT, MODE>(P, env);
+}
+
+template <class A>
+__global__ void __launch_bounds__(256) kf_generic_kernel(const __grid_constant__ GParams<A> G)
+{
+    extern __shared__ __align__(16) unsigned char kf_smem_raw[];
+    DeviceEnv env{kf_smem_raw};
+    generic_body<A>(G, env);
+}
+
+// tiled transpose of a rows x cols array of storage complexes (32 x 32 tiles, +1 column of padding)
+template <class C>
+__global__ void __launch_bounds__(256) kf_transpose_kernel(const C* __restrict__ in, C* __restrict__ out, long long rows,
+                                                          long long cols)
+{
+    __shared__ C tile[32][33];
+    const long long tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;   // 32 x 8
+    for (long long tI = blockIdx.x; tI < tiles_c * tiles_r; tI += gridDim.x) {
+        const long long r0 = (tI / tiles_c) * 32, c0 = (tI % tiles_c) * 32;
+        for (int j = ty; j < 32; j += 8)
+            if (r0 + j < rows && c0 + tx < cols) tile[j][tx] = in[(r0 + j) * cols + c0 + tx];
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8)
+            if (c0 + j < cols && r0 + tx < rows) out[(c0 + j) * rows + r0 + tx] = tile[tx][j];
+        __syncthreads();
+    }
+}
+
+}   // namespace kf

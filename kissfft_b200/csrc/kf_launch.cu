@@ -1,0 +1,202 @@
+// kf_launch.cu -- kernel selection and launch (the only translation unit that instantiates kernels).
+//
+// Built once per datatype (FIXED_POINT / kiss_fft_scalar macros, see include/kiss_fft.h).  The host layer
+// (kf_api.c) hands over a kfcu_plan that carries the reference's radix schedule and twiddle tables; this file
+// picks the compile-time fused plan when one is registered for the length (kf_plans.inc) and otherwise the
+// run-time shared-memory kernel.  There is no CPU path: if no kernel applies the call fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "../../include/kiss_fft.h"
+#include "kf_internal.h"
+#include "kf_kernels.cuh"
+#define KF_SCALAR_BYTES ((int)sizeof(kiss_fft_scalar))
+#include "kf_plan_list.h"
+
+using namespace kf;
+
+typedef Arith<kiss_fft_scalar> AT;
+typedef AT::C CT;
+static_assert(sizeof(CT) == sizeof(kiss_fft_cpx), "storage complex must match kiss_fft_cpx");
+
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_force_generic{0};
+
+struct DeviceInfo {
+    int sms = 0;
+    int max_smem_optin = 0;
+};
+static DeviceInfo device_info()
+{
+    static DeviceInfo cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (cache[dev].sms == 0) {
+        cudaDeviceGetAttribute(&cache[dev].sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&cache[dev].max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    return cache[dev];
+}
+
+static KParams<AT> make_params(const kfcu_plan* pl, const void* d_in, void* d_out, long long howmany, long long in_dist,
+                               long long out_dist, long long in_stride)
+{
+    KParams<AT> P;
+    P.in = (const CT*)d_in;
+    P.out = (CT*)d_out;
+    P.howmany = howmany;
+    P.in_dist = in_dist;
+    P.out_dist = out_dist;
+    P.in_stride = in_stride;
+    P.tw = (const CT*)pl->d_tw;
+    P.stw = (const CT*)pl->d_stw;
+    const CT* h = (const CT*)pl->h_tw;
+    const int N = pl->nfft;
+    // constants of kf_bfly3 / kf_bfly5 (kiss_fft.c:99, 143-144): twiddles[fstride*m] with fstride*m == N/p
+    CT z{};
+    P.pc.epi3 = AT::load((N % 3 == 0) ? h[N / 3] : z);
+    P.pc.ya = AT::load((N % 5 == 0) ? h[N / 5] : z);
+    P.pc.yb = AT::load((N % 5 == 0) ? h[2 * (N / 5)] : z);
+    P.inverse = pl->inverse;
+    return P;
+}
+
+// ---- fused plans ------------------------------------------------------------------------------------------
+typedef int (*fused_launch_fn)(const KParams<AT>&, cudaStream_t);
+
+template <class PT, int MODE>
+static int launch_fused(const KParams<AT>& P, cudaStream_t st)
+{
+    constexpr PlanDesc D = PT::D;
+    auto kern = kf_fused_kernel<AT, PT, MODE>;
+    constexpr size_t smem = (D.G >= 2 || MODE == kR2C || MODE == kC2R) ? (size_t)2 * D.tpc * D.pitch() * sizeof(CT) : 0;
+    static int blocks_per_sm[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (blocks_per_sm[dev] == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, D.threads(), smem);
+        if (e != cudaSuccess) return (int)e;
+        if (nb < 1) return (int)cudaErrorLaunchOutOfResources;
+        blocks_per_sm[dev] = nb;
+    }
+    const long long ntiles = (P.howmany + D.tpc - 1) / D.tpc;
+    long long grid = (long long)device_info().sms * blocks_per_sm[dev];
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) return 0;
+    kern<<<(unsigned)grid, D.threads(), smem, st>>>(P);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+struct FusedEntry {
+    int N;
+    fused_launch_fn fn[4];   // indexed by Mode; null = not instantiated
+};
+
+#define KF_FUSED_ALL(PT) { PT::D.N, { launch_fused<PT, kC2C>, launch_fused<PT, kC2CCol>, launch_fused<PT, kR2C>, launch_fused<PT, kC2R> } }
+#define KF_FUSED_C2C(PT) { PT::D.N, { launch_fused<PT, kC2C>, nullptr, nullptr, nullptr } }
+#define KF_FUSED_C2C_REAL(PT) { PT::D.N, { launch_fused<PT, kC2C>, nullptr, launch_fused<PT, kR2C>, launch_fused<PT, kC2R> } }
+
+#include "kf_plans.inc"
+
+static const FusedEntry* find_fused(int nfft, int mode)
+{
+    if (g_force_generic.load()) return nullptr;
+    for (const FusedEntry& e : kFusedTable)
+        if (e.N == nfft && e.fn[mode]) return &e;
+    return nullptr;
+}
+
+// ---- generic kernel ---------------------------------------------------------------------------------------
+static int launch_generic(int mode, const kfcu_plan* pl, const KParams<AT>& P, cudaStream_t st)
+{
+    const DeviceInfo di = device_info();
+    const size_t per = (size_t)2 * pl->nfft * sizeof(CT);
+    if (per > (size_t)di.max_smem_optin) return KFCU_ETOOBIG;
+    GParams<AT> G;
+    G.k = P;
+    G.plan.N = pl->nfft;
+    G.plan.L = pl->nstages;
+    for (int s = 0; s < pl->nstages; ++s) { G.plan.p[s] = pl->p[s]; G.plan.m[s] = pl->m[s]; }
+    G.mode = mode;
+    // transforms per CTA: fill ~32 KiB of exchange buffers; column mode wants >= 64-byte row segments
+    int tpc = (int)((32 * 1024) / per);
+    if (mode == kC2CCol) { int want = (int)(64 / sizeof(CT)); if (want < 1) want = 1; if (tpc < want) tpc = want; }
+    if (tpc < 1) tpc = 1;
+    while (tpc > 1 && (size_t)tpc * per > (size_t)di.max_smem_optin) --tpc;
+    if ((long long)tpc > P.howmany) tpc = (int)P.howmany;
+    G.tpc = tpc;
+    const size_t smem = (size_t)tpc * per;
+    auto kern = kf_generic_kernel<AT>;
+    static int attr_set[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin);
+        if (e != cudaSuccess) return (int)e;
+        attr_set[dev] = 1;
+    }
+    int nb = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (nb < 1) return (int)cudaErrorLaunchOutOfResources;
+    const long long ntiles = (P.howmany + tpc - 1) / tpc;
+    long long grid = (long long)di.sms * nb;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) return 0;
+    kern<<<(unsigned)grid, 256, smem, st>>>(G);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+// ---- C interface ------------------------------------------------------------------------------------------
+extern "C" int kfcu_exec(int mode, const kfcu_plan* plan, const void* d_in, void* d_out, long long howmany,
+                         long long in_dist, long long out_dist, long long in_stride, void* stream)
+{
+    if (!plan || !d_in || !d_out || mode < 0 || mode > 3 || howmany < 0) return KFCU_EINVAL;
+    if (howmany == 0) return 0;
+    if ((mode == kR2C || mode == kC2R) && !plan->d_stw && plan->nfft > 1) return KFCU_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    KParams<AT> P = make_params(plan, d_in, d_out, howmany, in_dist, out_dist, in_stride);
+    if (const FusedEntry* fe = find_fused(plan->nfft, mode)) return fe->fn[mode](P, st);
+    return launch_generic(mode, plan, P, st);
+}
+
+extern "C" int kfcu_transpose(const void* d_in, void* d_out, long long rows, long long cols, void* stream)
+{
+    if (!d_in || !d_out || rows < 0 || cols < 0) return KFCU_EINVAL;
+    if (rows == 0 || cols == 0) return 0;
+    const long long tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
+    long long grid = (long long)device_info().sms * 8;
+    if (grid > tiles) grid = tiles;
+    kf_transpose_kernel<CT><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const CT*)d_in, (CT*)d_out, rows, cols);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int kfcu_has_fused(int nfft, int mode)
+{
+    if (mode < 0 || mode > 3) return 0;
+    for (const FusedEntry& e : kFusedTable)
+        if (e.N == nfft && e.fn[mode]) return 1;
+    return 0;
+}
+
+extern "C" int kfcu_generic_max_nfft(void)
+{
+    const DeviceInfo di = device_info();
+    int smem = di.max_smem_optin > 0 ? di.max_smem_optin : 227 * 1024;
+    return (int)(smem / (2 * sizeof(CT)));
+}
+
+extern "C" long long kfcu_launch_count(void) { return g_launches.load(); }
+extern "C" void kfcu_force_generic(int on) { g_force_generic.store(on); }

@@ -1,0 +1,102 @@
+// kf_plan.h -- compile-time description of one batched Stockham plan.
+//
+// The radix schedule is the reference's (kf_factor, kiss_fft.c:306-328): stage 0 is the outermost /
+// last-executed radix, stage L-1 the innermost / first-executed one.  With
+//     F_s = p_0 * ... * p_{s-1}     (twiddle stride "fstride" of stage s, kiss_fft.c:235-300)
+//     m_s = N / (p_0 * ... * p_s)   (butterfly span of stage s)
+// the recursion of kf_work is equivalent to the breadth-first recurrence
+//     Y_s[off][k + r*m_s] = butterfly_{p_s}( Y_{s+1}[off + q*F_s][k] , twiddle tw[q*k*F_s] ),  q,r < p_s
+// with Y_L[off][0] = x[off] and X[k] = Y_0[0][k].  Every level is stored with the autosort address
+//     addr_s(off, k) = k*F_s + off
+// which is the natural input order at level L and the natural output order at level 0, so no digit
+// reversal pass exists anywhere.
+//
+// Consecutive stages are fused into "groups" (super-stages) that one thread executes entirely in registers:
+// group g covers stages s_hi(g) >= s >= s_lo(g), holds R(g) = prod p_s elements per work item and there are
+// N/R(g) work items per transform.  Groups exchange data through shared memory (level s_lo(g) array).
+#pragma once
+#include "kf_math.h"
+
+#if defined(__CUDACC__)
+#define KF_CE __host__ __device__ constexpr
+#else
+#define KF_CE constexpr
+#endif
+
+namespace kf {
+
+constexpr int kMaxStages = 16;
+constexpr int kMaxGroups = 8;
+
+struct PlanDesc {
+    int N;                  // transform length
+    int L;                  // number of radix stages
+    int p[kMaxStages];      // p[0] outermost ... p[L-1] innermost (reference order)
+    int G;                  // number of register groups; group 0 runs first and covers the innermost stages
+    int glen[kMaxGroups];   // stages per group, sum == L
+    int team;               // threads cooperating on one transform
+    int tpc;                // transforms per CTA
+    int logpad;             // shared-memory skew: phys(a) = a + (a >> logpad); >= 31 disables it
+    int minblocks;          // __launch_bounds__ min CTAs per SM
+
+    KF_CE int F(int s) const
+    {
+        int f = 1;
+        for (int j = 0; j < s; ++j) f *= p[j];
+        return f;
+    }
+    KF_CE int m(int s) const { return N / (F(s) * p[s]); }
+    KF_CE int s_hi(int g) const
+    {
+        int s = L - 1;
+        for (int j = 0; j < g; ++j) s -= glen[j];
+        return s;
+    }
+    KF_CE int s_lo(int g) const { return s_hi(g) - glen[g] + 1; }
+    KF_CE int R(int g) const
+    {
+        int r = 1;
+        for (int s = s_lo(g); s <= s_hi(g); ++s) r *= p[s];
+        return r;
+    }
+    KF_CE int Flo(int g) const { return F(s_lo(g)); }
+    KF_CE int mhi(int g) const { return m(s_hi(g)); }
+    KF_CE int items(int g) const { return N / R(g); }
+    KF_CE int iters(int g) const { return (items(g) + team - 1) / team; }
+    // weight of stage s's digit inside the register index of group g: W_{s_lo} = 1, W_{s+1} = W_s * p_s
+    KF_CE int W(int g, int s) const
+    {
+        int w = 1;
+        for (int j = s_lo(g); j < s; ++j) w *= p[j];
+        return w;
+    }
+    KF_CE int digit(int g, int s, int e) const { return (e / W(g, s)) % p[s]; }
+    // k offset contributed by the (already transformed) digits of stages above s inside group g
+    KF_CE int kabove(int g, int s, int e) const
+    {
+        int k = 0;
+        for (int j = s + 1; j <= s_hi(g); ++j) k += digit(g, j, e) * m(j);
+        return k;
+    }
+    // output position offset (in units of k) of register e after the whole group ran
+    KF_CE int kout(int g, int e) const
+    {
+        int k = 0;
+        for (int j = s_lo(g); j <= s_hi(g); ++j) k += digit(g, j, e) * m(j);
+        return k;
+    }
+    KF_CE int phys(int a) const { return logpad >= 31 ? a : a + (a >> logpad); }
+    // per-transform pitch of one exchange buffer (elements), made odd so that lanes which walk across
+    // transforms (strided-input mapping) fall into different banks
+    KF_CE int pitch() const { return phys(N - 1) + 1 + ((phys(N - 1) + 1) % 2 == 0 ? 1 : 0); }
+    KF_CE int threads() const { return team * tpc; }
+    KF_CE bool valid() const
+    {
+        int prod = 1, sum = 0;
+        for (int s = 0; s < L; ++s) prod *= p[s];
+        for (int g = 0; g < G; ++g) sum += glen[g];
+        return prod == N && sum == L && L <= kMaxStages && G <= kMaxGroups && team > 0 && tpc > 0;
+    }
+};
+
+}   // namespace kf

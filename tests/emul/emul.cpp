@@ -1,0 +1,124 @@
+// emul.cpp -- TEST-ONLY CPU emulator of the kernel bodies in kissfft_b200/csrc/kf_body.h.
+//
+// Purpose: exercise the index math of the kernels (autosort addressing, register-group digit bookkeeping,
+// exchange-buffer parity, tile tails, real pre/post passes) in the container that has no GPU.  Every CUDA
+// thread of a CTA becomes one std::thread and __syncthreads() becomes a std::barrier, so the very same
+// template code that nvcc compiles for sm_100a runs here.  This file is never part of the product library and
+// nothing in kissfft_b200/ calls it; GPU parity is established separately by the -m gpu tests.
+#include <barrier>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../include/kiss_fft.h"
+#define KF_SCALAR_BYTES ((int)sizeof(kiss_fft_scalar))
+#include "../../kissfft_b200/csrc/kf_body.h"
+#include "../../kissfft_b200/csrc/kf_plan_list.h"
+
+using namespace kf;
+typedef Arith<kiss_fft_scalar> AT;
+typedef AT::C CT;
+
+struct EmuEnv {
+    int tid_, nthreads_;
+    long long bid_, nblocks_;
+    unsigned char* smem_;
+    std::barrier<>* bar_;
+    int tid() const { return tid_; }
+    int nthreads() const { return nthreads_; }
+    long long bid() const { return bid_; }
+    long long nblocks() const { return nblocks_; }
+    void sync() const { bar_->arrive_and_wait(); }
+    unsigned char* smem() const { return smem_; }
+};
+
+static KParams<AT> mk_params(int nfft, int inverse, const void* in, void* out, long long howmany, long long in_dist,
+                             long long out_dist, long long in_stride, const void* tw, const void* stw)
+{
+    KParams<AT> P;
+    P.in = (const CT*)in;
+    P.out = (CT*)out;
+    P.howmany = howmany;
+    P.in_dist = in_dist;
+    P.out_dist = out_dist;
+    P.in_stride = in_stride;
+    P.tw = (const CT*)tw;
+    P.stw = (const CT*)stw;
+    const CT* h = (const CT*)tw;
+    CT z{};
+    P.pc.epi3 = AT::load((nfft % 3 == 0) ? h[nfft / 3] : z);
+    P.pc.ya = AT::load((nfft % 5 == 0) ? h[nfft / 5] : z);
+    P.pc.yb = AT::load((nfft % 5 == 0) ? h[2 * (nfft / 5)] : z);
+    P.inverse = inverse;
+    return P;
+}
+
+template <class F>
+static void run_cta_grid(int nthreads, long long nblocks, size_t smem_bytes, F&& body)
+{
+    for (long long b = 0; b < nblocks; ++b) {
+        std::vector<unsigned char> smem(smem_bytes + 64, 0xCD);
+        std::barrier<> bar(nthreads);
+        std::vector<std::thread> th;
+        th.reserve(nthreads);
+        for (int t = 0; t < nthreads; ++t)
+            th.emplace_back([&, t]() {
+                EmuEnv env{t, nthreads, b, nblocks, smem.data(), &bar};
+                body(env);
+            });
+        for (auto& x : th) x.join();
+    }
+}
+
+template <class PT, int MODE>
+static int run_fused(const KParams<AT>& P, long long nblocks)
+{
+    constexpr PlanDesc D = PT::D;
+    const size_t smem = (size_t)2 * D.tpc * D.pitch() * sizeof(CT);
+    run_cta_grid(D.threads(), nblocks, smem, [&](EmuEnv& env) { fused_body<AT, PT, MODE>(P, env); });
+    return 0;
+}
+
+typedef int (*fused_fn)(const KParams<AT>&, long long);
+struct Entry {
+    int N;
+    fused_fn fn[4];
+};
+#define KF_FUSED_ALL(PT) { PT::D.N, { run_fused<PT, kC2C>, run_fused<PT, kC2CCol>, run_fused<PT, kR2C>, run_fused<PT, kC2R> } }
+#define KF_FUSED_C2C(PT) { PT::D.N, { run_fused<PT, kC2C>, nullptr, nullptr, nullptr } }
+#define KF_FUSED_C2C_REAL(PT) { PT::D.N, { run_fused<PT, kC2C>, nullptr, run_fused<PT, kR2C>, run_fused<PT, kC2R> } }
+#define KF_ROW(tag, modes) KF_FUSED_##modes(tag),
+static const Entry kTable[] = { KF_PLAN_LIST(KF_ROW) };
+
+extern "C" int emul_num_plans(void) { return (int)(sizeof(kTable) / sizeof(kTable[0])); }
+extern "C" int emul_plan_nfft(int i) { return kTable[i].N; }
+extern "C" int emul_plan_has_mode(int i, int mode) { return kTable[i].fn[mode] != nullptr; }
+
+// returns 0, or -1 when no fused plan is registered for (nfft, mode)
+extern "C" int emul_fused(int nfft, int mode, int inverse, const void* in, void* out, long long howmany, long long in_dist,
+                          long long out_dist, long long in_stride, const void* tw, const void* stw, long long nblocks)
+{
+    for (const Entry& e : kTable)
+        if (e.N == nfft && e.fn[mode]) {
+            KParams<AT> P = mk_params(nfft, inverse, in, out, howmany, in_dist, out_dist, in_stride, tw, stw);
+            return e.fn[mode](P, nblocks);
+        }
+    return -1;
+}
+
+extern "C" int emul_generic(int nfft, int mode, int inverse, const int* factors, int nstages, const void* in, void* out,
+                            long long howmany, long long in_dist, long long out_dist, long long in_stride, const void* tw,
+                            const void* stw, int tpc, int nthreads, long long nblocks)
+{
+    GParams<AT> G;
+    G.k = mk_params(nfft, inverse, in, out, howmany, in_dist, out_dist, in_stride, tw, stw);
+    G.plan.N = nfft;
+    G.plan.L = nstages;
+    for (int s = 0; s < nstages; ++s) { G.plan.p[s] = factors[2 * s]; G.plan.m[s] = factors[2 * s + 1]; }
+    G.mode = mode;
+    G.tpc = tpc;
+    const size_t smem = (size_t)2 * tpc * nfft * sizeof(CT);
+    run_cta_grid(nthreads, nblocks, smem, [&](EmuEnv& env) { generic_body<AT>(G, env); });
+    return 0;
+}

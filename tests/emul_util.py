@@ -1,0 +1,59 @@
+"""ctypes wrapper of tests/emul (CPU emulator of the kernel bodies; test-only, see emul.cpp)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMUL = os.path.join(HERE, "emul")
+FLAGS = {"float": "-Dkiss_fft_scalar=float", "double": "-Dkiss_fft_scalar=double", "int16_t": "-DFIXED_POINT=16",
+         "int32_t": "-DFIXED_POINT=32"}
+C2C, C2C_COL, R2C, C2R = range(4)
+
+
+def _stale(lib):
+    if not os.path.exists(lib):
+        return True
+    t = os.path.getmtime(lib)
+    csrc = os.path.join(HERE, "..", "kissfft_b200", "csrc")
+    deps = [os.path.join(EMUL, "emul.cpp")] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(tname):
+    lib = os.path.join(EMUL, "_build", "libemul-%s.so" % tname)
+    if _stale(lib):
+        os.makedirs(os.path.dirname(lib), exist_ok=True)
+        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.run([gxx, "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", FLAGS[tname],
+                        os.path.join(EMUL, "emul.cpp"), "-o", lib], check=True)
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class Emulator:
+    def __init__(self, tname):
+        self.lib = ctypes.CDLL(build(tname))
+        vp, ci, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
+        self.lib.emul_fused.argtypes = [ci, ci, ci, vp, vp, ll, ll, ll, ll, vp, vp, ll]
+        self.lib.emul_generic.argtypes = [ci, ci, ci, vp, ci, vp, vp, ll, ll, ll, ll, vp, vp, ci, ci, ll]
+
+    def plans(self):
+        return [(self.lib.emul_plan_nfft(i), [m for m in range(4) if self.lib.emul_plan_has_mode(i, m)])
+                for i in range(self.lib.emul_num_plans())]
+
+    def fused(self, nfft, mode, inverse, inp, out, howmany, in_dist, out_dist, in_stride, tw, stw=None, nblocks=2):
+        rc = self.lib.emul_fused(nfft, mode, int(inverse), _p(inp), _p(out), howmany, in_dist, out_dist, in_stride,
+                                 _p(tw), _p(stw), nblocks)
+        assert rc == 0, "no fused plan for nfft=%d mode=%d" % (nfft, mode)
+
+    def generic(self, nfft, mode, inverse, factors, inp, out, howmany, in_dist, out_dist, in_stride, tw, stw=None,
+                tpc=2, nthreads=32, nblocks=2):
+        fac = np.array([x for pm in factors for x in pm], np.int32)
+        rc = self.lib.emul_generic(nfft, mode, int(inverse), _p(fac), len(factors), _p(inp), _p(out), howmany, in_dist,
+                                   out_dist, in_stride, _p(tw), _p(stw), tpc, nthreads, nblocks)
+        assert rc == 0

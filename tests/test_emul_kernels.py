@@ -1,0 +1,105 @@
+"""Index-math tests of the kernel bodies WITHOUT a GPU: the template code of kissfft_b200/csrc/kf_body.h is
+executed by tests/emul (one std::thread per CUDA thread) and compared with the oracle.  This proves the
+addressing / plan logic, not the GPU build -- the -m gpu tests compare the real kernels with the oracle."""
+import numpy as np
+import pytest
+
+from oracle.loader import TYPES, Oracle, random_input, rel_rms
+from tests.emul_util import C2C, C2C_COL, C2R, R2C, Emulator
+
+TOL = {"float": 1e-6, "double": 1e-14}
+
+
+def check(tname, got, want, nfft):
+    if tname in TOL:
+        assert rel_rms(got, want) <= TOL[tname] * max(1.0, np.log2(nfft))
+    else:
+        assert np.array_equal(got, want)
+
+
+@pytest.fixture(scope="module", params=TYPES)
+def env(request):
+    return request.param, Oracle(request.param), Emulator(request.param)
+
+
+def test_fused_c2c(env):
+    tname, o, em = env
+    for nfft, modes in em.plans():
+        if C2C not in modes:
+            continue
+        for inverse in (0, 1):
+            howmany = 11
+            x = random_input(tname, (howmany, nfft), 100 + nfft)
+            out = np.zeros_like(x)
+            em.fused(nfft, C2C, inverse, x, out, howmany, nfft, nfft, 1, o.twiddles(nfft, inverse))
+            check(tname, out, o.fft(x, inverse), nfft)
+
+
+def test_fused_c2c_strided_input(env):
+    tname, o, em = env
+    nfft, howmany, stride = 64, 5, 3
+    x = random_input(tname, (howmany, nfft * stride), 7)
+    out = np.zeros((howmany, nfft, 2), x.dtype)
+    em.fused(nfft, C2C, 0, x, out, howmany, nfft * stride, nfft, stride, o.twiddles(nfft, 0))
+    check(tname, out, o.fft(x, 0, in_stride=stride, nfft=nfft), nfft)
+
+
+def test_fused_columns(env):
+    tname, o, em = env
+    for nfft, modes in em.plans():
+        if C2C_COL not in modes or nfft > 1024:
+            continue
+        ncols = 37
+        x = random_input(tname, (nfft, ncols), 200 + nfft)           # [nfft][ncols]: column i strided by ncols
+        out = np.zeros((ncols, nfft, 2), x.dtype)
+        em.fused(nfft, C2C_COL, 0, x, out, ncols, 1, nfft, ncols, o.twiddles(nfft, 0))
+        want = o.fft(np.ascontiguousarray(x.transpose(1, 0, 2)), 0)
+        check(tname, out, want, nfft)
+
+
+def test_fused_real(env):
+    tname, o, em = env
+    for nc, modes in em.plans():
+        if R2C not in modes:
+            continue
+        nfft, howmany = 2 * nc, 9
+        x = random_input(tname, (howmany, nfft), 300 + nc, complex_=False)
+        X = np.zeros((howmany, nc + 1, 2), x.dtype)
+        em.fused(nc, R2C, 0, x, X, howmany, nc, nc + 1, 1, o.twiddles(nc, 0), o.super_twiddles(nc, 0))
+        want = o.fftr(x)
+        check(tname, X, want, nfft)
+        spec = want if tname in TOL else random_input(tname, (howmany, nc + 1), 301 + nc)
+        y = np.zeros((howmany, nfft), x.dtype)
+        em.fused(nc, C2R, 1, spec, y, howmany, nc + 1, nc, 1, o.twiddles(nc, 1), o.super_twiddles(nc, 1))
+        check(tname, y, o.fftri(spec), nfft)
+
+
+@pytest.mark.parametrize("nfft", [1, 2, 3, 5, 7, 12, 30, 74, 120, 143, 360])
+def test_generic_c2c(env, nfft):
+    tname, o, em = env
+    for inverse in (0, 1):
+        howmany = 5
+        x = random_input(tname, (howmany, nfft), 400 + nfft)
+        out = np.zeros_like(x)
+        em.generic(nfft, C2C, inverse, o.factor(nfft), x, out, howmany, nfft, nfft, 1, o.twiddles(nfft, inverse))
+        check(tname, out, o.fft(x, inverse), nfft)
+
+
+def test_generic_columns_and_real(env):
+    tname, o, em = env
+    nfft, ncols = 30, 7
+    x = random_input(tname, (nfft, ncols), 9)
+    out = np.zeros((ncols, nfft, 2), x.dtype)
+    em.generic(nfft, C2C_COL, 0, o.factor(nfft), x, out, ncols, 1, nfft, ncols, o.twiddles(nfft, 0), tpc=3)
+    check(tname, out, o.fft(np.ascontiguousarray(x.transpose(1, 0, 2)), 0), nfft)
+    for n in (2, 4, 6, 30, 120):
+        nc, howmany = n // 2, 5
+        xr = random_input(tname, (howmany, n), 500 + n, complex_=False)
+        X = np.zeros((howmany, nc + 1, 2), xr.dtype)
+        em.generic(nc, R2C, 0, o.factor(nc), xr, X, howmany, nc, nc + 1, 1, o.twiddles(nc, 0), o.super_twiddles(nc, 0))
+        want = o.fftr(xr)
+        check(tname, X, want, n)
+        spec = want if tname in TOL else random_input(tname, (howmany, nc + 1), 501 + n)
+        y = np.zeros((howmany, n), xr.dtype)
+        em.generic(nc, C2R, 1, o.factor(nc), spec, y, howmany, nc + 1, nc, 1, o.twiddles(nc, 1), o.super_twiddles(nc, 1))
+        check(tname, y, o.fftri(spec), n)

@@ -1,0 +1,412 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI of libkissfft-<type>.so, against the oracle
+(oracle/kiss_oracle.c, itself pinned bit-for-bit to the compiled reference by tests/test_oracle_pin.py).
+
+Bars (BASELINE.json north_star): Q15/Q31 bit-exact; float relative RMS <= 1e-6*log2(N); double <= 1e-14*log2(N).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle.loader import TYPES, Oracle, Reference, have_reference, random_input, rel_rms
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+TOL = {"float": 1e-6, "double": 1e-14}
+
+
+def check(tname, got, want, n, what=""):
+    if tname in TOL:
+        err = rel_rms(got, want)
+        assert err <= TOL[tname] * max(1.0, np.log2(max(n, 2))), "%s %s n=%d rel-rms %.3g" % (tname, what, n, err)
+    else:
+        got = np.asarray(got)
+        want = np.asarray(want)
+        nbad = int(np.count_nonzero(got != want))
+        assert nbad == 0, "%s %s n=%d: %d of %d scalars differ" % (tname, what, n, nbad, got.size)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+@pytest.fixture(scope="module", params=TYPES)
+def ctx(request):
+    import kissfft_b200
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    lib = kissfft_b200.get(request.param)
+    yield request.param, lib, Oracle(request.param)
+    lib.force_generic(False)
+
+
+C2C_SIZES = [1, 2, 3, 4, 5, 7, 8, 16, 30, 64, 74, 120, 143, 148, 256, 360, 1000, 1009, 1024, 1155, 1800, 2048, 4096]
+
+
+@pytest.mark.parametrize("nfft", C2C_SIZES)
+def test_c2c_batch(ctx, nfft):
+    tname, lib, o = ctx
+    howmany = 37
+    for inverse in (False, True):
+        x = random_input(tname, (howmany, nfft), 1000 + nfft)
+        d_in, d_out = dev(x), dev(np.zeros_like(x))
+        cfg = lib.alloc(nfft, inverse)
+        lib.fft_batch_dev(cfg, d_in, d_out, howmany, nfft, nfft)
+        torch.cuda.synchronize()
+        check(tname, host(d_out), o.fft(x, inverse), nfft, "c2c inv=%d" % inverse)
+        assert np.array_equal(host(d_in), x), "input must not be modified"
+        # in place
+        lib.fft_batch_dev(cfg, d_in, d_in, howmany, nfft, nfft)
+        torch.cuda.synchronize()
+        check(tname, host(d_in), o.fft(x, inverse), nfft, "c2c in-place inv=%d" % inverse)
+        lib.free(cfg)
+
+
+@pytest.mark.parametrize("nfft", [16, 64, 256, 1000, 1024, 1155, 2048])
+def test_generic_kernel_matches_on_fused_sizes(ctx, nfft):
+    """the run-time kernel must give the same answer as the compile-time plans (bit-exact in fixed point)"""
+    tname, lib, o = ctx
+    howmany = 9
+    x = random_input(tname, (howmany, nfft), 77 + nfft)
+    cfg = lib.alloc(nfft, False)
+    d_in, d_out = dev(x), dev(np.zeros_like(x))
+    assert lib.plan_kind(nfft) == 1
+    lib.force_generic(True)
+    try:
+        lib.fft_batch_dev(cfg, d_in, d_out, howmany, nfft, nfft)
+        torch.cuda.synchronize()
+    finally:
+        lib.force_generic(False)
+    check(tname, host(d_out), o.fft(x, False), nfft, "generic")
+    lib.free(cfg)
+
+
+def test_c2c_strided_input_and_distances(ctx):
+    tname, lib, o = ctx
+    for nfft, stride in ((64, 3), (1024, 2), (30, 5), (1000, 2)):
+        howmany = 6
+        x = random_input(tname, (howmany, nfft * stride + 4), 5 + nfft)
+        d_in = dev(x)
+        d_out = dev(np.zeros((howmany, nfft + 3, 2), x.dtype))
+        cfg = lib.alloc(nfft)
+        lib.fft_batch_dev(cfg, d_in, d_out, howmany, nfft * stride + 4, nfft + 3, stride)
+        torch.cuda.synchronize()
+        want = o.fft(x[:, : nfft * stride], False, in_stride=stride, nfft=nfft)
+        got = host(d_out)
+        check(tname, got[:, :nfft], want, nfft, "stride")
+        assert not got[:, nfft:].any(), "padding between output rows must stay untouched"
+        lib.free(cfg)
+
+
+REAL_SIZES = [2, 4, 6, 30, 120, 128, 512, 1000, 2000, 2048, 2310, 4096]
+
+
+@pytest.mark.parametrize("nfft", REAL_SIZES)
+def test_real_batch(ctx, nfft):
+    tname, lib, o = ctx
+    howmany = 19
+    x = random_input(tname, (howmany, nfft), 2000 + nfft, complex_=False)
+    nb = nfft // 2 + 1
+    d_x, d_X = dev(x), dev(np.zeros((howmany, nb, 2), x.dtype))
+    cfg = lib.allocr(nfft, False)
+    lib.fftr_batch_dev(cfg, d_x, d_X, howmany, nfft, nb)
+    torch.cuda.synchronize()
+    want = o.fftr(x)
+    check(tname, host(d_X), want, nfft, "fftr")
+    lib.free(cfg)
+    spec = want if tname in TOL else random_input(tname, (howmany, nb), 2001 + nfft)
+    d_S, d_y = dev(spec), dev(np.zeros((howmany, nfft), x.dtype))
+    cfgi = lib.allocr(nfft, True)
+    lib.fftri_batch_dev(cfgi, d_S, d_y, howmany, nb, nfft)
+    torch.cuda.synchronize()
+    check(tname, host(d_y), o.fftri(spec), nfft, "fftri")
+    lib.free(cfgi)
+
+
+ND_DIMS = [(8,), (4, 3), (2, 3, 4), (30, 20, 12), (64, 64), (16, 16, 16), (256, 64), (5, 6, 7, 4), (64, 128, 32)]
+
+
+@pytest.mark.parametrize("dims", ND_DIMS)
+def test_fftnd(ctx, dims):
+    tname, lib, o = ctx
+    n = int(np.prod(dims))
+    for inverse in (False, True):
+        x = random_input(tname, dims, 31 + n)
+        want = o.fftnd(x, inverse)
+        cfg = lib.allocnd(dims, inverse)
+        d_in, d_out = dev(x), dev(np.zeros_like(x))
+        lib.fftnd_dev(cfg, d_in, d_out)
+        torch.cuda.synchronize()
+        check(tname, host(d_out), want, n, "fftnd %s" % (dims,))
+        assert np.array_equal(host(d_in), x)
+        d_work = dev(np.zeros_like(x))
+        lib.fftnd_dev(cfg, d_in, d_in, d_work)     # in place, caller-provided scratch
+        torch.cuda.synchronize()
+        check(tname, host(d_in), want, n, "fftnd in-place %s" % (dims,))
+        lib.free(cfg)
+
+
+@pytest.mark.parametrize("dims", [(4, 6), (2, 3, 4), (30, 20, 12), (16, 16, 64), (5, 6, 8), (3, 4, 5, 6)])
+def test_fftndr(ctx, dims):
+    tname, lib, o = ctx
+    n = int(np.prod(dims))
+    x = random_input(tname, dims, 41 + n, complex_=False)
+    want = o.fftndr(x)
+    cfg = lib.allocndr(dims, False)
+    d_x, d_X = dev(x), dev(np.zeros(want.shape, x.dtype))
+    lib.fftndr_dev(cfg, d_x, d_X)
+    torch.cuda.synchronize()
+    check(tname, host(d_X), want, n, "fftndr %s" % (dims,))
+    lib.free(cfg)
+    spec = want if tname in TOL else random_input(tname, want.shape[:-1], 43 + n)
+    cfgi = lib.allocndr(dims, True)
+    d_S, d_y = dev(spec), dev(np.zeros(dims, x.dtype))
+    lib.fftndri_dev(cfgi, d_S, d_y)
+    torch.cuda.synchronize()
+    check(tname, host(d_y), o.fftndri(spec), n, "fftndri %s" % (dims,))
+    lib.free(cfgi)
+
+
+def test_reference_api_with_host_pointers(ctx):
+    """the unmodified reference call sequence (kiss_fft_alloc / kiss_fft / free) on ordinary host memory"""
+    tname, lib, o = ctx
+    nfft = 120
+    x = random_input(tname, (nfft,), 3)
+    out = np.zeros_like(x)
+    cfg = lib.alloc(nfft)
+    lib.fft(cfg, x, out)
+    check(tname, out, o.fft(x), nfft, "kiss_fft host")
+    y = x.copy()
+    lib.fft(cfg, y, y)                                    # fin == fout (kiss_fft.c:377-395)
+    check(tname, y, o.fft(x), nfft, "kiss_fft host in-place")
+    lib.free(cfg)
+    xs = random_input(tname, (21 * 5,), 4)
+    cfg = lib.alloc(21)
+    out = np.zeros((21, 2), xs.dtype)
+    lib.fft_stride(cfg, xs, out, 5)
+    check(tname, out, o.fft(xs, False, in_stride=5, nfft=21), 21, "kiss_fft_stride host")
+    lib.free(cfg)
+    # real
+    n = 240
+    xr = random_input(tname, (n,), 5, complex_=False)
+    X = np.zeros((n // 2 + 1, 2), xr.dtype)
+    cfg = lib.allocr(n, False)
+    lib.fftr(cfg, xr, X)
+    check(tname, X, o.fftr(xr), n, "kiss_fftr host")
+    before = xr.copy()
+    lib.fftri(cfg, X, xr)                                 # wrong direction: logged no-op (kiss_fftr.c:124-127)
+    assert np.array_equal(before, xr)
+    lib.free(cfg)
+    spec = o.fftr(xr) if tname in TOL else random_input(tname, (n // 2 + 1,), 6)
+    cfgi = lib.allocr(n, True)
+    y = np.zeros(n, xr.dtype)
+    lib.fftri(cfgi, spec, y)
+    check(tname, y, o.fftri(spec), n, "kiss_fftri host")
+    lib.free(cfgi)
+    # N-D, also in place as tools/fftutil.c:51 uses it
+    dims = (6, 10, 4)
+    xn = random_input(tname, dims, 8)
+    cfg = lib.allocnd(dims)
+    out = np.zeros_like(xn)
+    lib.fftnd(cfg, xn, out)
+    check(tname, out, o.fftnd(xn), 240, "kiss_fftnd host")
+    yn = xn.copy()
+    lib.fftnd(cfg, yn, yn)
+    check(tname, yn, o.fftnd(xn), 240, "kiss_fftnd host in-place")
+    lib.free(cfg)
+    dims = (6, 10, 8)
+    xr = random_input(tname, dims, 9, complex_=False)
+    cfg = lib.allocndr(dims, False)
+    want = o.fftndr(xr)
+    X = np.zeros(want.shape, xr.dtype)
+    lib.fftndr(cfg, xr, X)
+    check(tname, X, want, 480, "kiss_fftndr host")
+    lib.free(cfg)
+    spec = want if tname in TOL else random_input(tname, want.shape[:-1], 10)
+    cfgi = lib.allocndr(dims, True)
+    y = np.zeros(dims, xr.dtype)
+    lib.fftndri(cfgi, spec, y)
+    check(tname, y, o.fftndri(spec), 480, "kiss_fftndri host")
+    lib.free(cfgi)
+
+
+def test_host_batch_pipeline(ctx):
+    tname, lib, o = ctx
+    nfft, howmany = 1024, 300
+    x = random_input(tname, (howmany, nfft), 12)
+    out = np.zeros_like(x)
+    cfg = lib.alloc(nfft)
+    lib.fft_batch(cfg, x, out, howmany)
+    check(tname, out, o.fft(x), nfft, "kiss_fft_batch host")
+    lib.free(cfg)
+    n = 4096
+    xr = random_input(tname, (howmany, n), 13, complex_=False)
+    X = np.zeros((howmany, n // 2 + 1, 2), xr.dtype)
+    cfg = lib.allocr(n, False)
+    lib.fftr_batch(cfg, xr, X, howmany)
+    want = o.fftr(xr)
+    check(tname, X, want, n, "kiss_fftr_batch host")
+    lib.free(cfg)
+    spec = want if tname in TOL else random_input(tname, (howmany, n // 2 + 1), 14)
+    y = np.zeros((howmany, n), xr.dtype)
+    cfgi = lib.allocr(n, True)
+    lib.fftri_batch(cfgi, spec, y, howmany)
+    check(tname, y, o.fftri(spec), n, "kiss_fftri_batch host")
+    lib.free(cfgi)
+
+
+def test_structured_inputs(ctx):
+    """impulse, constant and two-tone rows (reference test/twotonetest.c:38-47)"""
+    tname, lib, o = ctx
+    nfft = 1024
+    amp = 1.0 if tname in TOL else (16383 if tname == "int16_t" else 1073741823)
+    rows = np.zeros((4, nfft, 2), np.float64)
+    rows[0, 0, 0] = amp
+    rows[1, :, 0] = amp
+    t = np.arange(nfft)
+    rows[2, :, 0] = amp * 0.5 * (np.cos(2 * np.pi * 17 * t / nfft) + np.cos(2 * np.pi * 200 * t / nfft))
+    rows[3, 5, 1] = -amp
+    x = rows.astype(o.dtype)
+    cfg = lib.alloc(nfft)
+    d_in, d_out = dev(x), dev(np.zeros_like(x))
+    lib.fft_batch_dev(cfg, d_in, d_out, 4, nfft, nfft)
+    torch.cuda.synchronize()
+    check(tname, host(d_out), o.fft(x), nfft, "structured")
+    lib.free(cfg)
+
+
+def test_error_paths(ctx):
+    tname, lib, o = ctx
+    import kissfft_b200
+    assert lib.lib.kiss_fftr_alloc(31, 0, None, None) is None          # odd real length (kiss_fftr.c:29-32)
+    need = ctypes.c_size_t(0)
+    assert lib.lib.kiss_fft_alloc(64, 0, None, ctypes.byref(need)) is None and need.value > 0   # size query
+    small = ctypes.c_size_t(8)
+    buf = ctypes.create_string_buffer(need.value)
+    assert lib.lib.kiss_fft_alloc(64, 0, buf, ctypes.byref(small)) is None and small.value == need.value
+    ok = ctypes.c_size_t(need.value)
+    cfg = lib.lib.kiss_fft_alloc(64, 0, buf, ctypes.byref(ok))
+    assert cfg == ctypes.addressof(buf)
+    x = random_input(tname, (2, 64), 1)
+    d_in, d_out = dev(x), dev(np.zeros_like(x))
+    lib.fft_batch_dev(cfg, d_in, d_out, 2, 64, 64)                      # a cfg placed in caller memory works
+    torch.cuda.synchronize()
+    check(tname, host(d_out), o.fft(x), 64, "placed cfg")
+    cfgr = lib.allocr(64, True)
+    with pytest.raises(kissfft_b200.KissFFTError):
+        lib.fftr_batch_dev(cfgr, d_in, d_out, 1, 64, 33)               # forward call with an inverse cfg
+    lib.free(cfgr)
+
+
+# ---- BASELINE.json configurations at full size ----------------------------------------------------------------
+
+def _full_batch_check(tname, lib, o, nfft, howmany, seed, sample=1024):
+    """full batch on the GPU; oracle on an evenly spaced sample of rows + whole-batch size-independent properties"""
+    x = random_input(tname, (howmany, nfft), seed)
+    d_in = dev(x)
+    d_out = torch.zeros_like(d_in)
+    cfg = lib.alloc(nfft)
+    lib.fft_batch_dev(cfg, d_in, d_out, howmany, nfft, nfft)
+    torch.cuda.synchronize()
+    got = host(d_out)
+    idx = np.unique(np.concatenate([np.linspace(0, howmany - 1, sample).astype(np.int64), np.arange(howmany - 8, howmany)]))
+    check(tname, got[idx], o.fft(x[idx]), nfft, "full-size sample")
+    if have_reference(tname):
+        # the compiled reference itself over the WHOLE batch, all host cores
+        ref = Reference(tname).fft(x, nthreads=0 or __import__("os").cpu_count())
+        check(tname, got, ref, nfft, "full batch vs compiled reference")
+    if tname in TOL:
+        # Parseval over the whole batch: sum |X|^2 == N * sum |x|^2
+        ex = np.sum(x.astype(np.float64) ** 2, axis=(1, 2))
+        eX = np.sum(got.astype(np.float64) ** 2, axis=(1, 2))
+        assert np.allclose(eX, nfft * ex, rtol=1e-4 if tname == "float" else 1e-10)
+        # forward o inverse == N * x  (reference README: unscaled in both directions)
+        cfgi = lib.alloc(nfft, True)
+        d_back = torch.zeros_like(d_in)
+        lib.fft_batch_dev(cfgi, d_out, d_back, howmany, nfft, nfft)
+        torch.cuda.synchronize()
+        assert rel_rms(host(d_back) / nfft, x) <= 2 * TOL[tname] * np.log2(nfft)
+        lib.free(cfgi)
+    else:
+        # DC bin == sround-chain of the row sum: cheap whole-batch property -- every row's output must be
+        # identical when the same row is transformed alone (batch independence)
+        pick = np.array([0, howmany // 3, howmany - 1])
+        d_one = dev(x[pick])
+        d_res = torch.zeros_like(d_one)
+        lib.fft_batch_dev(cfg, d_one, d_res, len(pick), nfft, nfft)
+        torch.cuda.synchronize()
+        assert np.array_equal(host(d_res), got[pick])
+    lib.free(cfg)
+
+
+def test_config1_c2c_1024_x_65536():
+    import kissfft_b200
+    _full_batch_check("float", kissfft_b200.get("float"), Oracle("float"), 1024, 65536, 11)
+
+
+@pytest.mark.parametrize("tname", ["float", "double"])
+@pytest.mark.parametrize("nfft", [1000, 1155])
+def test_config3_mixed_radix_x_100000(tname, nfft):
+    import kissfft_b200
+    _full_batch_check(tname, kissfft_b200.get(tname), Oracle(tname), nfft, 100000, 12, sample=512)
+
+
+@pytest.mark.parametrize("tname", ["int16_t", "int32_t"])
+def test_config4_fixed_2048_x_65536(tname):
+    import kissfft_b200
+    _full_batch_check(tname, kissfft_b200.get(tname), Oracle(tname), 2048, 65536, 13, sample=512)
+
+
+def test_config2_real_4096_x_32768():
+    import kissfft_b200
+    tname, nfft, howmany = "float", 4096, 32768
+    lib, o = kissfft_b200.get(tname), Oracle(tname)
+    x = random_input(tname, (howmany, nfft), 14, complex_=False)
+    nb = nfft // 2 + 1
+    d_x = dev(x)
+    d_X = torch.zeros((howmany, nb, 2), dtype=d_x.dtype, device="cuda")
+    cfg = lib.allocr(nfft, False)
+    lib.fftr_batch_dev(cfg, d_x, d_X, howmany, nfft, nb)
+    torch.cuda.synchronize()
+    got = host(d_X)
+    idx = np.linspace(0, howmany - 1, 512).astype(np.int64)
+    check(tname, got[idx], o.fftr(x[idx]), nfft, "r2c sample")
+    if have_reference(tname):
+        check(tname, got, Reference(tname).fftr(x, nthreads=__import__("os").cpu_count()), nfft, "r2c full vs reference")
+    # C2R(R2C(x)) == nfft * x over the whole batch
+    cfgi = lib.allocr(nfft, True)
+    d_y = torch.zeros_like(d_x)
+    lib.fftri_batch_dev(cfgi, d_X, d_y, howmany, nb, nfft)
+    torch.cuda.synchronize()
+    assert rel_rms(host(d_y) / nfft, x) <= 2e-6 * np.log2(nfft)
+    check(tname, host(d_y)[idx], o.fftri(got[idx]), nfft, "c2r sample")
+    lib.free(cfg)
+    lib.free(cfgi)
+
+
+def test_config5_3d_single_gpu_256():
+    """kiss_fftnd 3-D at 256^3 against the oracle (1024^3 is exercised by bench.py / the multi-GPU tests)"""
+    import kissfft_b200
+    tname = "float"
+    lib, o = kissfft_b200.get(tname), Oracle(tname)
+    dims = (256, 256, 256)
+    x = random_input(tname, dims, 15)
+    d_in = dev(x)
+    d_out = torch.zeros_like(d_in)
+    d_work = torch.zeros_like(d_in)
+    cfg = lib.allocnd(dims)
+    lib.fftnd_dev(cfg, d_in, d_out, d_work)
+    torch.cuda.synchronize()
+    got = host(d_out)
+    want = np.fft.fftn(x[..., 0].astype(np.float64) + 1j * x[..., 1].astype(np.float64))
+    assert rel_rms(got, np.stack([want.real, want.imag], -1)) <= 1e-6 * 24
+    if have_reference(tname):
+        check(tname, got, Reference(tname).fftnd(x), 256 ** 3, "3-D vs compiled reference")
+    else:
+        check(tname, got, o.fftnd(x), 256 ** 3, "3-D vs oracle")
+    lib.free(cfg)
