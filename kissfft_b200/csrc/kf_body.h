@@ -57,11 +57,15 @@ KF_HD C ld_stream(const C* p)
 #endif
 }
 
-template <class A>
+template <class A, bool UNIT>
 struct SrcGlobal {
     const typename A::C* base;
-    long long stride;
-    KF_HD cx<typename A::R> load(int i) const { return A::load(ld_stream(base + (long long)i * stride)); }
+    long long stride;   // ignored when UNIT (contiguous rows: element offsets fold into the load immediates)
+    KF_HD cx<typename A::R> load(int i) const
+    {
+        if constexpr (UNIT) return A::load(ld_stream(base + i));
+        else return A::load(ld_stream(base + (long long)i * stride));
+    }
 };
 template <class A>
 struct SrcShared {
@@ -126,7 +130,7 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
         C* b1 = (par ? bufA : bufB) + team * kPitch;
 
         if constexpr (MODE == kC2C) {
-            SrcGlobal<A> src{P.in + b * P.in_dist, P.in_stride};
+            SrcGlobal<A, true> src{P.in + b * P.in_dist, 1};   // in_stride == 1 (other strides: generic kernel)
             DstGlobal<A> dst{P.out + b * P.out_dist};
             // group 0 writes b1... sequence: g0 -> W(b1); g1: R(b1) W(b0); g2: R(b0) W(b1) ...
             run_groups<A, D, 0>(env, t, active, src, dst, b0, b1, tw, P.pc, P.inverse);
@@ -136,16 +140,16 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             static_assert(D.G >= 2, "column mode needs a shared-memory exchange");
             const int cteam = tid % D.tpc, ct = tid / D.tpc;
             const long long cb = tile * D.tpc + cteam;
-            SrcGlobal<A> src{P.in + cb * P.in_dist, P.in_stride};
+            SrcGlobal<A, false> src{P.in + cb * P.in_dist, P.in_stride};
             DstGlobal<A> dst{P.out + b * P.out_dist};
             C* cb1 = (par ? bufA : bufB) + cteam * kPitch;
-            run_group<A, D, 0, SrcGlobal<A>, DstGlobal<A>>(ct, cb < P.howmany, src, dst, nullptr, cb1, tw, P.pc, P.inverse);
+            run_group<A, D, 0, SrcGlobal<A, false>, DstGlobal<A>>(ct, cb < P.howmany, src, dst, nullptr, cb1, tw, P.pc, P.inverse);
             env.sync();
             run_groups<A, D, 1>(env, t, active, src, dst, b1, b0, tw, P.pc, P.inverse);
             par ^= (D.G - 1) & 1;
         } else if constexpr (MODE == kR2C) {
             // packed complex transform, last group leaves T[] in natural order in shared memory
-            SrcGlobal<A> src{P.in + b * P.in_dist, 1};
+            SrcGlobal<A, true> src{P.in + b * P.in_dist, 1};
             // buffer written by the last group: after G-1 exchanges the "next write" buffer
             C* tb = (((D.G - 1) & 1) ? b0 : b1);
             DstShared<A> dst{tb};
@@ -286,7 +290,7 @@ KF_HD void generic_body(const GParams<A>& G, Env& env)
                     X v[5];
                     for (int q = 0; q < p; ++q) v[q] = A::load(r[(k * p + q) * F + off]);
                     if (p == 2) bfly2<A, false>(v, tw.get(F * k));
-                    else if (p == 4) bfly4<A, false>(v, tw.get(F * k), tw.get(2 * F * k), tw.get(3 * F * k), P.inverse);
+                    else if (p == 4) bfly4<A, false>(v, tw.get(F * k), tw.get(2 * F * k), tw.get(3 * F * k), A::sign_of(P.inverse));
                     else if (p == 3) bfly3<A, false>(v, tw.get(F * k), tw.get(2 * F * k), P.pc.epi3.i);
                     else bfly5<A, false>(v, tw.get(F * k), tw.get(2 * F * k), tw.get(3 * F * k), tw.get(4 * F * k), P.pc.ya, P.pc.yb);
                     for (int q = 0; q < p; ++q) w[(k + q * m) * F + off] = A::store(v[q]);

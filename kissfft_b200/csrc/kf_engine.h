@@ -148,7 +148,7 @@ KF_HD void bfly_generic_float(cx<typename A::R>* v, int ks, const TwTab<A>& tw)
 // one radix stage s of group g applied to the R(g) registers of a work item whose k' is `kp`
 // ---------------------------------------------------------------------------------------------------------
 template <class A, PlanDesc D, int g, int s>
-KF_HD void run_stage(cx<typename A::R>* v, int kp, const TwTab<A>& tw, const PlanConsts<A>& pc, int inverse)
+KF_HD void run_stage(cx<typename A::R>* v, int kp, const TwTab<A>& tw, const PlanConsts<A>& pc, typename A::R sg)
 {
     typedef cx<typename A::R> X;
     constexpr int p = D.p[s], Ws = D.W(g, s), Fs = D.F(s), ms = D.m(s), R = D.R(g);
@@ -166,7 +166,7 @@ KF_HD void run_stage(cx<typename A::R>* v, int kp, const TwTab<A>& tw, const Pla
                 bfly2<A, kTw1>(x, kTw1 ? X{} : tw.get(Fs * ks));
             } else if constexpr (p == 4) {
                 bfly4<A, kTw1>(x, kTw1 ? X{} : tw.get(Fs * ks), kTw1 ? X{} : tw.get(2 * Fs * ks),
-                               kTw1 ? X{} : tw.get(3 * Fs * ks), inverse);
+                               kTw1 ? X{} : tw.get(3 * Fs * ks), sg);
             } else if constexpr (p == 3) {
                 bfly3<A, kTw1>(x, kTw1 ? X{} : tw.get(Fs * ks), kTw1 ? X{} : tw.get(2 * Fs * ks), pc.epi3.i);
             } else if constexpr (p == 5) {
@@ -183,10 +183,10 @@ KF_HD void run_stage(cx<typename A::R>* v, int kp, const TwTab<A>& tw, const Pla
 }
 
 template <class A, PlanDesc D, int g, int s>
-KF_HD void run_stages_from(cx<typename A::R>* v, int kp, const TwTab<A>& tw, const PlanConsts<A>& pc, int inverse)
+KF_HD void run_stages_from(cx<typename A::R>* v, int kp, const TwTab<A>& tw, const PlanConsts<A>& pc, typename A::R sg)
 {
-    run_stage<A, D, g, s>(v, kp, tw, pc, inverse);
-    if constexpr (s > D.s_lo(g)) run_stages_from<A, D, g, s - 1>(v, kp, tw, pc, inverse);
+    run_stage<A, D, g, s>(v, kp, tw, pc, sg);
+    if constexpr (s > D.s_lo(g)) run_stages_from<A, D, g, s - 1>(v, kp, tw, pc, sg);
 }
 
 KF_HD int phys_rt(int a, int logpad) { return logpad >= 31 ? a : a + (a >> logpad); }
@@ -204,6 +204,11 @@ KF_HD void run_group(int t, bool active, const Src& src, const Dst& dst, const t
     typedef cx<typename A::R> X;
     constexpr int R = D.R(g), WI = D.items(g), IT = D.iters(g), Flo = D.Flo(g);
     constexpr bool kFirst = (g == 0), kLast = (g == D.G - 1);
+    // When the skew phys(a) = a + (a >> logpad) cannot carry between the thread-dependent base and the
+    // register-dependent offset (true for all power-of-two plans, see PlanDesc::lin_rd/lin_wr) the offset part is
+    // a compile-time constant and folds into the LDS/STS immediate.
+    constexpr bool kLinRd = D.lin_rd(g), kLinWr = D.lin_wr(g);
+    const typename A::R sg = A::sign_of(inverse);
     static_for<IT>([&](auto ITER) {
         constexpr int it = decltype(ITER)::value;
         const int w = t + it * D.team;
@@ -211,17 +216,20 @@ KF_HD void run_group(int t, bool active, const Src& src, const Dst& dst, const t
         if (on) {
             const int off = w % Flo, kp = w / Flo;
             X v[R];
+            const int rbase = kFirst ? off : phys_rt(kp * (Flo * R) + off, D.logpad);
             static_for<R>([&](auto E) {
                 constexpr int e = decltype(E)::value;
-                if constexpr (kFirst) v[e] = src.load(off + e * Flo);
+                if constexpr (kFirst) v[e] = src.load(rbase + e * Flo);
+                else if constexpr (kLinRd) v[e] = A::load(rd[rbase + D.phys(e * Flo)]);
                 else v[e] = A::load(rd[phys_rt(kp * (Flo * R) + off + e * Flo, D.logpad)]);
             });
-            run_stages_from<A, D, g, D.s_hi(g)>(v, kp, tw, pc, inverse);
+            run_stages_from<A, D, g, D.s_hi(g)>(v, kp, tw, pc, sg);
+            const int wbase = kLast ? kp : phys_rt(kp * Flo + off, D.logpad);
             static_for<R>([&](auto E) {
                 constexpr int e = decltype(E)::value;
-                const int k = kp + D.kout(g, e);
-                if constexpr (kLast) dst.store(k, v[e]);
-                else wr[phys_rt(k * Flo + off, D.logpad)] = A::store(v[e]);
+                if constexpr (kLast) dst.store(wbase + D.kout(g, e), v[e]);
+                else if constexpr (kLinWr) wr[wbase + D.phys(D.kout(g, e) * Flo)] = A::store(v[e]);
+                else wr[phys_rt((kp + D.kout(g, e)) * Flo + off, D.logpad)] = A::store(v[e]);
             });
         }
     });

@@ -167,7 +167,9 @@ extern "C" int kfcu_exec(int mode, const kfcu_plan* plan, const void* d_in, void
     if ((mode == kR2C || mode == kC2R) && !plan->d_stw && plan->nfft > 1) return KFCU_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     KParams<AT> P = make_params(plan, d_in, d_out, howmany, in_dist, out_dist, in_stride);
-    if (const FusedEntry* fe = find_fused(plan->nfft, mode)) return fe->fn[mode](P, st);
+    // the fused C2C kernels assume contiguous input rows; other strides take the run-time kernel
+    if (!(mode == kC2C && in_stride != 1))
+        if (const FusedEntry* fe = find_fused(plan->nfft, mode)) return fe->fn[mode](P, st);
     return launch_generic(mode, plan, P, st);
 }
 

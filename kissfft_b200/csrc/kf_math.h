@@ -49,6 +49,8 @@ struct ArithFloat {
     static KF_HD R add(R a, R b) { return a + b; }
     static KF_HD R sub(R a, R b) { return a - b; }
     static KF_HD R neg(R a) { return -a; }
+    static KF_HD R mad_sign(R sg, R a, R b) { return sg * a + b; }   // sg == +-1: exact
+    static KF_HD R sign_of(int inverse) { return inverse ? (F)-1 : (F)1; }
     static KF_HD R wrap(R a) { return a; }
     static KF_HD R smul(R a, R b) { return a * b; }                    // S_MUL, _kiss_fft_guts.h:86
     static KF_HD R half(R a) { return a * (F)0.5; }                     // HALF_OF, :138
@@ -84,6 +86,8 @@ struct Arith<int16_t> {
     static KF_HD R add(R a, R b) { return (R)((uint32_t)a + (uint32_t)b); }
     static KF_HD R sub(R a, R b) { return (R)((uint32_t)a - (uint32_t)b); }
     static KF_HD R neg(R a) { return (R)(0u - (uint32_t)a); }
+    static KF_HD R mad_sign(R sg, R a, R b) { return (R)((uint32_t)sg * (uint32_t)a + (uint32_t)b); }
+    static KF_HD R sign_of(int inverse) { return inverse ? -1 : 1; }
     static KF_HD R wrap(R a) { return (R)(int16_t)a; }
     static KF_HD R sround(int32_t x) { return (R)(int16_t)((x + (1 << (kFrac - 1))) >> kFrac); }   // :65
     static KF_HD R smul(R a, R b) { return sround(a * b); }                                        // :67
@@ -113,6 +117,8 @@ struct Arith<int32_t> {
     static KF_HD R add(R a, R b) { return (R)((uint32_t)a + (uint32_t)b); }
     static KF_HD R sub(R a, R b) { return (R)((uint32_t)a - (uint32_t)b); }
     static KF_HD R neg(R a) { return (R)(0u - (uint32_t)a); }
+    static KF_HD R mad_sign(R sg, R a, R b) { return (R)((uint32_t)sg * (uint32_t)a + (uint32_t)b); }
+    static KF_HD R sign_of(int inverse) { return inverse ? -1 : 1; }
     static KF_HD R wrap(R a) { return a; }
     static KF_HD R sround(int64_t x) { return (R)((x + ((int64_t)1 << (kFrac - 1))) >> kFrac); }
     static KF_HD R smul(R a, R b) { return sround((int64_t)a * b); }
@@ -169,7 +175,7 @@ KF_HD void bfly2(cx<typename A::R>* v, const cx<typename A::R>& t1)
 // kf_bfly4, kiss_fft.c:38-84
 template <class A, bool TW1>
 KF_HD void bfly4(cx<typename A::R>* v, const cx<typename A::R>& t1, const cx<typename A::R>& t2,
-                 const cx<typename A::R>& t3, int inverse)
+                 const cx<typename A::R>& t3, typename A::R sg)
 {
     typedef cx<typename A::R> X;
     X f0 = cfixdiv<A, 4>(v[0]), f1 = cfixdiv<A, 4>(v[1]), f2 = cfixdiv<A, 4>(v[2]), f3 = cfixdiv<A, 4>(v[3]);
@@ -182,11 +188,11 @@ KF_HD void bfly4(cx<typename A::R>* v, const cx<typename A::R>& t1, const cx<typ
     X s4 = csub<A>(s0, s2);
     v[2] = cwrap<A>(csub<A>(f0, s3));
     v[0] = cwrap<A>(cadd<A>(f0, s3));
-    // forward: F[k+m] = s5 - j*s4, F[k+3m] = s5 + j*s4; inverse swaps them (kiss_fft.c:71-81)
-    X u{A::add(s5.r, s4.i), A::sub(s5.i, s4.r)};
-    X w{A::sub(s5.r, s4.i), A::add(s5.i, s4.r)};
-    v[1] = cwrap<A>(inverse ? w : u);
-    v[3] = cwrap<A>(inverse ? u : w);
+    // forward: F[k+m] = s5 - j*s4, F[k+3m] = s5 + j*s4; inverse swaps them (kiss_fft.c:71-81).  The direction
+    // enters as sg = +1 (forward) / -1 (inverse) through a multiply-add, which is exact (|sg| == 1) and costs
+    // the same instruction as the add it replaces -- no select, no second kernel instantiation.
+    v[1] = cwrap<A>(X{A::mad_sign(sg, s4.i, s5.r), A::mad_sign(A::neg(sg), s4.r, s5.i)});
+    v[3] = cwrap<A>(X{A::mad_sign(A::neg(sg), s4.i, s5.r), A::mad_sign(sg, s4.r, s5.i)});
 }
 
 // kf_bfly3, kiss_fft.c:86-128.  epi3i = twiddles[N/3].i (sign carries the direction)

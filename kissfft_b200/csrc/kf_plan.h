@@ -86,6 +86,21 @@ struct PlanDesc {
         return k;
     }
     KF_CE int phys(int a) const { return logpad >= 31 ? a : a + (a >> logpad); }
+    // phys(base + delta) == phys(base) + phys(delta) for every work item of group g?  (no carry out of the low
+    // logpad bits).  Reads: base = kp*Flo*R + off (off < Flo), delta = e*Flo.  Writes: base = kp*Flo + off
+    // (kp < m_hi), delta = kout(e)*Flo, a multiple of m_hi*Flo.
+    KF_CE bool lin_rd(int g) const
+    {
+        if (logpad >= 31) return true;
+        const int P = 1 << logpad, fl = Flo(g);
+        return ((fl * R(g)) % P == 0) && (P % fl == 0 || fl % P == 0);
+    }
+    KF_CE bool lin_wr(int g) const
+    {
+        if (logpad >= 31) return true;
+        const int P = 1 << logpad, u = mhi(g) * Flo(g);
+        return (u % P == 0) || (P % u == 0);
+    }
     // per-transform pitch of one exchange buffer (elements), made odd so that lanes which walk across
     // transforms (strided-input mapping) fall into different banks
     KF_CE int pitch() const { return phys(N - 1) + 1 + ((phys(N - 1) + 1) % 2 == 0 ? 1 : 0); }
