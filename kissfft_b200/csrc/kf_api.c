@@ -396,6 +396,7 @@ void kiss_fft_cleanup(void)
         cudaSetDevice(e->device);
         cudaFree((void *)e->plan.d_tw);
         if (e->plan.d_stw) cudaFree((void *)e->plan.d_stw);
+        if (e->plan.d_gtw) cudaFree(e->plan.d_gtw);
         free(e->h_tw);
         free(e);
         e = n;
@@ -479,7 +480,7 @@ int kiss_fft_batch_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx 
     }
     const kf_devplan *dp;
     KF_CHECK(kf_get_devplan(cfg, NULL, &dp));
-    KF_CHECK(kfcu_exec(KFCU_C2C, &dp->plan, d_in, d_out, (long long)howmany, (long long)in_dist, (long long)out_dist,
+    KF_CHECK(kfcu_exec(KFCU_C2C, (kfcu_plan *)&dp->plan, d_in, d_out, (long long)howmany, (long long)in_dist, (long long)out_dist,
                        (long long)in_stride, stream));
     return 0;
 }
@@ -495,7 +496,7 @@ int kiss_fft_axis_pass_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_
     KF_CHECK(kf_get_devplan(cfg, NULL, &dp));
     /* column i: elements d_in[i + j*col_stride]; written as row i: d_out[i*nfft + k]  (kiss_fftnd.c:176-177) */
     const int mode = (col_stride == 1 && ncols == 1) ? KFCU_C2C : KFCU_C2C_COL;
-    KF_CHECK(kfcu_exec(mode, &dp->plan, d_in, d_out, (long long)ncols, 1, (long long)cfg->nfft, (long long)col_stride, stream));
+    KF_CHECK(kfcu_exec(mode, (kfcu_plan *)&dp->plan, d_in, d_out, (long long)ncols, 1, (long long)cfg->nfft, (long long)col_stride, stream));
     return 0;
 }
 
@@ -521,7 +522,7 @@ int kiss_fftr_batch_dev(kiss_fftr_cfg cfg, const kiss_fft_scalar *d_time, kiss_f
     }
     const kf_devplan *dp;
     KF_CHECK(kf_get_devplan(cfg->substate, cfg->super_twiddles, &dp));
-    KF_CHECK(kfcu_exec(KFCU_R2C, &dp->plan, d_time, d_freq, (long long)howmany, (long long)(time_dist / 2),
+    KF_CHECK(kfcu_exec(KFCU_R2C, (kfcu_plan *)&dp->plan, d_time, d_freq, (long long)howmany, (long long)(time_dist / 2),
                        (long long)freq_dist, 1, stream));
     return 0;
 }
@@ -543,7 +544,7 @@ int kiss_fftri_batch_dev(kiss_fftr_cfg cfg, const kiss_fft_cpx *d_freq, kiss_fft
     }
     const kf_devplan *dp;
     KF_CHECK(kf_get_devplan(cfg->substate, cfg->super_twiddles, &dp));
-    KF_CHECK(kfcu_exec(KFCU_C2R, &dp->plan, d_freq, d_time, (long long)howmany, (long long)freq_dist,
+    KF_CHECK(kfcu_exec(KFCU_C2R, (kfcu_plan *)&dp->plan, d_freq, d_time, (long long)howmany, (long long)freq_dist,
                        (long long)(time_dist / 2), 1, stream));
     return 0;
 }

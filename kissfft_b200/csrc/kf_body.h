@@ -14,6 +14,8 @@
 //   kR2C      kiss_fftr: packed complex transform + split-twiddle post pass fused     (kiss_fftr.c:63-117)
 //   kC2R      kiss_fftri: split pre pass fused + inverse complex transform            (kiss_fftr.c:119-155)
 #pragma once
+#include <stddef.h>
+
 #include "kf_engine.h"
 
 namespace kf {
@@ -29,6 +31,8 @@ struct KParams {
     long long in_stride;         // element stride of the input (kiss_fft_stride's in_stride)
     const typename A::C* tw;     // N twiddles (kR2C/kC2R: of the ncfft-point sub-transform)
     const typename A::C* stw;    // ncfft/2 split twiddles (kiss_fftr.c:53-59), real modes only
+    const typename A::C* gtw;    // per-group stage-twiddle tables of the fused plan (kf_twtab.h), unused by the generic kernel
+    cx<typename A::R> g0tw[kMaxG0Slots];   // group 0's stage twiddles (plan constants -> constant bank)
     PlanConsts<A> pc;
     int inverse;
 };
@@ -100,41 +104,138 @@ KF_HD void run_groups(Env& env, int t, bool active, const Src& src, const Dst& d
     }
 }
 
+// Shared-memory layout of one CTA of the fused kernel.
+//   [exchange buffer A][exchange buffer B]   tpc * pitch elements each (skewed autosort arrays between groups)
+//   [input ring: nstage stages]              each stage = one tile of tpc contiguous input rows, natural order,
+//                                            filled by a bulk asynchronous copy (TMA, cp.async.bulk) that
+//                                            completes on the stage's mbarrier
+//   [nstage mbarriers]
+template <class A, class PT, int MODE>
+struct FusedLayout {
+    static constexpr PlanDesc D = PT::D;
+    static constexpr bool kRing = D.nstage > 0 && MODE != kC2CCol;
+    static constexpr int kRowIn = (MODE == kC2R) ? D.N + 1 : D.N;   // complex elements per input row
+    static constexpr size_t kExchBytes = (D.G >= 2 || MODE == kR2C || MODE == kC2R) ? (size_t)2 * D.tpc * D.pitch() * sizeof(typename A::C) : 0;
+    static constexpr size_t kRingOff = (kExchBytes + 127) / 128 * 128;
+    static constexpr size_t kStageBytes = ((size_t)D.tpc * kRowIn * sizeof(typename A::C) + 127) / 128 * 128;
+    static constexpr size_t kBarOff = kRingOff + (kRing ? D.nstage * kStageBytes : 0);
+    static constexpr size_t kTotal = kRing ? kBarOff + 8 * (size_t)D.nstage : kExchBytes;
+};
+
 // PT is a tag type carrying the plan as `static constexpr PlanDesc D`.
-// Env abstracts the execution environment (thread/block ids, CTA barrier, dynamic shared memory) so that the
-// identical body runs as a CUDA kernel (DeviceEnv, kf_kernels.cuh) and, for index-math tests without a GPU,
-// under tests/emul's thread-per-CUDA-thread emulator.
+// Env abstracts the execution environment (thread/block ids, CTA barrier, dynamic shared memory, bulk async
+// copies + mbarriers) so that the identical body runs as a CUDA kernel (DeviceEnv, kf_kernels.cuh) and, for
+// index-math tests without a GPU, under tests/emul's thread-per-CUDA-thread emulator.
+//
+// Input path when D.nstage > 0 (all modes with contiguous input rows): one elected thread keeps `nstage` tiles
+// in flight with cp.async.bulk (global -> shared, completion on an mbarrier); the team reads its row from the
+// landed stage with conflict-free LDS.  A stage is recycled right after the barrier that follows the only
+// group that reads it, so the HBM read stream never waits for the butterflies.  With D.nstage == 0 (and always
+// for the column mode, whose rows are strided) the first group loads straight from global memory.
 template <class A, class PT, int MODE, class Env>
 KF_HD void fused_body(const KParams<A>& P, Env& env)
 {
     constexpr PlanDesc D = PT::D;
+    typedef FusedLayout<A, PT, MODE> LY;
     typedef typename A::C C;
     typedef cx<typename A::R> X;
     static_assert(D.valid(), "inconsistent plan descriptor");
-    C* const smem = reinterpret_cast<C*>(env.smem());
+    unsigned char* const smem_raw = env.smem();
+    C* const smem = reinterpret_cast<C*>(smem_raw);
     constexpr int kPitch = D.pitch();
+    constexpr bool kRing = LY::kRing;
+    constexpr int kRowIn = LY::kRowIn;
     // two exchange buffers of tpc * pitch elements each
     C* const bufA = smem;
     C* const bufB = smem + D.tpc * kPitch;
 
     const int tid = env.tid();
     const int team = tid / D.team, t = tid % D.team;              // standard mapping: a team owns a transform
-    const TwTab<A> tw{P.tw};
+    const TwTab<A> tw{P.tw, P.gtw, P.g0tw};
     const long long ntiles = (P.howmany + D.tpc - 1) / D.tpc;
     int par = 0;   // parity of the exchange buffer sequence, carried across tiles (see run_groups)
 
-    for (long long tile = env.bid(); tile < ntiles; tile += env.nblocks()) {
+    // ---- input ring ----
+    auto stage_ptr = [&](int s) { return reinterpret_cast<C*>(smem_raw + LY::kRingOff + (size_t)s * LY::kStageBytes); };
+    auto bar_ptr = [&](int s) { return smem_raw + LY::kBarOff + 8 * (size_t)s; };
+    auto issue = [&](int s, long long tl) {   // elected thread only
+        const long long row0 = tl * D.tpc;
+        const long long rows = (P.howmany - row0) < D.tpc ? (P.howmany - row0) : D.tpc;
+        env.bulk_load(bar_ptr(s), stage_ptr(s), P.in + row0 * kRowIn, (unsigned)(rows * kRowIn * sizeof(C)));
+    };
+    if constexpr (kRing) {
+        if (tid == 0)
+            for (int s = 0; s < D.nstage; ++s) env.mbar_init(bar_ptr(s));
+        env.mbar_fence_init();
+        env.sync();
+        if (tid == 0)
+            for (int s = 0; s < D.nstage; ++s) {
+                const long long tl = env.bid() + (long long)s * env.nblocks();
+                if (tl < ntiles) issue(s, tl);
+            }
+    }
+
+    int it = 0;
+    for (long long tile = env.bid(); tile < ntiles; tile += env.nblocks(), ++it) {
         const long long b = tile * D.tpc + team;
         const bool active = b < P.howmany;
         C* b0 = (par ? bufB : bufA) + team * kPitch;
         C* b1 = (par ? bufA : bufB) + team * kPitch;
+        const int stg = kRing ? it % (D.nstage > 0 ? D.nstage : 1) : 0;
+        const C* srow = nullptr;
+        if constexpr (kRing) {
+            env.mbar_wait(bar_ptr(stg), it / (D.nstage > 0 ? D.nstage : 1));
+            srow = stage_ptr(stg) + team * kRowIn;
+        }
+        // after the CTA barrier that follows the last read of the stage: refill it with the tile nstage rounds ahead
+        auto recycle = [&]() {
+            if constexpr (LY::kRing) {
+                if (tid == 0) {
+                    const long long nxt = tile + (long long)PT::D.nstage * env.nblocks();
+                    if (nxt < ntiles) issue(stg, nxt);
+                }
+            }
+        };
 
-        if constexpr (MODE == kC2C) {
-            SrcGlobal<A, true> src{P.in + b * P.in_dist, 1};   // in_stride == 1 (other strides: generic kernel)
-            DstGlobal<A> dst{P.out + b * P.out_dist};
-            // group 0 writes b1... sequence: g0 -> W(b1); g1: R(b1) W(b0); g2: R(b0) W(b1) ...
-            run_groups<A, D, 0>(env, t, active, src, dst, b0, b1, tw, P.pc, P.inverse);
-            if constexpr (D.G >= 2) par ^= (D.G - 1) & 1;
+        if constexpr (MODE == kC2C || MODE == kR2C) {
+            // kR2C: the real row is read as ncfft packed complex (kiss_fftr.c:77); the last group leaves T[] in
+            // natural order in the next exchange buffer for the split pass
+            C* tb = (((D.G - 1) & 1) ? b0 : b1);
+            DstGlobal<A> dstg{P.out + b * P.out_dist};
+            DstShared<A> dsts{tb};
+            auto run_from = [&](auto src, auto dst) {
+                typedef decltype(src) S;
+                typedef decltype(dst) Dd;
+                run_group<A, PT::D, 0, S, Dd>(t, active, src, dst, b0, b1, tw, P.pc, P.inverse);
+                if constexpr (PT::D.G >= 2 || LY::kRing) env.sync();
+                recycle();
+                if constexpr (PT::D.G >= 2) run_groups<A, PT::D, 1, S, Dd>(env, t, active, src, dst, b1, b0, tw, P.pc, P.inverse);
+            };
+            auto with_dst = [&](auto src) {
+                if constexpr (MODE == kC2C) run_from(src, dstg);
+                else run_from(src, dsts);
+            };
+            if constexpr (kRing) with_dst(SrcShared<A>{srow});
+            else with_dst(SrcGlobal<A, true>{P.in + b * P.in_dist, 1});   // contiguous rows (other strides: generic kernel)
+            if constexpr (MODE == kC2C) {
+                if constexpr (D.G >= 2) par ^= (D.G - 1) & 1;
+            } else {
+                env.sync();
+                if (active) {
+                    constexpr int nc = D.N;
+                    C* out = P.out + b * P.out_dist;
+                    for (int k = t; k <= nc / 2; k += D.team) {
+                        X Tk = A::load(tb[k]);
+                        X Tnk = (k == 0) ? Tk : A::load(tb[nc - k]);
+                        X st = (k == 0) ? Tk : A::load(TwTab<A>::ro_load_c(P.stw + (k - 1)));
+                        X ok, onk;
+                        fftr_post_pair<A>(k, nc, Tk, Tnk, st, ok, onk);
+                        out[k] = A::store(ok);
+                        out[nc - k] = A::store(onk);
+                    }
+                }
+                par ^= D.G & 1;   // G exchanges were used (G-1 between groups + the T[] buffer)
+            }
         } else if constexpr (MODE == kC2CCol) {
             // group 0 uses the transposed mapping: consecutive lanes take consecutive transforms (columns)
             static_assert(D.G >= 2, "column mode needs a shared-memory exchange");
@@ -147,36 +248,14 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             env.sync();
             run_groups<A, D, 1>(env, t, active, src, dst, b1, b0, tw, P.pc, P.inverse);
             par ^= (D.G - 1) & 1;
-        } else if constexpr (MODE == kR2C) {
-            // packed complex transform, last group leaves T[] in natural order in shared memory
-            SrcGlobal<A, true> src{P.in + b * P.in_dist, 1};
-            // buffer written by the last group: after G-1 exchanges the "next write" buffer
-            C* tb = (((D.G - 1) & 1) ? b0 : b1);
-            DstShared<A> dst{tb};
-            run_groups<A, D, 0>(env, t, active, src, dst, b0, b1, tw, P.pc, P.inverse);
-            env.sync();
-            if (active) {
-                constexpr int nc = D.N;
-                C* out = P.out + b * P.out_dist;
-                for (int k = t; k <= nc / 2; k += D.team) {
-                    X Tk = A::load(tb[k]);
-                    X Tnk = (k == 0) ? Tk : A::load(tb[nc - k]);
-                    X st = (k == 0) ? Tk : A::load(TwTab<A>::ro_load_c(P.stw + (k - 1)));
-                    X ok, onk;
-                    fftr_post_pair<A>(k, nc, Tk, Tnk, st, ok, onk);
-                    out[k] = A::store(ok);
-                    out[nc - k] = A::store(onk);
-                }
-            }
-            par ^= D.G & 1;   // G exchanges were used (G-1 between groups + the T[] buffer)
         } else {   // kC2R
             constexpr int nc = D.N;
             // split pre pass writes T[] (natural order) into b1, group 0 then reads it from shared memory
             if (active) {
-                const C* in = P.in + b * P.in_dist;
+                const C* in = kRing ? srow : P.in + b * P.in_dist;
                 for (int k = t; k <= nc / 2; k += D.team) {
-                    X Fk = A::load(ld_stream(in + k));
-                    X Fnk = A::load(ld_stream(in + (nc - k)));
+                    X Fk = A::load(kRing ? in[k] : ld_stream(in + k));
+                    X Fnk = A::load(kRing ? in[nc - k] : ld_stream(in + (nc - k)));
                     X st = (k == 0) ? Fk : A::load(TwTab<A>::ro_load_c(P.stw + (k - 1)));
                     X Tk, Tnk;
                     fftri_pre_pair<A>(k, Fk, Fnk, st, Tk, Tnk);
@@ -185,6 +264,7 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
                 }
             }
             env.sync();
+            recycle();
             SrcShared<A> src{b1};
             DstGlobal<A> dst{P.out + b * P.out_dist};
             // group 0 reads b1 (via src) and writes b0; g1 reads b0 writes b1 ...
@@ -241,7 +321,7 @@ KF_HD void generic_body(const GParams<A>& G, Env& env)
     const int N = G.plan.N, L = G.plan.L, tpc = G.tpc, mode = G.mode;
     C* const buf0 = reinterpret_cast<C*>(env.smem());
     C* const buf1 = buf0 + (size_t)tpc * N;
-    const TwTab<A> tw{P.tw};
+    const TwTab<A> tw{P.tw, nullptr, nullptr};
     const int nthr = env.nthreads(), tid = env.tid();
     const long long ntiles = (P.howmany + tpc - 1) / tpc;
 

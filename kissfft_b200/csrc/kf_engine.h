@@ -41,7 +41,9 @@ template <class A>
 struct TwTab {
     typedef typename A::C C;
     typedef cx<typename A::R> X;
-    const C* tw;   // N entries, tw[i] = exp(-+2 pi j i/N) generated on the host exactly like kiss_fft.c:361-367
+    const C* tw;    // N entries, tw[i] = exp(-+2 pi j i/N) generated on the host exactly like kiss_fft.c:361-367
+    const C* gtw;   // per-group stage-twiddle tables [g][slot][work item] (PlanDesc::slot), exact copies of tw[] entries
+    const X* g0;    // group 0's slots (kernel parameter space)
     KF_HD X get(int idx) const
     {
         // all storage complexes are plain {S r, i}; load as one vector
@@ -75,6 +77,14 @@ struct PlanConsts {
     cx<typename A::R> yb;     // tw[2N/5]
 };
 
+// stage twiddle of slot `slot` (compile-time) for work item w of group g
+template <class A, PlanDesc D, int g>
+KF_HD cx<typename A::R> stage_tw(const TwTab<A>& tw, int slot, int w)
+{
+    if constexpr (g == 0) return tw.g0[slot];
+    else return A::load(TwTab<A>::ro_load_c(tw.gtw + (D.gtw_offset(g) + slot * D.items(g)) + w));
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // generic radix p (kf_bfly_generic, kiss_fft.c:192-233)
 // ---------------------------------------------------------------------------------------------------------
@@ -104,9 +114,10 @@ KF_HD void bfly_generic_fixed(cx<typename A::R>* v, int ks, const TwTab<A>& tw)
 // twiddles are applied first (p-1 products, as the radix-2..5 butterflies do) and the remaining constant
 // p-point DFT uses the conjugate symmetry W_p^(p-j) = conj(W_p^j): outputs q1 and p-q1 share their sums.
 // Same operands, different association => equal up to rounding (parity is relative-RMS for float/double).
-template <class A, int N, int p, int Fs, int ms, bool TW1>
-KF_HD void bfly_generic_float(cx<typename A::R>* v, int ks, const TwTab<A>& tw)
+template <class A, PlanDesc D, int g, int p, bool TW1>
+KF_HD void bfly_generic_float(cx<typename A::R>* v, int slot0, int w, const TwTab<A>& tw)
 {
+    constexpr int N = D.N;
     typedef typename A::R R;
     typedef cx<R> X;
     static_assert(p % 2 == 1, "generic radices are odd (kf_factor emits 4, 2, then odd numbers)");
@@ -115,7 +126,7 @@ KF_HD void bfly_generic_float(cx<typename A::R>* v, int ks, const TwTab<A>& tw)
     y[0] = v[0];
     static_for<p - 1>([&](auto Qm1) {
         constexpr int q = decltype(Qm1)::value + 1;
-        y[q] = TW1 ? v[q] : A::cmul(v[q], tw.get(q * Fs * ks));
+        y[q] = TW1 ? v[q] : A::cmul(v[q], stage_tw<A, D, g>(tw, slot0 + q - 1, w));
     });
     X a[h + 1], b[h + 1];
     X sum = y[0];
@@ -148,7 +159,7 @@ KF_HD void bfly_generic_float(cx<typename A::R>* v, int ks, const TwTab<A>& tw)
 // one radix stage s of group g applied to the R(g) registers of a work item whose k' is `kp`
 // ---------------------------------------------------------------------------------------------------------
 template <class A, PlanDesc D, int g, int s>
-KF_HD void run_stage(cx<typename A::R>* v, int kp, const TwTab<A>& tw, const PlanConsts<A>& pc, typename A::R sg)
+KF_HD void run_stage(cx<typename A::R>* v, int kp, int w, const TwTab<A>& tw, const PlanConsts<A>& pc, typename A::R sg)
 {
     typedef cx<typename A::R> X;
     constexpr int p = D.p[s], Ws = D.W(g, s), Fs = D.F(s), ms = D.m(s), R = D.R(g);
@@ -162,20 +173,20 @@ KF_HD void run_stage(cx<typename A::R>* v, int kp, const TwTab<A>& tw, const Pla
             const int ks = (g == 0 ? 0 : kp) + kab;
             X x[p];
             static_for<p>([&](auto Q) { constexpr int q = decltype(Q)::value; x[q] = v[e + q * Ws]; });
+            constexpr int sl = D.slot(g, s, e);
+            auto T = [&](int q) { return stage_tw<A, D, g>(tw, sl + q - 1, w); };
             if constexpr (p == 2) {
-                bfly2<A, kTw1>(x, kTw1 ? X{} : tw.get(Fs * ks));
+                bfly2<A, kTw1>(x, kTw1 ? X{} : T(1));
             } else if constexpr (p == 4) {
-                bfly4<A, kTw1>(x, kTw1 ? X{} : tw.get(Fs * ks), kTw1 ? X{} : tw.get(2 * Fs * ks),
-                               kTw1 ? X{} : tw.get(3 * Fs * ks), sg);
+                bfly4<A, kTw1>(x, kTw1 ? X{} : T(1), kTw1 ? X{} : T(2), kTw1 ? X{} : T(3), sg);
             } else if constexpr (p == 3) {
-                bfly3<A, kTw1>(x, kTw1 ? X{} : tw.get(Fs * ks), kTw1 ? X{} : tw.get(2 * Fs * ks), pc.epi3.i);
+                bfly3<A, kTw1>(x, kTw1 ? X{} : T(1), kTw1 ? X{} : T(2), pc.epi3.i);
             } else if constexpr (p == 5) {
-                bfly5<A, kTw1>(x, kTw1 ? X{} : tw.get(Fs * ks), kTw1 ? X{} : tw.get(2 * Fs * ks),
-                               kTw1 ? X{} : tw.get(3 * Fs * ks), kTw1 ? X{} : tw.get(4 * Fs * ks), pc.ya, pc.yb);
+                bfly5<A, kTw1>(x, kTw1 ? X{} : T(1), kTw1 ? X{} : T(2), kTw1 ? X{} : T(3), kTw1 ? X{} : T(4), pc.ya, pc.yb);
             } else if constexpr (A::kFixed) {
                 bfly_generic_fixed<A, D.N, p, Fs, ms>(x, ks, tw);
             } else {
-                bfly_generic_float<A, D.N, p, Fs, ms, kTw1>(x, ks, tw);
+                bfly_generic_float<A, D, g, p, kTw1>(x, sl, w, tw);
             }
             static_for<p>([&](auto Q) { constexpr int q = decltype(Q)::value; v[e + q * Ws] = x[q]; });
         }
@@ -183,10 +194,10 @@ KF_HD void run_stage(cx<typename A::R>* v, int kp, const TwTab<A>& tw, const Pla
 }
 
 template <class A, PlanDesc D, int g, int s>
-KF_HD void run_stages_from(cx<typename A::R>* v, int kp, const TwTab<A>& tw, const PlanConsts<A>& pc, typename A::R sg)
+KF_HD void run_stages_from(cx<typename A::R>* v, int kp, int w, const TwTab<A>& tw, const PlanConsts<A>& pc, typename A::R sg)
 {
-    run_stage<A, D, g, s>(v, kp, tw, pc, sg);
-    if constexpr (s > D.s_lo(g)) run_stages_from<A, D, g, s - 1>(v, kp, tw, pc, sg);
+    run_stage<A, D, g, s>(v, kp, w, tw, pc, sg);
+    if constexpr (s > D.s_lo(g)) run_stages_from<A, D, g, s - 1>(v, kp, w, tw, pc, sg);
 }
 
 KF_HD int phys_rt(int a, int logpad) { return logpad >= 31 ? a : a + (a >> logpad); }
@@ -223,7 +234,7 @@ KF_HD void run_group(int t, bool active, const Src& src, const Dst& dst, const t
                 else if constexpr (kLinRd) v[e] = A::load(rd[rbase + D.phys(e * Flo)]);
                 else v[e] = A::load(rd[phys_rt(kp * (Flo * R) + off + e * Flo, D.logpad)]);
             });
-            run_stages_from<A, D, g, D.s_hi(g)>(v, kp, tw, pc, sg);
+            run_stages_from<A, D, g, D.s_hi(g)>(v, kp, w, tw, pc, sg);
             const int wbase = kLast ? kp : phys_rt(kp * Flo + off, D.logpad);
             static_for<R>([&](auto E) {
                 constexpr int e = decltype(E)::value;

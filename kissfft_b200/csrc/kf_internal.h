@@ -25,12 +25,14 @@ typedef struct kfcu_plan {
     const void *d_tw;  /* nfft complex twiddles in device memory */
     const void *d_stw; /* nfft/2 split twiddles (real modes) or NULL */
     const void *h_tw;  /* the same twiddles on the host (for the butterfly constants) */
+    void *d_gtw;       /* per-group stage-twiddle tables of the fused plan; created lazily by kf_launch.cu, freed by
+                          kiss_fft_cleanup together with d_tw */
 } kfcu_plan;
 
 /* Runs `howmany` transforms. Distances are in complex elements of the respective side (for KFCU_R2C the input
  * side and for KFCU_C2R the output side are real rows viewed as packed complex, i.e. scalars/2).
  * Returns 0 or a cudaError_t value; KFCU_E* (negative) for argument errors. */
-int kfcu_exec(int mode, const kfcu_plan *plan, const void *d_in, void *d_out, long long howmany, long long in_dist,
+int kfcu_exec(int mode, kfcu_plan *plan, const void *d_in, void *d_out, long long howmany, long long in_dist,
               long long out_dist, long long in_stride, void *stream);
 
 /* out[c][r] = in[r][c] for a rows x cols array of complex elements (kiss_fftndr's bin-major <-> row-major

@@ -15,6 +15,43 @@ struct DeviceEnv {
     __device__ __forceinline__ long long nblocks() const { return (long long)gridDim.x; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
     __device__ __forceinline__ unsigned char* smem() const { return smem_; }
+
+    // ---- mbarrier + bulk asynchronous copy (TMA engine, SASS: UBLKCP / SYNCS) ----
+    static __device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+    __device__ __forceinline__ void mbar_init(void* bar) const
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar)) : "memory");
+    }
+    __device__ __forceinline__ void mbar_fence_init() const
+    {
+        // make the initialised barriers visible to the async proxy before the first bulk copy signals them
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // one elected thread: arm the barrier with the byte count, then start global -> shared
+    __device__ __forceinline__ void bulk_load(void* bar, void* dst, const void* src, unsigned bytes) const
+    {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)),
+                     "l"(src), "r"(bytes), "r"(s32(bar))
+                     : "memory");
+    }
+    // all threads: wait for the k-th completion of the barrier (phase parity k & 1)
+    __device__ __forceinline__ void mbar_wait(void* bar, int k) const
+    {
+        const unsigned parity = (unsigned)k & 1u, addr = s32(bar);
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "KF_WAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+            "@p bra KF_DONE_%=;\n\t"
+            "bra KF_WAIT_%=;\n\t"
+            "KF_DONE_%=:\n\t"
+            "}" ::"r"(addr),
+            "r"(parity)
+            : "memory");
+    }
 };
 
 // PT is a tag type carrying the plan as `static constexpr PlanDesc D` (a class-type non-type template argument

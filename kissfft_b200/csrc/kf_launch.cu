@@ -9,10 +9,12 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "../../include/kiss_fft.h"
 #include "kf_internal.h"
 #include "kf_kernels.cuh"
+#include "kf_twtab.h"
 #define KF_SCALAR_BYTES ((int)sizeof(kiss_fft_scalar))
 #include "kf_plan_list.h"
 
@@ -54,6 +56,7 @@ static KParams<AT> make_params(const kfcu_plan* pl, const void* d_in, void* d_ou
     P.in_stride = in_stride;
     P.tw = (const CT*)pl->d_tw;
     P.stw = (const CT*)pl->d_stw;
+    P.gtw = nullptr;
     const CT* h = (const CT*)pl->h_tw;
     const int N = pl->nfft;
     // constants of kf_bfly3 / kf_bfly5 (kiss_fft.c:99, 143-144): twiddles[fstride*m] with fstride*m == N/p
@@ -66,14 +69,50 @@ static KParams<AT> make_params(const kfcu_plan* pl, const void* d_in, void* d_ou
 }
 
 // ---- fused plans ------------------------------------------------------------------------------------------
-typedef int (*fused_launch_fn)(const KParams<AT>&, cudaStream_t);
+typedef int (*fused_launch_fn)(kfcu_plan*, KParams<AT>&, cudaStream_t);
+
+static std::mutex g_gtw_mutex;
+static int launch_generic(int mode, const kfcu_plan* pl, const KParams<AT>& P, cudaStream_t st);
+
+// rows [first, first+count) of a call
+static KParams<AT> sub_rows(const KParams<AT>& P, long long first, long long count)
+{
+    KParams<AT> Q = P;
+    Q.in = P.in + first * P.in_dist;
+    Q.out = P.out + first * P.out_dist;
+    Q.howmany = count;
+    return Q;
+}
 
 template <class PT, int MODE>
-static int launch_fused(const KParams<AT>& P, cudaStream_t st)
+static int launch_fused(kfcu_plan* pl, KParams<AT>& P, cudaStream_t st)
 {
     constexpr PlanDesc D = PT::D;
+    // stage-twiddle tables of this plan: built once per (device plan) from the host twiddles, then cached
+    if (D.gtw_total() > 0 && !pl->d_gtw) {
+        std::lock_guard<std::mutex> lk(g_gtw_mutex);
+        if (!pl->d_gtw) {
+            std::vector<CT> tab = build_gtw<AT, PT>((const CT*)pl->h_tw);
+            void* d = nullptr;
+            cudaError_t e = cudaMalloc(&d, tab.size() * sizeof(CT));
+            if (e != cudaSuccess) return (int)e;
+            e = cudaMemcpy(d, tab.data(), tab.size() * sizeof(CT), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { cudaFree(d); return (int)e; }
+            pl->d_gtw = d;
+        }
+    }
+    P.gtw = (const CT*)pl->d_gtw;
+    fill_g0tw<AT, PT>(P, (const CT*)pl->h_tw);
+    // rows the fused kernel may take (alignment rules of the bulk-async ring); the remainder, normally none,
+    // goes to the run-time kernel
+    const long long nfused = fused_rows<AT, PT, MODE>(P);
+    if (nfused < P.howmany) {
+        int rc = launch_generic(MODE, pl, sub_rows(P, nfused, P.howmany - nfused), st);
+        if (rc != 0 || nfused == 0) return rc;
+        P = sub_rows(P, 0, nfused);
+    }
     auto kern = kf_fused_kernel<AT, PT, MODE>;
-    constexpr size_t smem = (D.G >= 2 || MODE == kR2C || MODE == kC2R) ? (size_t)2 * D.tpc * D.pitch() * sizeof(CT) : 0;
+    constexpr size_t smem = FusedLayout<AT, PT, MODE>::kTotal;
     static int blocks_per_sm[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -159,7 +198,7 @@ static int launch_generic(int mode, const kfcu_plan* pl, const KParams<AT>& P, c
 }
 
 // ---- C interface ------------------------------------------------------------------------------------------
-extern "C" int kfcu_exec(int mode, const kfcu_plan* plan, const void* d_in, void* d_out, long long howmany,
+extern "C" int kfcu_exec(int mode, kfcu_plan* plan, const void* d_in, void* d_out, long long howmany,
                          long long in_dist, long long out_dist, long long in_stride, void* stream)
 {
     if (!plan || !d_in || !d_out || mode < 0 || mode > 3 || howmany < 0) return KFCU_EINVAL;
@@ -167,9 +206,7 @@ extern "C" int kfcu_exec(int mode, const kfcu_plan* plan, const void* d_in, void
     if ((mode == kR2C || mode == kC2R) && !plan->d_stw && plan->nfft > 1) return KFCU_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     KParams<AT> P = make_params(plan, d_in, d_out, howmany, in_dist, out_dist, in_stride);
-    // the fused C2C kernels assume contiguous input rows; other strides take the run-time kernel
-    if (!(mode == kC2C && in_stride != 1))
-        if (const FusedEntry* fe = find_fused(plan->nfft, mode)) return fe->fn[mode](P, st);
+    if (const FusedEntry* fe = find_fused(plan->nfft, mode)) return fe->fn[mode](plan, P, st);
     return launch_generic(mode, plan, P, st);
 }
 

@@ -27,6 +27,7 @@ namespace kf {
 
 constexpr int kMaxStages = 16;
 constexpr int kMaxGroups = 8;
+constexpr int kMaxG0Slots = 64;   // stage twiddles of group 0 carried in the kernel parameters
 
 struct PlanDesc {
     int N;                  // transform length
@@ -38,6 +39,7 @@ struct PlanDesc {
     int tpc;                // transforms per CTA
     int logpad;             // shared-memory skew: phys(a) = a + (a >> logpad); >= 31 disables it
     int minblocks;          // __launch_bounds__ min CTAs per SM
+    int nstage;             // depth of the bulk-async (TMA) input ring; 0 = first group loads directly from global
 
     KF_CE int F(int s) const
     {
@@ -85,6 +87,35 @@ struct PlanDesc {
         for (int j = s_lo(g); j <= s_hi(g); ++j) k += digit(g, j, e) * m(j);
         return k;
     }
+    // ---- per-group twiddle tables ------------------------------------------------------------------------
+    // Every butterfly (g, s, e) of a work item needs the p_s - 1 stage twiddles tw[q*F_s*(k' + kabove)].  They
+    // depend on the work item only through k', so each (butterfly, q) pair gets a "slot" and the plan carries a
+    // table gtw[g][slot][w] laid out with the work item w innermost: a warp's fetch of one slot is one contiguous,
+    // immediate-addressed vector load instead of a gather over the N-entry twiddle array.  Group 0 has k' == 0:
+    // its slots are plan constants and travel in the kernel parameters (constant bank).
+    KF_CE int nslots_stage(int g, int s) const { return (R(g) / p[s]) * (p[s] - 1); }
+    KF_CE int slot(int g, int s, int e) const   // first slot of the butterfly whose base register is e
+    {
+        int n = 0;
+        for (int j = s_hi(g); j > s; --j) n += nslots_stage(g, j);
+        int cnt = 0;
+        for (int e2 = 0; e2 < e; ++e2)
+            if (digit(g, s, e2) == 0) ++cnt;
+        return n + cnt * (p[s] - 1);
+    }
+    KF_CE int nslots(int g) const
+    {
+        int n = 0;
+        for (int s = s_lo(g); s <= s_hi(g); ++s) n += nslots_stage(g, s);
+        return n;
+    }
+    KF_CE int gtw_offset(int g) const   // entries before group g's table (groups 1..G-1 only)
+    {
+        int n = 0;
+        for (int j = 1; j < g; ++j) n += nslots(j) * items(j);
+        return n;
+    }
+    KF_CE int gtw_total() const { return gtw_offset(G); }
     KF_CE int phys(int a) const { return logpad >= 31 ? a : a + (a >> logpad); }
     // phys(base + delta) == phys(base) + phys(delta) for every work item of group g?  (no carry out of the low
     // logpad bits).  Reads: base = kp*Flo*R + off (off < Flo), delta = e*Flo.  Writes: base = kp*Flo + off
@@ -110,7 +141,7 @@ struct PlanDesc {
         int prod = 1, sum = 0;
         for (int s = 0; s < L; ++s) prod *= p[s];
         for (int g = 0; g < G; ++g) sum += glen[g];
-        return prod == N && sum == L && L <= kMaxStages && G <= kMaxGroups && team > 0 && tpc > 0;
+        return prod == N && sum == L && L <= kMaxStages && G <= kMaxGroups && team > 0 && tpc > 0 && nslots(0) <= kMaxG0Slots;
     }
 };
 

@@ -14,7 +14,7 @@
 namespace kf {
 
 constexpr PlanDesc make_plan(int N, std::initializer_list<int> radices, std::initializer_list<int> groups, int team, int tpc,
-                             int logpad, int minblocks)
+                             int logpad, int minblocks, int nstage = 0)
 {
     PlanDesc d{};
     d.N = N;
@@ -26,6 +26,7 @@ constexpr PlanDesc make_plan(int N, std::initializer_list<int> radices, std::ini
     d.tpc = tpc;
     d.logpad = logpad;
     d.minblocks = minblocks;
+    d.nstage = nstage;
     return d;
 }
 
@@ -33,30 +34,30 @@ constexpr PlanDesc make_plan(int N, std::initializer_list<int> radices, std::ini
 // ---- Q15: 4-byte complex ------------------------------------------------------------------------------
 struct kP16 { static constexpr PlanDesc D = make_plan(16,   {4, 4},             {2},       1,   128, 31, 1); };
 struct kP64 { static constexpr PlanDesc D = make_plan(64,   {4, 4, 4},          {1, 2},    16,  16,  4,  1); };
-struct kP256 { static constexpr PlanDesc D = make_plan(256,  {4, 4, 4, 4},       {2, 2},    16,  16,  4,  1); };
-struct kP1024 { static constexpr PlanDesc D = make_plan(1024, {4, 4, 4, 4, 4},    {2, 2, 1}, 64,  4,   4,  1); };
-struct kP2048 { static constexpr PlanDesc D = make_plan(2048, {4, 4, 4, 4, 4, 2}, {2, 2, 2}, 128, 2,   4,  1); };
-struct kP1000 { static constexpr PlanDesc D = make_plan(1000, {4, 2, 5, 5, 5},    {2, 2, 1}, 50,  5,   4,  1); };
-struct kP1155 { static constexpr PlanDesc D = make_plan(1155, {3, 5, 7, 11},      {1, 1, 2}, 105, 2,   4,  1); };
+struct kP256 { static constexpr PlanDesc D = make_plan(256,  {4, 4, 4, 4},       {2, 2},    16,  16,  4,  1, 2); };
+struct kP1024 { static constexpr PlanDesc D = make_plan(1024, {4, 4, 4, 4, 4},    {2, 2, 1}, 64,  4,   4,  1, 3); };
+struct kP2048 { static constexpr PlanDesc D = make_plan(2048, {4, 4, 4, 4, 4, 2}, {2, 2, 2}, 128, 2,   4,  1, 2); };
+struct kP1000 { static constexpr PlanDesc D = make_plan(1000, {4, 2, 5, 5, 5},    {2, 2, 1}, 50,  5,   4,  1, 2); };
+struct kP1155 { static constexpr PlanDesc D = make_plan(1155, {3, 5, 7, 11},      {1, 1, 2}, 105, 2,   4,  1, 2); };
 #elif defined(FIXED_POINT)
 // ---- Q31: 8-byte complex ------------------------------------------------------------------------------
 struct kP16 { static constexpr PlanDesc D = make_plan(16,   {4, 4},             {2},       1,   128, 31, 1); };
 struct kP64 { static constexpr PlanDesc D = make_plan(64,   {4, 4, 4},          {1, 2},    16,  16,  4,  1); };
-struct kP256 { static constexpr PlanDesc D = make_plan(256,  {4, 4, 4, 4},       {2, 2},    16,  16,  4,  1); };
-struct kP1024 { static constexpr PlanDesc D = make_plan(1024, {4, 4, 4, 4, 4},    {2, 2, 1}, 64,  4,   4,  1); };
-struct kP2048 { static constexpr PlanDesc D = make_plan(2048, {4, 4, 4, 4, 4, 2}, {2, 2, 2}, 128, 2,   4,  1); };
-struct kP1000 { static constexpr PlanDesc D = make_plan(1000, {4, 2, 5, 5, 5},    {2, 2, 1}, 50,  5,   4,  1); };
-struct kP1155 { static constexpr PlanDesc D = make_plan(1155, {3, 5, 7, 11},      {1, 1, 2}, 105, 2,   4,  1); };
+struct kP256 { static constexpr PlanDesc D = make_plan(256,  {4, 4, 4, 4},       {2, 2},    16,  16,  4,  1, 2); };
+struct kP1024 { static constexpr PlanDesc D = make_plan(1024, {4, 4, 4, 4, 4},    {2, 2, 1}, 64,  4,   4,  1, 3); };
+struct kP2048 { static constexpr PlanDesc D = make_plan(2048, {4, 4, 4, 4, 4, 2}, {2, 2, 2}, 128, 2,   4,  1, 2); };
+struct kP1000 { static constexpr PlanDesc D = make_plan(1000, {4, 2, 5, 5, 5},    {2, 2, 1}, 50,  5,   4,  1, 2); };
+struct kP1155 { static constexpr PlanDesc D = make_plan(1155, {3, 5, 7, 11},      {1, 1, 2}, 105, 2,   4,  1, 2); };
 #else
 // ---- float (8-byte complex) and double (16-byte complex) ----------------------------------------------
 static constexpr int kTs = (KF_SCALAR_BYTES == 8) ? 2 : 1;   // double: halve the transforms per CTA
 struct kP16 { static constexpr PlanDesc D = make_plan(16,   {4, 4},             {2},       1,   128, 31, 1); };
 struct kP64 { static constexpr PlanDesc D = make_plan(64,   {4, 4, 4},          {1, 2},    16,  16 / kTs, 4, 1); };
-struct kP256 { static constexpr PlanDesc D = make_plan(256,  {4, 4, 4, 4},       {2, 2},    16,  16 / kTs, 4, 1); };
-struct kP1024 { static constexpr PlanDesc D = make_plan(1024, {4, 4, 4, 4, 4},    {2, 2, 1}, 64,  4 / kTs,  4, 1); };
-struct kP2048 { static constexpr PlanDesc D = make_plan(2048, {4, 4, 4, 4, 4, 2}, {2, 2, 2}, 128, 2 / kTs,  4, 1); };
-struct kP1000 { static constexpr PlanDesc D = make_plan(1000, {4, 2, 5, 5, 5},    {2, 2, 1}, 50,  5,        4, 1); };
-struct kP1155 { static constexpr PlanDesc D = make_plan(1155, {3, 5, 7, 11},      {1, 1, 2}, 105, 2,        4, 1); };
+struct kP256 { static constexpr PlanDesc D = make_plan(256,  {4, 4, 4, 4},       {2, 2},    16,  16 / kTs, 4, 1, 2); };
+struct kP1024 { static constexpr PlanDesc D = make_plan(1024, {4, 4, 4, 4, 4},    {2, 2, 1}, 64,  4 / kTs,  4, 1, 3); };
+struct kP2048 { static constexpr PlanDesc D = make_plan(2048, {4, 4, 4, 4, 4, 2}, {2, 2, 2}, 128, 2 / kTs,  4, 1, 2); };
+struct kP1000 { static constexpr PlanDesc D = make_plan(1000, {4, 2, 5, 5, 5},    {2, 2, 1}, 50,  5,        4, 1, 2); };
+struct kP1155 { static constexpr PlanDesc D = make_plan(1155, {3, 5, 7, 11},      {1, 1, 2}, 105, 2,        4, 1, 2); };
 #endif
 
 

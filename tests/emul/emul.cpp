@@ -5,7 +5,9 @@
 // thread of a CTA becomes one std::thread and __syncthreads() becomes a std::barrier, so the very same
 // template code that nvcc compiles for sm_100a runs here.  This file is never part of the product library and
 // nothing in kissfft_b200/ calls it; GPU parity is established separately by the -m gpu tests.
+#include <atomic>
 #include <barrier>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -13,7 +15,7 @@
 
 #include "../../include/kiss_fft.h"
 #define KF_SCALAR_BYTES ((int)sizeof(kiss_fft_scalar))
-#include "../../kissfft_b200/csrc/kf_body.h"
+#include "../../kissfft_b200/csrc/kf_twtab.h"
 #include "../../kissfft_b200/csrc/kf_plan_list.h"
 
 using namespace kf;
@@ -31,6 +33,20 @@ struct EmuEnv {
     long long nblocks() const { return nblocks_; }
     void sync() const { bar_->arrive_and_wait(); }
     unsigned char* smem() const { return smem_; }
+    // emulated mbarrier: the 8 bytes hold a completion counter; the "bulk copy" is an immediate memcpy
+    static std::atomic<unsigned long long>* ctr(void* bar) { return reinterpret_cast<std::atomic<unsigned long long>*>(bar); }
+    void mbar_init(void* bar) const { ctr(bar)->store(0); }
+    void mbar_fence_init() const {}
+    void bulk_load(void* bar, void* dst, const void* src, unsigned bytes) const
+    {
+        if (bytes % 16 || ((uintptr_t)dst % 16) || ((uintptr_t)src % 16)) abort();   // cp.async.bulk alignment rules
+        std::memcpy(dst, src, bytes);
+        ctr(bar)->fetch_add(1, std::memory_order_release);
+    }
+    void mbar_wait(void* bar, int k) const
+    {
+        while (ctr(bar)->load(std::memory_order_acquire) < (unsigned long long)k + 1) std::this_thread::yield();
+    }
 };
 
 static KParams<AT> mk_params(int nfft, int inverse, const void* in, void* out, long long howmany, long long in_dist,
@@ -45,6 +61,7 @@ static KParams<AT> mk_params(int nfft, int inverse, const void* in, void* out, l
     P.in_stride = in_stride;
     P.tw = (const CT*)tw;
     P.stw = (const CT*)stw;
+    P.gtw = nullptr;
     const CT* h = (const CT*)tw;
     CT z{};
     P.pc.epi3 = AT::load((nfft % 3 == 0) ? h[nfft / 3] : z);
@@ -58,13 +75,14 @@ template <class F>
 static void run_cta_grid(int nthreads, long long nblocks, size_t smem_bytes, F&& body)
 {
     for (long long b = 0; b < nblocks; ++b) {
-        std::vector<unsigned char> smem(smem_bytes + 64, 0xCD);
+        std::vector<unsigned char> smem_store(smem_bytes + 256, 0xCD);
+        unsigned char* smem_al = (unsigned char*)(((uintptr_t)smem_store.data() + 127) & ~(uintptr_t)127);
         std::barrier<> bar(nthreads);
         std::vector<std::thread> th;
         th.reserve(nthreads);
         for (int t = 0; t < nthreads; ++t)
             th.emplace_back([&, t]() {
-                EmuEnv env{t, nthreads, b, nblocks, smem.data(), &bar};
+                EmuEnv env{t, nthreads, b, nblocks, smem_al, &bar};
                 body(env);
             });
         for (auto& x : th) x.join();
@@ -72,15 +90,22 @@ static void run_cta_grid(int nthreads, long long nblocks, size_t smem_bytes, F&&
 }
 
 template <class PT, int MODE>
-static int run_fused(const KParams<AT>& P, long long nblocks)
+static int run_fused(KParams<AT>& P, long long nblocks)
 {
     constexpr PlanDesc D = PT::D;
-    const size_t smem = (size_t)2 * D.tpc * D.pitch() * sizeof(CT);
+    std::vector<CT> gtw = build_gtw<AT, PT>(P.tw);
+    P.gtw = gtw.data();
+    fill_g0tw<AT, PT>(P, P.tw);
+    // like the launcher: only the rows the alignment rules allow; the caller runs the rest on the run-time kernel
+    const long long nfused = fused_rows<AT, PT, MODE>(P);
+    P.howmany = nfused;
+    if (nfused == 0) return 0;
+    const size_t smem = FusedLayout<AT, PT, MODE>::kTotal;
     run_cta_grid(D.threads(), nblocks, smem, [&](EmuEnv& env) { fused_body<AT, PT, MODE>(P, env); });
-    return 0;
+    return (int)nfused;
 }
 
-typedef int (*fused_fn)(const KParams<AT>&, long long);
+typedef int (*fused_fn)(KParams<AT>&, long long);
 struct Entry {
     int N;
     fused_fn fn[4];
@@ -95,7 +120,8 @@ extern "C" int emul_num_plans(void) { return (int)(sizeof(kTable) / sizeof(kTabl
 extern "C" int emul_plan_nfft(int i) { return kTable[i].N; }
 extern "C" int emul_plan_has_mode(int i, int mode) { return kTable[i].fn[mode] != nullptr; }
 
-// returns 0, or -1 when no fused plan is registered for (nfft, mode)
+// returns the number of leading rows processed (the launcher sends the rest to the run-time kernel), or -1 when no
+// fused plan is registered for (nfft, mode)
 extern "C" int emul_fused(int nfft, int mode, int inverse, const void* in, void* out, long long howmany, long long in_dist,
                           long long out_dist, long long in_stride, const void* tw, const void* stw, long long nblocks)
 {

@@ -46,10 +46,21 @@ class Emulator:
         return [(self.lib.emul_plan_nfft(i), [m for m in range(4) if self.lib.emul_plan_has_mode(i, m)])
                 for i in range(self.lib.emul_num_plans())]
 
-    def fused(self, nfft, mode, inverse, inp, out, howmany, in_dist, out_dist, in_stride, tw, stw=None, nblocks=2):
-        rc = self.lib.emul_fused(nfft, mode, int(inverse), _p(inp), _p(out), howmany, in_dist, out_dist, in_stride,
-                                 _p(tw), _p(stw), nblocks)
-        assert rc == 0, "no fused plan for nfft=%d mode=%d" % (nfft, mode)
+    def fused(self, nfft, mode, inverse, inp, out, howmany, in_dist, out_dist, in_stride, tw, stw=None, nblocks=2, factors=None):
+        """mirrors kf_launch.cu: the fused kernel takes the rows its alignment rules allow, the run-time kernel the rest"""
+        done = self.lib.emul_fused(nfft, mode, int(inverse), _p(inp), _p(out), howmany, in_dist, out_dist, in_stride,
+                                   _p(tw), _p(stw), nblocks)
+        assert done >= 0, "no fused plan for nfft=%d mode=%d" % (nfft, mode)
+        if done < howmany:
+            assert factors is not None, "ragged tail needs the run-time kernel"
+            esz = inp.dtype.itemsize * 2
+            tail_in = ctypes.c_void_p(inp.ctypes.data + done * in_dist * esz)
+            tail_out = ctypes.c_void_p(out.ctypes.data + done * out_dist * esz)
+            fac = np.array([x for pm in factors for x in pm], np.int32)
+            rc = self.lib.emul_generic(nfft, mode, int(inverse), _p(fac), len(factors), tail_in, tail_out, howmany - done,
+                                       in_dist, out_dist, in_stride, _p(tw), _p(stw), 2, 32, 1)
+            assert rc == 0
+        return done
 
     def generic(self, nfft, mode, inverse, factors, inp, out, howmany, in_dist, out_dist, in_stride, tw, stw=None,
                 tpc=2, nthreads=32, nblocks=2):

@@ -31,7 +31,7 @@ def test_fused_c2c(env):
             howmany = 11
             x = random_input(tname, (howmany, nfft), 100 + nfft)
             out = np.zeros_like(x)
-            em.fused(nfft, C2C, inverse, x, out, howmany, nfft, nfft, 1, o.twiddles(nfft, inverse))
+            em.fused(nfft, C2C, inverse, x, out, howmany, nfft, nfft, 1, o.twiddles(nfft, inverse), factors=o.factor(nfft))
             check(tname, out, o.fft(x, inverse), nfft)
 
 
@@ -66,12 +66,12 @@ def test_fused_real(env):
         nfft, howmany = 2 * nc, 9
         x = random_input(tname, (howmany, nfft), 300 + nc, complex_=False)
         X = np.zeros((howmany, nc + 1, 2), x.dtype)
-        em.fused(nc, R2C, 0, x, X, howmany, nc, nc + 1, 1, o.twiddles(nc, 0), o.super_twiddles(nc, 0))
+        em.fused(nc, R2C, 0, x, X, howmany, nc, nc + 1, 1, o.twiddles(nc, 0), o.super_twiddles(nc, 0), factors=o.factor(nc))
         want = o.fftr(x)
         check(tname, X, want, nfft)
         spec = want if tname in TOL else random_input(tname, (howmany, nc + 1), 301 + nc)
         y = np.zeros((howmany, nfft), x.dtype)
-        em.fused(nc, C2R, 1, spec, y, howmany, nc + 1, nc, 1, o.twiddles(nc, 1), o.super_twiddles(nc, 1))
+        em.fused(nc, C2R, 1, spec, y, howmany, nc + 1, nc, 1, o.twiddles(nc, 1), o.super_twiddles(nc, 1), factors=o.factor(nc))
         check(tname, y, o.fftri(spec), nfft)
 
 

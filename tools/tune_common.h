@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include "../kissfft_b200/csrc/kf_twtab.h"
+
 typedef kf::Arith<kiss_fft_scalar> AT;
 typedef AT::C CT;
 
@@ -18,12 +20,24 @@ struct TuneEntry {
     size_t smem;
     const void* kernel;
     void (*launch)(const kf::KParams<AT>&, unsigned grid, size_t smem);
+    void (*prepare)(kf::KParams<AT>&, const CT* h_tw, CT** d_gtw);
 };
 
 template <class PT, int MODE>
 static void launch_variant(const kf::KParams<AT>& P, unsigned grid, size_t smem)
 {
     kf::kf_fused_kernel<AT, PT, MODE><<<grid, PT::D.threads(), smem>>>(P);
+}
+
+template <class PT>
+static void prepare_variant(kf::KParams<AT>& P, const CT* h_tw, CT** d_gtw)
+{
+    std::vector<CT> tab = kf::build_gtw<AT, PT>(h_tw);
+    if (*d_gtw) cudaFree(*d_gtw);
+    cudaMalloc(d_gtw, tab.size() * sizeof(CT));
+    cudaMemcpy(*d_gtw, tab.data(), tab.size() * sizeof(CT), cudaMemcpyHostToDevice);
+    P.gtw = *d_gtw;
+    kf::fill_g0tw<AT, PT>(P, h_tw);
 }
 
 template <class PT, int MODE>
@@ -34,9 +48,10 @@ static TuneEntry make_entry(const char* label)
     e.label = label;
     e.threads = D.threads();
     e.tpc = D.tpc;
-    e.smem = (D.G >= 2 || MODE == kf::kR2C || MODE == kf::kC2R) ? (size_t)2 * D.tpc * D.pitch() * sizeof(CT) : 0;
+    e.smem = kf::FusedLayout<AT, PT, MODE>::kTotal;
     e.kernel = (const void*)kf::kf_fused_kernel<AT, PT, MODE>;
     e.launch = launch_variant<PT, MODE>;
+    e.prepare = prepare_variant<PT>;
     return e;
 }
 
@@ -63,6 +78,8 @@ static int tune_main(int argc, char** argv, std::vector<TuneEntry>& vars, int nf
 {
     const long long batch = argc > 1 ? atoll(argv[1]) : 65536;
     const int iters = argc > 2 ? atoi(argv[2]) : 10;
+    const char* filter = argc > 3 ? argv[3] : nullptr;
+    CT* d_gtw = nullptr;
     const bool real_in = (mode == kf::kR2C), real_out = (mode == kf::kC2R);
     // element counts per row in complex units (real rows are packed complex of nfft)
     const long long in_row = real_out ? nfft + 1 : nfft, out_row = real_in ? nfft + 1 : nfft;
@@ -120,6 +137,8 @@ static int tune_main(int argc, char** argv, std::vector<TuneEntry>& vars, int nf
     std::vector<CT> h_ref((size_t)out_row * 64), h_out((size_t)out_row * 64);
     bool have_ref = false;
     for (auto& v : vars) {
+        if (filter && v.label.find(filter) == std::string::npos) continue;
+        v.prepare(P, h_tw.data(), &d_gtw);
         if (cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem) != cudaSuccess) {
             cudaGetLastError();
             printf("{\"variant\": \"%s\", \"error\": \"smem %zu too large\"}\n", v.label.c_str(), v.smem);
