@@ -56,6 +56,13 @@ int KISS_FFT_API kiss_fftnd_dev(kiss_fftnd_cfg cfg, const kiss_fft_cpx *d_in, ki
 int KISS_FFT_API kiss_fft_axis_pass_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, size_t ncols,
                                         size_t col_stride, void *stream);
 
+/* the same axis pass over `nplanes` independent planes in one launch: plane p, column c reads
+ * d_in[p*in_plane_dist + c + j*col_stride] (j < nfft) and writes row d_out[p*out_plane_dist + c*nfft + k].
+ * Building block of the slab-decomposed multi-GPU 3-D transform (kissfft_b200/slab.py). */
+int KISS_FFT_API kiss_fft_planes_pass_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, size_t nplanes,
+                                          size_t ncols, size_t col_stride, size_t in_plane_dist, size_t out_plane_dist,
+                                          void *stream);
+
 /* kiss_fftndr / kiss_fftndri on device buffers (kiss_fftndr.c:86-132) */
 int KISS_FFT_API kiss_fftndr_dev(kiss_fftndr_cfg cfg, const kiss_fft_scalar *d_time, kiss_fft_cpx *d_freq, void *stream);
 int KISS_FFT_API kiss_fftndri_dev(kiss_fftndr_cfg cfg, const kiss_fft_cpx *d_freq, kiss_fft_scalar *d_time, void *stream);

@@ -21,7 +21,7 @@ API_SYMBOLS = (
     "kiss_fftr_alloc", "kiss_fftr", "kiss_fftri",
     "kiss_fftnd_alloc", "kiss_fftnd",
     "kiss_fftndr_alloc", "kiss_fftndr", "kiss_fftndri",
-    "kiss_fft_batch_dev", "kiss_fftr_batch_dev", "kiss_fftri_batch_dev", "kiss_fftnd_dev", "kiss_fft_axis_pass_dev",
+    "kiss_fft_batch_dev", "kiss_fftr_batch_dev", "kiss_fftri_batch_dev", "kiss_fftnd_dev", "kiss_fft_axis_pass_dev", "kiss_fft_planes_pass_dev",
     "kiss_fftndr_dev", "kiss_fftndri_dev", "kiss_fft_batch", "kiss_fftr_batch", "kiss_fftri_batch",
     "kiss_fft_cuda_last_error", "kiss_fft_cuda_launch_count", "kiss_fft_cuda_plan_kind", "kiss_fft_cuda_scalar_bytes",
     "kiss_fft_cuda_is_fixed_point", "kiss_fft_cuda_force_generic",
@@ -81,6 +81,7 @@ class KissFFT:
         L.kiss_fftri_batch_dev.argtypes = [vp, vp, vp, sz, sz, sz, vp]
         L.kiss_fftnd_dev.argtypes = [vp, vp, vp, vp, vp]
         L.kiss_fft_axis_pass_dev.argtypes = [vp, vp, vp, sz, sz, vp]
+        L.kiss_fft_planes_pass_dev.argtypes = [vp, vp, vp, sz, sz, sz, sz, sz, vp]
         L.kiss_fftndr_dev.argtypes = [vp, vp, vp, vp]
         L.kiss_fftndri_dev.argtypes = [vp, vp, vp, vp]
         L.kiss_fft_batch.argtypes = [vp, vp, vp, sz]
@@ -154,6 +155,10 @@ class KissFFT:
     def axis_pass_dev(self, cfg, d_in, d_out, ncols, col_stride, stream=0):
         self._check(self.lib.kiss_fft_axis_pass_dev(cfg, _ptr(d_in), _ptr(d_out), ncols, col_stride,
                                                     ctypes.c_void_p(stream)), "kiss_fft_axis_pass_dev")
+
+    def planes_pass_dev(self, cfg, d_in, d_out, nplanes, ncols, col_stride, in_plane_dist, out_plane_dist, stream=0):
+        self._check(self.lib.kiss_fft_planes_pass_dev(cfg, _ptr(d_in), _ptr(d_out), nplanes, ncols, col_stride, in_plane_dist,
+                                                      out_plane_dist, ctypes.c_void_p(stream)), "kiss_fft_planes_pass_dev")
 
     def fftndr_dev(self, cfg, d_time, d_freq, stream=0):
         self._check(self.lib.kiss_fftndr_dev(cfg, _ptr(d_time), _ptr(d_freq), ctypes.c_void_p(stream)), "kiss_fftndr_dev")

@@ -23,7 +23,7 @@ HOSTCC = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
 TYPES = ("float", "double", "int16_t", "int32_t")
 TYPEFLAGS = {
     "float": ["-Dkiss_fft_scalar=float"],
-    "double": ["-Dkiss_fft_scalar=double"],
+    "double": ["-Dkiss_fft_scalar=double", "-DKF_IS_DOUBLE"],
     "int16_t": ["-DFIXED_POINT=16"],
     "int32_t": ["-DFIXED_POINT=32"],
 }

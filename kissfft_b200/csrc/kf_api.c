@@ -396,7 +396,8 @@ void kiss_fft_cleanup(void)
         cudaSetDevice(e->device);
         cudaFree((void *)e->plan.d_tw);
         if (e->plan.d_stw) cudaFree((void *)e->plan.d_stw);
-        if (e->plan.d_gtw) cudaFree(e->plan.d_gtw);
+        for (int m = 0; m < 4; ++m)
+            if (e->plan.d_gtw[m]) cudaFree(e->plan.d_gtw[m]);
         free(e->h_tw);
         free(e);
         e = n;
@@ -497,6 +498,20 @@ int kiss_fft_axis_pass_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_
     /* column i: elements d_in[i + j*col_stride]; written as row i: d_out[i*nfft + k]  (kiss_fftnd.c:176-177) */
     const int mode = (col_stride == 1 && ncols == 1) ? KFCU_C2C : KFCU_C2C_COL;
     KF_CHECK(kfcu_exec(mode, (kfcu_plan *)&dp->plan, d_in, d_out, (long long)ncols, 1, (long long)cfg->nfft, (long long)col_stride, stream));
+    return 0;
+}
+
+int kiss_fft_planes_pass_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, size_t nplanes, size_t ncols,
+                             size_t col_stride, size_t in_plane_dist, size_t out_plane_dist, void *stream)
+{
+    if (!cfg || cfg->magic != KF_MAGIC_1D || !d_in || !d_out || col_stride < 1) {
+        KF_ERROR("kiss_fft_planes_pass_dev: bad argument");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    const kf_devplan *dp;
+    KF_CHECK(kf_get_devplan(cfg, NULL, &dp));
+    KF_CHECK(kfcu_exec_planes((kfcu_plan *)&dp->plan, d_in, d_out, (long long)nplanes, (long long)ncols, (long long)col_stride,
+                              (long long)in_plane_dist, (long long)out_plane_dist, stream));
     return 0;
 }
 

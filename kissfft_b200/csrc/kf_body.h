@@ -29,6 +29,11 @@ struct KParams {
     long long howmany;
     long long in_dist, out_dist; // distance between consecutive transforms, in complex elements of each side
     long long in_stride;         // element stride of the input (kiss_fft_stride's in_stride)
+    // column mode only: transforms are numbered plane-major, `ncols` columns per plane; plane p starts at
+    // in + p*in_pdist / out + p*out_pdist and column c of it at + c*in_dist / + c*out_dist.  ncols == 0: one plane.
+    long long ncols, in_pdist, out_pdist;
+    KF_HD long long in_off(long long b) const { return ncols > 0 ? (b / ncols) * in_pdist + (b % ncols) * in_dist : b * in_dist; }
+    KF_HD long long out_off(long long b) const { return ncols > 0 ? (b / ncols) * out_pdist + (b % ncols) * out_dist : b * out_dist; }
     const typename A::C* tw;     // N twiddles (kR2C/kC2R: of the ncfft-point sub-transform)
     const typename A::C* stw;    // ncfft/2 split twiddles (kiss_fftr.c:53-59), real modes only
     const typename A::C* gtw;    // per-group stage-twiddle tables of the fused plan (kf_twtab.h), unused by the generic kernel
@@ -241,8 +246,8 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             static_assert(D.G >= 2, "column mode needs a shared-memory exchange");
             const int cteam = tid % D.tpc, ct = tid / D.tpc;
             const long long cb = tile * D.tpc + cteam;
-            SrcGlobal<A, false> src{P.in + cb * P.in_dist, P.in_stride};
-            DstGlobal<A> dst{P.out + b * P.out_dist};
+            SrcGlobal<A, false> src{P.in + P.in_off(cb), P.in_stride};
+            DstGlobal<A> dst{P.out + P.out_off(b)};
             C* cb1 = (par ? bufA : bufB) + cteam * kPitch;
             run_group<A, D, 0, SrcGlobal<A, false>, DstGlobal<A>>(ct, cb < P.howmany, src, dst, nullptr, cb1, tw, P.pc, P.inverse);
             env.sync();
@@ -307,7 +312,7 @@ KF_HD cx<typename A::R> generic_output(const typename A::C* rd, int u, int off, 
         if (twidx >= N) twidx -= N;
         X sq = A::load(rd[(u * p + q) * F + off]);
         sq = X{A::divk_rt(sq.r, p), A::divk_rt(sq.i, p)};
-        acc = cadd<A>(acc, A::cmul(sq, tw.get(twidx)));
+        acc = cadd<A>(acc, A::cmul_bf(sq, tw.get(twidx)));
     }
     return cwrap<A>(acc);
 }
@@ -344,7 +349,7 @@ KF_HD void generic_body(const GParams<A>& G, Env& env)
         } else if (mode == kC2CCol) {
             for (int i = tid; i < tpc * N; i += nthr) {
                 const int bl = i % tpc, n = i / tpc;
-                if (bl < nb) buf0[bl * N + n] = P.in[(bbase + bl) * P.in_dist + (long long)n * P.in_stride];
+                if (bl < nb) buf0[bl * N + n] = P.in[P.in_off(bbase + bl) + (long long)n * P.in_stride];
             }
         } else {
             for (int i = tid; i < nb * N; i += nthr) {
@@ -403,7 +408,7 @@ KF_HD void generic_body(const GParams<A>& G, Env& env)
         } else {
             for (int i = tid; i < nb * N; i += nthr) {
                 const int bl = i / N, k = i % N;
-                P.out[(bbase + bl) * P.out_dist + k] = rd[i];
+                P.out[P.out_off(bbase + bl) + k] = rd[i];
             }
         }
         env.sync();

@@ -104,7 +104,7 @@ KF_HD void bfly_generic_fixed(cx<typename A::R>* v, int ks, const TwTab<A>& tw)
         static_for<p - 1>([&](auto Qm1) {
             twidx += Fs * k;
             if (twidx >= N) twidx -= N;
-            acc = cadd<A>(acc, A::cmul(sc[decltype(Qm1)::value + 1], tw.get(twidx)));
+            acc = cadd<A>(acc, A::cmul_bf(sc[decltype(Qm1)::value + 1], tw.get(twidx)));
         });
         v[q1] = cwrap<A>(acc);
     });
@@ -126,7 +126,7 @@ KF_HD void bfly_generic_float(cx<typename A::R>* v, int slot0, int w, const TwTa
     y[0] = v[0];
     static_for<p - 1>([&](auto Qm1) {
         constexpr int q = decltype(Qm1)::value + 1;
-        y[q] = TW1 ? v[q] : A::cmul(v[q], stage_tw<A, D, g>(tw, slot0 + q - 1, w));
+        y[q] = TW1 ? v[q] : A::cmul_bf(v[q], stage_tw<A, D, g>(tw, slot0 + q - 1, w));
     });
     X a[h + 1], b[h + 1];
     X sum = y[0];

@@ -25,8 +25,8 @@ typedef struct kfcu_plan {
     const void *d_tw;  /* nfft complex twiddles in device memory */
     const void *d_stw; /* nfft/2 split twiddles (real modes) or NULL */
     const void *h_tw;  /* the same twiddles on the host (for the butterfly constants) */
-    void *d_gtw;       /* per-group stage-twiddle tables of the fused plan; created lazily by kf_launch.cu, freed by
-                          kiss_fft_cleanup together with d_tw */
+    void *d_gtw[4];    /* per-group stage-twiddle tables of the fused plan serving each mode (KFCU_C2C..KFCU_C2R);
+                          created lazily by kf_launch.cu, freed by kiss_fft_cleanup together with d_tw */
 } kfcu_plan;
 
 /* Runs `howmany` transforms. Distances are in complex elements of the respective side (for KFCU_R2C the input
@@ -34,6 +34,11 @@ typedef struct kfcu_plan {
  * Returns 0 or a cudaError_t value; KFCU_E* (negative) for argument errors. */
 int kfcu_exec(int mode, kfcu_plan *plan, const void *d_in, void *d_out, long long howmany, long long in_dist,
               long long out_dist, long long in_stride, void *stream);
+
+/* KFCU_C2C_COL over `nplanes` independent planes (slab decomposition): plane p, column c reads
+ * in[p*in_pdist + c + j*col_stride], j < nfft, and writes out[p*out_pdist + c*nfft + k] */
+int kfcu_exec_planes(kfcu_plan *plan, const void *d_in, void *d_out, long long nplanes, long long ncols, long long col_stride,
+                     long long in_pdist, long long out_pdist, void *stream);
 
 /* out[c][r] = in[r][c] for a rows x cols array of complex elements (kiss_fftndr's bin-major <-> row-major
  * scatter loops, kiss_fftndr.c:101-102, 107-108) */

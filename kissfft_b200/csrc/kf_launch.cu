@@ -48,6 +48,8 @@ static KParams<AT> make_params(const kfcu_plan* pl, const void* d_in, void* d_ou
                                long long out_dist, long long in_stride)
 {
     KParams<AT> P;
+    P.ncols = 0;
+    P.in_pdist = P.out_pdist = 0;
     P.in = (const CT*)d_in;
     P.out = (CT*)d_out;
     P.howmany = howmany;
@@ -89,19 +91,19 @@ static int launch_fused(kfcu_plan* pl, KParams<AT>& P, cudaStream_t st)
 {
     constexpr PlanDesc D = PT::D;
     // stage-twiddle tables of this plan: built once per (device plan) from the host twiddles, then cached
-    if (D.gtw_total() > 0 && !pl->d_gtw) {
+    if (D.gtw_total() > 0 && !pl->d_gtw[MODE]) {
         std::lock_guard<std::mutex> lk(g_gtw_mutex);
-        if (!pl->d_gtw) {
+        if (!pl->d_gtw[MODE]) {
             std::vector<CT> tab = build_gtw<AT, PT>((const CT*)pl->h_tw);
             void* d = nullptr;
             cudaError_t e = cudaMalloc(&d, tab.size() * sizeof(CT));
             if (e != cudaSuccess) return (int)e;
             e = cudaMemcpy(d, tab.data(), tab.size() * sizeof(CT), cudaMemcpyHostToDevice);
             if (e != cudaSuccess) { cudaFree(d); return (int)e; }
-            pl->d_gtw = d;
+            pl->d_gtw[MODE] = d;
         }
     }
-    P.gtw = (const CT*)pl->d_gtw;
+    P.gtw = (const CT*)pl->d_gtw[MODE];
     fill_g0tw<AT, PT>(P, (const CT*)pl->h_tw);
     // rows the fused kernel may take (alignment rules of the bulk-async ring); the remainder, normally none,
     // goes to the run-time kernel
@@ -113,6 +115,7 @@ static int launch_fused(kfcu_plan* pl, KParams<AT>& P, cudaStream_t st)
     }
     auto kern = kf_fused_kernel<AT, PT, MODE>;
     constexpr size_t smem = FusedLayout<AT, PT, MODE>::kTotal;
+    static_assert(smem <= 232448, "plan exceeds the 227 KiB of shared memory a CTA can opt in to");
     static int blocks_per_sm[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -143,6 +146,11 @@ struct FusedEntry {
 #define KF_FUSED_ALL(PT) { PT::D.N, { launch_fused<PT, kC2C>, launch_fused<PT, kC2CCol>, launch_fused<PT, kR2C>, launch_fused<PT, kC2R> } }
 #define KF_FUSED_C2C(PT) { PT::D.N, { launch_fused<PT, kC2C>, nullptr, nullptr, nullptr } }
 #define KF_FUSED_C2C_REAL(PT) { PT::D.N, { launch_fused<PT, kC2C>, nullptr, launch_fused<PT, kR2C>, launch_fused<PT, kC2R> } }
+#define KF_FUSED_C2C_COL(PT) { PT::D.N, { launch_fused<PT, kC2C>, launch_fused<PT, kC2CCol>, nullptr, nullptr } }
+#define KF_FUSED_COL(PT) { PT::D.N, { nullptr, launch_fused<PT, kC2CCol>, nullptr, nullptr } }
+#define KF_FUSED_R2C(PT) { PT::D.N, { nullptr, nullptr, launch_fused<PT, kR2C>, nullptr } }
+#define KF_FUSED_C2R(PT) { PT::D.N, { nullptr, nullptr, nullptr, launch_fused<PT, kC2R> } }
+#define KF_FUSED_REAL(PT) { PT::D.N, { nullptr, nullptr, launch_fused<PT, kR2C>, launch_fused<PT, kC2R> } }
 
 #include "kf_plans.inc"
 
@@ -208,6 +216,20 @@ extern "C" int kfcu_exec(int mode, kfcu_plan* plan, const void* d_in, void* d_ou
     KParams<AT> P = make_params(plan, d_in, d_out, howmany, in_dist, out_dist, in_stride);
     if (const FusedEntry* fe = find_fused(plan->nfft, mode)) return fe->fn[mode](plan, P, st);
     return launch_generic(mode, plan, P, st);
+}
+
+// plane-batched column pass: plane p, column c: in[p*in_pdist + c + j*col_stride] (j < nfft) -> out[p*out_pdist + c*nfft + k]
+extern "C" int kfcu_exec_planes(kfcu_plan* plan, const void* d_in, void* d_out, long long nplanes, long long ncols,
+                                long long col_stride, long long in_pdist, long long out_pdist, void* stream)
+{
+    if (!plan || !d_in || !d_out || nplanes < 0 || ncols < 0) return KFCU_EINVAL;
+    if (nplanes == 0 || ncols == 0) return 0;
+    KParams<AT> P = make_params(plan, d_in, d_out, nplanes * ncols, 1, plan->nfft, col_stride);
+    P.ncols = ncols;
+    P.in_pdist = in_pdist;
+    P.out_pdist = out_pdist;
+    if (const FusedEntry* fe = find_fused(plan->nfft, kC2CCol)) return fe->fn[kC2CCol](plan, P, (cudaStream_t)stream);
+    return launch_generic(kC2CCol, plan, P, (cudaStream_t)stream);
 }
 
 extern "C" int kfcu_transpose(const void* d_in, void* d_out, long long rows, long long cols, void* stream)

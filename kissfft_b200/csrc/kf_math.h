@@ -61,6 +61,8 @@ struct ArithFloat {
     {
         return cx<R>{a.r * b.r - a.i * b.i, a.r * b.i + a.i * b.r};
     }
+    static KF_HD cx<R> cmul_bf(const cx<R>& a, const cx<R>& b) { return cmul(a, b); }
+    static KF_HD R smul_bf(R a, R b) { return a * b; }
 };
 template <>
 struct Arith<float> : ArithFloat<float> {};
@@ -90,14 +92,24 @@ struct Arith<int16_t> {
     static KF_HD R sign_of(int inverse) { return inverse ? -1 : 1; }
     static KF_HD R wrap(R a) { return (R)(int16_t)a; }
     static KF_HD R sround(int32_t x) { return (R)(int16_t)((x + (1 << (kFrac - 1))) >> kFrac); }   // :65
+    // same value without re-creating the int16 truncation: only where the result provably fits in int16 --
+    //   * x * (SAMP_MAX/k), k >= 2, |x| <= 32768                       -> |result| <= 16384
+    //   * a * twiddle inside a butterfly, a pre-scaled by 1/p (p >= 2)  -> |result| <= 23171 (|a| <= 16384*sqrt2, |tw| ~ 32767)
+    //   * S_MUL of a butterfly-internal sum with a twiddle component    -> |result| <= 30894
+    static KF_HD R sround_fit(int32_t x) { return (R)((x + (1 << (kFrac - 1))) >> kFrac); }
     static KF_HD R smul(R a, R b) { return sround(a * b); }                                        // :67
+    static KF_HD R smul_bf(R a, R b) { return sround_fit(a * b); }
     static KF_HD R half(R a) { return a >> 1; }                                                    // :130
     template <int K>
-    static KF_HD R divk(R a) { return sround(a * (kSampMax / K)); }                                // :73-78
-    static KF_HD R divk_rt(R a, int k) { return sround(a * (kSampMax / k)); }
+    static KF_HD R divk(R a) { return sround_fit(a * (kSampMax / K)); }                            // :73-78
+    static KF_HD R divk_rt(R a, int k) { return sround_fit(a * (kSampMax / k)); }
     static KF_HD cx<R> cmul(const cx<R>& a, const cx<R>& b)                                        // :69-71
     {
         return cx<R>{sround(a.r * b.r - a.i * b.i), sround(a.r * b.i + a.i * b.r)};
+    }
+    static KF_HD cx<R> cmul_bf(const cx<R>& a, const cx<R>& b)
+    {
+        return cx<R>{sround_fit(a.r * b.r - a.i * b.i), sround_fit(a.r * b.i + a.i * b.r)};
     }
 };
 
@@ -130,6 +142,8 @@ struct Arith<int32_t> {
     {
         return cx<R>{sround((int64_t)a.r * b.r - (int64_t)a.i * b.i), sround((int64_t)a.r * b.i + (int64_t)a.i * b.r)};
     }
+    static KF_HD cx<R> cmul_bf(const cx<R>& a, const cx<R>& b) { return cmul(a, b); }
+    static KF_HD R smul_bf(R a, R b) { return smul(a, b); }
 };
 
 template <class A>
@@ -167,7 +181,7 @@ KF_HD void bfly2(cx<typename A::R>* v, const cx<typename A::R>& t1)
 {
     typedef cx<typename A::R> X;
     X a = cfixdiv<A, 2>(v[0]), b = cfixdiv<A, 2>(v[1]);
-    X t = TW1 ? b : A::cmul(b, t1);
+    X t = TW1 ? b : A::cmul_bf(b, t1);
     v[1] = cwrap<A>(csub<A>(a, t));
     v[0] = cwrap<A>(cadd<A>(a, t));
 }
@@ -179,9 +193,9 @@ KF_HD void bfly4(cx<typename A::R>* v, const cx<typename A::R>& t1, const cx<typ
 {
     typedef cx<typename A::R> X;
     X f0 = cfixdiv<A, 4>(v[0]), f1 = cfixdiv<A, 4>(v[1]), f2 = cfixdiv<A, 4>(v[2]), f3 = cfixdiv<A, 4>(v[3]);
-    X s0 = TW1 ? f1 : A::cmul(f1, t1);
-    X s1 = TW1 ? f2 : A::cmul(f2, t2);
-    X s2 = TW1 ? f3 : A::cmul(f3, t3);
+    X s0 = TW1 ? f1 : A::cmul_bf(f1, t1);
+    X s1 = TW1 ? f2 : A::cmul_bf(f2, t2);
+    X s2 = TW1 ? f3 : A::cmul_bf(f3, t3);
     X s5 = csub<A>(f0, s1);
     f0 = cadd<A>(f0, s1);
     X s3 = cadd<A>(s0, s2);
@@ -201,13 +215,13 @@ KF_HD void bfly3(cx<typename A::R>* v, const cx<typename A::R>& t1, const cx<typ
 {
     typedef cx<typename A::R> X;
     X f0 = cfixdiv<A, 3>(v[0]), f1 = cfixdiv<A, 3>(v[1]), f2 = cfixdiv<A, 3>(v[2]);
-    X s1 = TW1 ? f1 : A::cmul(f1, t1);
-    X s2 = TW1 ? f2 : A::cmul(f2, t2);
+    X s1 = TW1 ? f1 : A::cmul_bf(f1, t1);
+    X s2 = TW1 ? f2 : A::cmul_bf(f2, t2);
     X s3 = cwrap<A>(cadd<A>(s1, s2));
     X s0 = cwrap<A>(csub<A>(s1, s2));
     X fm{A::sub(f0.r, A::half(s3.r)), A::sub(f0.i, A::half(s3.i))};
-    s0.r = A::smul(s0.r, epi3i);   // C_MULBYSCALAR
-    s0.i = A::smul(s0.i, epi3i);
+    s0.r = A::smul_bf(s0.r, epi3i);   // C_MULBYSCALAR
+    s0.i = A::smul_bf(s0.i, epi3i);
     v[0] = cwrap<A>(cadd<A>(f0, s3));
     v[2] = cwrap<A>(X{A::add(fm.r, s0.i), A::sub(fm.i, s0.r)});
     v[1] = cwrap<A>(X{A::sub(fm.r, s0.i), A::add(fm.i, s0.r)});
@@ -223,26 +237,26 @@ KF_HD void bfly5(cx<typename A::R>* v, const cx<typename A::R>& t1, const cx<typ
     typedef cx<R> X;
     X f0 = cfixdiv<A, 5>(v[0]), f1 = cfixdiv<A, 5>(v[1]), f2 = cfixdiv<A, 5>(v[2]), f3 = cfixdiv<A, 5>(v[3]),
       f4 = cfixdiv<A, 5>(v[4]);
-    X s1 = TW1 ? f1 : A::cmul(f1, t1);
-    X s2 = TW1 ? f2 : A::cmul(f2, t2);
-    X s3 = TW1 ? f3 : A::cmul(f3, t3);
-    X s4 = TW1 ? f4 : A::cmul(f4, t4);
+    X s1 = TW1 ? f1 : A::cmul_bf(f1, t1);
+    X s2 = TW1 ? f2 : A::cmul_bf(f2, t2);
+    X s3 = TW1 ? f3 : A::cmul_bf(f3, t3);
+    X s4 = TW1 ? f4 : A::cmul_bf(f4, t4);
     X s7 = cwrap<A>(cadd<A>(s1, s4)), s10 = cwrap<A>(csub<A>(s1, s4));
     X s8 = cwrap<A>(cadd<A>(s2, s3)), s9 = cwrap<A>(csub<A>(s2, s3));
 
     v[0] = cwrap<A>(X{A::add(f0.r, A::add(s7.r, s8.r)), A::add(f0.i, A::add(s7.i, s8.i))});
 
-    X s5{A::add(A::add(f0.r, A::smul(s7.r, ya.r)), A::smul(s8.r, yb.r)),
-         A::add(A::add(f0.i, A::smul(s7.i, ya.r)), A::smul(s8.i, yb.r))};
-    X s6{A::add(A::smul(s10.i, ya.i), A::smul(s9.i, yb.i)),
-         A::sub(A::neg(A::smul(s10.r, ya.i)), A::smul(s9.r, yb.i))};
+    X s5{A::add(A::add(f0.r, A::smul_bf(s7.r, ya.r)), A::smul_bf(s8.r, yb.r)),
+         A::add(A::add(f0.i, A::smul_bf(s7.i, ya.r)), A::smul_bf(s8.i, yb.r))};
+    X s6{A::add(A::smul_bf(s10.i, ya.i), A::smul_bf(s9.i, yb.i)),
+         A::sub(A::neg(A::smul_bf(s10.r, ya.i)), A::smul_bf(s9.r, yb.i))};
     v[1] = cwrap<A>(csub<A>(s5, s6));
     v[4] = cwrap<A>(cadd<A>(s5, s6));
 
-    X s11{A::add(A::add(f0.r, A::smul(s7.r, yb.r)), A::smul(s8.r, ya.r)),
-          A::add(A::add(f0.i, A::smul(s7.i, yb.r)), A::smul(s8.i, ya.r))};
-    X s12{A::add(A::neg(A::smul(s10.i, yb.i)), A::smul(s9.i, ya.i)),
-          A::sub(A::smul(s10.r, yb.i), A::smul(s9.r, ya.i))};
+    X s11{A::add(A::add(f0.r, A::smul_bf(s7.r, yb.r)), A::smul_bf(s8.r, ya.r)),
+          A::add(A::add(f0.i, A::smul_bf(s7.i, yb.r)), A::smul_bf(s8.i, ya.r))};
+    X s12{A::add(A::neg(A::smul_bf(s10.i, yb.i)), A::smul_bf(s9.i, ya.i)),
+          A::sub(A::smul_bf(s10.r, yb.i), A::smul_bf(s9.r, ya.i))};
     v[2] = cwrap<A>(cadd<A>(s11, s12));
     v[3] = cwrap<A>(csub<A>(s11, s12));
 }

@@ -93,15 +93,15 @@ struct PlanDesc {
     // table gtw[g][slot][w] laid out with the work item w innermost: a warp's fetch of one slot is one contiguous,
     // immediate-addressed vector load instead of a gather over the N-entry twiddle array.  Group 0 has k' == 0:
     // its slots are plan constants and travel in the kernel parameters (constant bank).
-    KF_CE int nslots_stage(int g, int s) const { return (R(g) / p[s]) * (p[s] - 1); }
+    // butterflies of stage s that agree in the digits of the stages above s (already transformed inside the group)
+    // have the same kabove and therefore the same twiddles: one slot set per combination of upper digits
+    KF_CE int nupper(int g, int s) const { return R(g) / (W(g, s) * p[s]); }
+    KF_CE int nslots_stage(int g, int s) const { return nupper(g, s) * (p[s] - 1); }
     KF_CE int slot(int g, int s, int e) const   // first slot of the butterfly whose base register is e
     {
         int n = 0;
         for (int j = s_hi(g); j > s; --j) n += nslots_stage(g, j);
-        int cnt = 0;
-        for (int e2 = 0; e2 < e; ++e2)
-            if (digit(g, s, e2) == 0) ++cnt;
-        return n + cnt * (p[s] - 1);
+        return n + (e / (W(g, s) * p[s])) * (p[s] - 1);
     }
     KF_CE int nslots(int g) const
     {

@@ -30,45 +30,63 @@ constexpr PlanDesc make_plan(int N, std::initializer_list<int> radices, std::ini
     return d;
 }
 
+// Tuned on B200 with tools/tune_gen.py (logs under profiles/).  Fixed-point plans keep kf_factor's radix order
+// (bit-exactness); float/double plans may reorder / regroup radices (parity there is relative RMS).
+#define KF_PLAN(tag, ...) struct tag { static constexpr PlanDesc D = make_plan(__VA_ARGS__); }
+
+// small lengths shared by all datatypes (exercise G == 1, G == 2 and the column mode in the tests)
+KF_PLAN(kP16,  16,  {4, 4},       {2},    1,  128, 31, 1, 0);
+KF_PLAN(kP64,  64,  {4, 4, 4},    {1, 2}, 16, 8,   4,  1, 0);
+KF_PLAN(kP256, 256, {4, 4, 4, 4}, {2, 2}, 16, 8,   4,  1, 2);
+
 #if defined(FIXED_POINT) && (FIXED_POINT == 16)
-// ---- Q15: 4-byte complex ------------------------------------------------------------------------------
-struct kP16 { static constexpr PlanDesc D = make_plan(16,   {4, 4},             {2},       1,   128, 31, 1); };
-struct kP64 { static constexpr PlanDesc D = make_plan(64,   {4, 4, 4},          {1, 2},    16,  16,  4,  1); };
-struct kP256 { static constexpr PlanDesc D = make_plan(256,  {4, 4, 4, 4},       {2, 2},    16,  16,  4,  1, 2); };
-struct kP1024 { static constexpr PlanDesc D = make_plan(1024, {4, 4, 4, 4, 4},    {2, 2, 1}, 64,  4,   4,  1, 3); };
-struct kP2048 { static constexpr PlanDesc D = make_plan(2048, {4, 4, 4, 4, 4, 2}, {2, 2, 2}, 128, 2,   4,  1, 2); };
-struct kP1000 { static constexpr PlanDesc D = make_plan(1000, {4, 2, 5, 5, 5},    {2, 2, 1}, 50,  5,   4,  1, 2); };
-struct kP1155 { static constexpr PlanDesc D = make_plan(1155, {3, 5, 7, 11},      {1, 1, 2}, 105, 2,   4,  1, 2); };
-#elif defined(FIXED_POINT)
-// ---- Q31: 8-byte complex ------------------------------------------------------------------------------
-struct kP16 { static constexpr PlanDesc D = make_plan(16,   {4, 4},             {2},       1,   128, 31, 1); };
-struct kP64 { static constexpr PlanDesc D = make_plan(64,   {4, 4, 4},          {1, 2},    16,  16,  4,  1); };
-struct kP256 { static constexpr PlanDesc D = make_plan(256,  {4, 4, 4, 4},       {2, 2},    16,  16,  4,  1, 2); };
-struct kP1024 { static constexpr PlanDesc D = make_plan(1024, {4, 4, 4, 4, 4},    {2, 2, 1}, 64,  4,   4,  1, 3); };
-struct kP2048 { static constexpr PlanDesc D = make_plan(2048, {4, 4, 4, 4, 4, 2}, {2, 2, 2}, 128, 2,   4,  1, 2); };
-struct kP1000 { static constexpr PlanDesc D = make_plan(1000, {4, 2, 5, 5, 5},    {2, 2, 1}, 50,  5,   4,  1, 2); };
-struct kP1155 { static constexpr PlanDesc D = make_plan(1155, {3, 5, 7, 11},      {1, 1, 2}, 105, 2,   4,  1, 2); };
-#else
-// ---- float (8-byte complex) and double (16-byte complex) ----------------------------------------------
-static constexpr int kTs = (KF_SCALAR_BYTES == 8) ? 2 : 1;   // double: halve the transforms per CTA
-struct kP16 { static constexpr PlanDesc D = make_plan(16,   {4, 4},             {2},       1,   128, 31, 1); };
-struct kP64 { static constexpr PlanDesc D = make_plan(64,   {4, 4, 4},          {1, 2},    16,  16 / kTs, 4, 1); };
-struct kP256 { static constexpr PlanDesc D = make_plan(256,  {4, 4, 4, 4},       {2, 2},    16,  16 / kTs, 4, 1, 2); };
-struct kP1024 { static constexpr PlanDesc D = make_plan(1024, {4, 4, 4, 4, 4},    {2, 2, 1}, 64,  4 / kTs,  4, 1, 3); };
-struct kP2048 { static constexpr PlanDesc D = make_plan(2048, {4, 4, 4, 4, 4, 2}, {2, 2, 2}, 128, 2 / kTs,  4, 1, 2); };
-struct kP1000 { static constexpr PlanDesc D = make_plan(1000, {4, 2, 5, 5, 5},    {2, 2, 1}, 50,  5,        4, 1, 2); };
-struct kP1155 { static constexpr PlanDesc D = make_plan(1155, {3, 5, 7, 11},      {1, 1, 2}, 105, 2,        4, 1, 2); };
-#endif
-
-
-// X(tag, modes) with modes in {ALL, C2C, C2C_REAL}: which kernel modes are instantiated for the length
+// ---- Q15: 4-byte complex, integer-issue bound -------------------------------------------------------------
+KF_PLAN(kP1024,    1024, {4, 4, 4, 4, 4},    {2, 2, 1}, 64,  2, 4, 4, 2);
+KF_PLAN(kP2048,    2048, {4, 4, 4, 4, 4, 2}, {2, 2, 2}, 128, 1, 4, 4, 2);
+KF_PLAN(kP1000,    1000, {4, 2, 5, 5, 5},    {2, 2, 1}, 50,  4, 4, 1, 2);
+KF_PLAN(kP1155,    1155, {3, 5, 7, 11},      {1, 1, 2}, 105, 2, 4, 1, 0);
+KF_PLAN(kP1024col, 1024, {4, 4, 4, 4, 4},    {2, 2, 1}, 64,  8, 4, 1, 0);
+KF_PLAN(kP2048col, 2048, {4, 4, 4, 4, 4, 2}, {2, 2, 2}, 128, 8, 4, 1, 0);
 #define KF_PLAN_LIST(X) \
-    X(kP16, C2C)        \
-    X(kP64, ALL)        \
-    X(kP256, ALL)       \
-    X(kP1024, ALL)      \
-    X(kP2048, ALL)      \
-    X(kP1000, C2C_REAL) \
-    X(kP1155, C2C)
+    X(kP16, C2C) X(kP64, ALL) X(kP256, ALL) X(kP1024, C2C_REAL) X(kP1024col, COL) X(kP2048, C2C_REAL) X(kP2048col, COL) \
+    X(kP1000, C2C_REAL) X(kP1155, C2C)
+#elif defined(FIXED_POINT)
+// ---- Q31: 8-byte complex, 64-bit products -------------------------------------------------------------------
+KF_PLAN(kP1024,    1024, {4, 4, 4, 4, 4},    {2, 2, 1}, 64,  2, 4, 4, 0);
+KF_PLAN(kP2048,    2048, {4, 4, 4, 4, 4, 2}, {2, 2, 2}, 128, 1, 4, 2, 0);
+KF_PLAN(kP1000,    1000, {4, 2, 5, 5, 5},    {2, 2, 1}, 50,  4, 4, 1, 2);
+KF_PLAN(kP1155,    1155, {3, 5, 7, 11},      {1, 1, 2}, 105, 2, 4, 1, 0);
+KF_PLAN(kP1024col, 1024, {4, 4, 4, 4, 4},    {2, 2, 1}, 64,  8, 4, 1, 0);
+KF_PLAN(kP2048col, 2048, {4, 4, 4, 4, 4, 2}, {2, 2, 2}, 128, 4, 4, 1, 0);
+#define KF_PLAN_LIST(X) \
+    X(kP16, C2C) X(kP64, ALL) X(kP256, ALL) X(kP1024, C2C_REAL) X(kP1024col, COL) X(kP2048, C2C_REAL) X(kP2048col, COL) \
+    X(kP1000, C2C_REAL) X(kP1155, C2C)
+#elif defined(KF_IS_DOUBLE)   /* the double build passes -DKF_IS_DOUBLE next to -Dkiss_fft_scalar=double */
+// ---- double: 16-byte complex --------------------------------------------------------------------------------
+KF_PLAN(kP1024,    1024, {4, 4, 4, 4, 4},    {2, 2, 1},    64,  2, 4, 2, 2);
+KF_PLAN(kP2048,    2048, {4, 4, 4, 4, 4, 2}, {2, 2, 2},    128, 1, 4, 2, 2);
+KF_PLAN(kP1000,    1000, {4, 2, 5, 5, 5},    {1, 1, 1, 2}, 200, 1, 4, 1, 2);
+KF_PLAN(kP1155,    1155, {11, 5, 3, 7},      {1, 2, 1},    77,  1, 4, 3, 2);
+KF_PLAN(kP1024col, 1024, {4, 4, 4, 4, 4},    {2, 2, 1},    64,  4, 4, 1, 0);
+KF_PLAN(kP2048col, 2048, {4, 4, 4, 4, 4, 2}, {2, 2, 2},    128, 2, 4, 1, 0);
+#define KF_PLAN_LIST(X) \
+    X(kP16, C2C) X(kP64, ALL) X(kP256, ALL) X(kP1024, C2C_REAL) X(kP1024col, COL) X(kP2048, C2C_REAL) X(kP2048col, COL) \
+    X(kP1000, C2C_REAL) X(kP1155, C2C)
+#else
+// ---- float: 8-byte complex ------------------------------------------------------------------------------------
+// 1024 = (4*2*4) * (4*2*4): two 32-point register groups, one warp per transform, ONE shared-memory exchange
+KF_PLAN(kP1024,    1024, {4, 2, 4, 4, 2, 4},    {3, 3},    32,  2, 5, 6, 2);
+KF_PLAN(kP2048,    2048, {4, 4, 4, 4, 4, 2},    {2, 2, 2}, 128, 1, 4, 4, 2);
+// kiss_fftr / kiss_fftri nfft = 4096 (packed complex length 2048): separately tuned per direction
+KF_PLAN(kP2048r2c, 2048, {2, 2, 4, 4, 2, 4, 4}, {2, 2, 3}, 128, 1, 4, 4, 0);
+KF_PLAN(kP2048c2r, 2048, {4, 4, 2, 4, 2, 4, 2}, {2, 3, 2}, 128, 2, 4, 2, 2);
+KF_PLAN(kP1000,    1000, {5, 5, 5, 4, 2},       {3, 2},    40,  1, 4, 6, 2);
+KF_PLAN(kP1155,    1155, {7, 5, 11, 3},         {2, 2},    35,  2, 4, 3, 0);
+KF_PLAN(kP1024col, 1024, {4, 4, 4, 4, 4},       {2, 2, 1}, 64,  8, 4, 1, 0);
+KF_PLAN(kP2048col, 2048, {4, 4, 4, 4, 4, 2},    {2, 2, 2}, 128, 4, 4, 1, 0);
+#define KF_PLAN_LIST(X) \
+    X(kP16, C2C) X(kP64, ALL) X(kP256, ALL) X(kP1024, C2C_REAL) X(kP1024col, COL) X(kP2048r2c, R2C) X(kP2048c2r, C2R) \
+    X(kP2048, C2C) X(kP2048col, COL) X(kP1000, C2C_REAL) X(kP1155, C2C)
+#endif
 
 }   // namespace kf

@@ -1,0 +1,199 @@
+"""Slab-decomposed 3-D complex transform across G GPUs (one process per GPU).
+
+The reference has no distributed code; kiss_fftnd (kiss_fftnd.c:156-188) sweeps the axes of ONE array.  This module
+splits a d0 x d1 x d2 array into slabs of d0/G planes per rank and needs a single exchange:
+
+  A. rows (axis 2) of the local slab          -> kiss_fft_batch_dev, in place            [d0/G][d1][d2]
+  B. columns (axis 1) of every local plane    -> kiss_fft_planes_pass_dev, which also transposes each plane and
+                                                 writes it pre-sorted by destination rank  [G][d0/G][d2/G][d1]
+  X. all-to-all: block s goes to rank s        -> NCCL (torch.distributed.all_to_all_single), or, when the peers'
+                                                 receive buffers are mapped (symmetric memory), step B stores straight
+                                                 into them over NVLink and X degenerates to a barrier
+  C. axis 0, now complete on every rank        -> kiss_fft_axis_pass_dev                   [d2/G][d1][d0]
+
+The result is the 3-D DFT X[k0][k1][k2] stored as out[k2 - r*d2/G][k1][k0] on rank r ("transposed-out", distributed
+along k2) -- the usual contract of slab FFTs; `gather_natural` re-assembles the natural order for checks.  Float and
+double only agree with kiss_fftnd up to rounding because the axes run in the order 2,1,0 instead of 0,1,2; the
+fixed-point builds are bit-exact only in the single-GPU kiss_fftnd path.
+
+The geometry (who owns what, exchange counts and offsets) is plain integer logic in `SlabGeometry` so that it is
+testable on CPU with the gloo backend; the compute steps call the CUDA library and fail without it.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass(frozen=True)
+class SlabGeometry:
+    d0: int
+    d1: int
+    d2: int
+    world: int
+    rank: int
+
+    def __post_init__(self):
+        if self.d0 % self.world or self.d2 % self.world:
+            raise ValueError("d0 and d2 must be divisible by the number of ranks")
+
+    @property
+    def planes(self):          # local planes of the input slab
+        return self.d0 // self.world
+
+    @property
+    def cols(self):            # k2 values owned after the exchange
+        return self.d2 // self.world
+
+    @property
+    def local_elems(self):
+        return self.planes * self.d1 * self.d2
+
+    @property
+    def block_elems(self):     # one (source rank, destination rank) block of the exchange
+        return self.planes * self.cols * self.d1
+
+    def plane_range(self, rank=None):
+        r = self.rank if rank is None else rank
+        return r * self.planes, (r + 1) * self.planes
+
+    def col_range(self, rank=None):
+        r = self.rank if rank is None else rank
+        return r * self.cols, (r + 1) * self.cols
+
+    def send_offset(self, dst):
+        """element offset of the block for rank dst inside the step-B output [G][planes][cols][d1]"""
+        return dst * self.block_elems
+
+    def recv_offset(self, src):
+        """element offset of the block from rank src inside the receive buffer [d0][cols][d1] (= [G][planes][cols][d1])"""
+        return src * self.block_elems
+
+    def a2a_bytes_per_rank(self, itemsize):
+        """bytes this rank sends to OTHER ranks (NVLink roofline numerator)"""
+        return (self.world - 1) * self.block_elems * itemsize
+
+
+def batch_shard(howmany, rank, world):
+    """contiguous share of a batch of independent transforms: (first, count).  No communication is ever needed."""
+    base, rem = divmod(howmany, world)
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+class SlabFFT3D:
+    """forward/inverse 3-D transform of a slab-distributed array; all buffers are torch CUDA tensors of shape (..., 2)"""
+
+    def __init__(self, dims, tname="float", inverse=False, group=None, backend=None, p2p=False):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.group = group
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.geo = SlabGeometry(int(dims[0]), int(dims[1]), int(dims[2]), world, rank)
+        self.inverse = bool(inverse)
+        self.tname = tname
+        if backend is None:
+            import kissfft_b200
+            backend = CudaBackend(kissfft_b200.get(tname), self.geo, self.inverse)
+        self.backend = backend
+        self.p2p = bool(p2p) and world > 1
+        self._symm = None
+
+    # ---- buffers ----
+    def alloc(self):
+        """(local input slab [P][d1][d2][2], staging [G][P][C][d1][2], output [C][d1][d0][2])"""
+        g, be = self.geo, self.backend
+        x = be.empty((g.planes, g.d1, g.d2, 2))
+        recv = self._alloc_recv()
+        send = None if self.p2p else be.empty((g.world, g.planes, g.cols, g.d1, 2))
+        out = be.empty((g.cols, g.d1, g.d0, 2))
+        return x, send, recv, out
+
+    def _alloc_recv(self):
+        g, be = self.geo, self.backend
+        shape = (g.world, g.planes, g.cols, g.d1, 2)
+        if not self.p2p:
+            return be.empty(shape)
+        import torch.distributed._symmetric_memory as symm
+        t = symm.empty(shape, dtype=be.torch_dtype, device=be.device)
+        self._symm = symm.rendezvous(t, self.group if self.group is not None else self.dist.group.WORLD)
+        return t
+
+    # ---- the transform ----
+    def forward(self, x, send, recv, out, stream=0):
+        """x is overwritten by step A (in place, like kiss_fft with fin == fout)."""
+        g, be = self.geo, self.backend
+        be.rows_inplace(x, stream)                                   # A
+        if g.world == 1:
+            be.planes_cols(x, recv, dst_rank=None, stream=stream)    # B: whole plane, no exchange
+        elif self.p2p:
+            # B + X fused: every destination's block is stored straight into that rank's receive buffer
+            self._symm.barrier()      # peers are done reading their receive buffer (step C of the previous call)
+            for s in range(g.world):
+                peer = self._symm.get_buffer(s, recv.shape, recv.dtype)
+                be.planes_cols(x, peer, dst_rank=s, stream=stream, dst_block=g.rank)
+            self._symm.barrier()
+        else:
+            for s in range(g.world):
+                be.planes_cols(x, send, dst_rank=s, stream=stream, dst_block=s)
+            self.dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)     # X
+        be.axis0(recv, out, stream)                                  # C
+        return out
+
+    def gather_natural(self, out):
+        """collects the distributed transposed result into the natural-order [d0][d1][d2][2] array on every rank (testing aid)"""
+        g, torch, dist = self.geo, self.torch, self.dist
+        if g.world == 1:
+            full = out
+        else:
+            parts = [torch.empty_like(out) for _ in range(g.world)]
+            dist.all_gather(parts, out.contiguous(), group=self.group)
+            full = torch.cat(parts, dim=0)                # [d2][d1][d0][2]
+        return full.permute(2, 1, 0, 3).contiguous()
+
+
+class CudaBackend:
+    """the three compute steps on the CUDA library (kissfft_b200.KissFFT); no CPU path"""
+
+    def __init__(self, lib, geo, inverse):
+        import torch
+        self.torch = torch
+        self.lib, self.geo = lib, geo
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.torch_dtype = {"float": torch.float32, "double": torch.float64, "int16_t": torch.int16, "int32_t": torch.int32}[lib.tname]
+        self.cfg2 = lib.alloc(geo.d2, inverse)
+        self.cfg1 = lib.alloc(geo.d1, inverse)
+        self.cfg0 = lib.alloc(geo.d0, inverse)
+
+    def empty(self, shape):
+        return self.torch.empty(shape, dtype=self.torch_dtype, device=self.device)
+
+    def rows_inplace(self, x, stream):
+        g = self.geo
+        self.lib.fft_batch_dev(self.cfg2, x, x, g.planes * g.d1, g.d2, g.d2, 1, stream)
+
+    def planes_cols(self, x, dst, dst_rank, stream, dst_block=0):
+        """axis 1 of every local plane; k2 columns of destination rank `dst_rank` (all if None) -> dst block"""
+        g = self.geo
+        esz = x.element_size() * 2
+        if dst_rank is None:
+            self.lib.planes_pass_dev(self.cfg1, x, dst, g.planes, g.d2, g.d2, g.d1 * g.d2, g.d2 * g.d1, stream)
+            return
+        c0, _ = g.col_range(dst_rank)
+        src_ptr = x.data_ptr() + c0 * esz
+        dst_ptr = dst.data_ptr() + dst_block * g.block_elems * esz
+        self.lib.planes_pass_dev(self.cfg1, src_ptr, dst_ptr, g.planes, g.cols, g.d2, g.d1 * g.d2, g.cols * g.d1, stream)
+
+    def axis0(self, recv, out, stream):
+        g = self.geo
+        ncols = g.cols * g.d1
+        self.lib.axis_pass_dev(self.cfg0, recv, out, ncols, ncols, stream)
+
+
+def reference_slab_numpy(x_full, world):
+    """what every rank must end up with, from numpy: list over ranks of out[k2_local][k1][k0] (complex128).  Testing aid."""
+    X = np.fft.fftn(x_full)
+    d2 = X.shape[2]
+    c = d2 // world
+    return [np.ascontiguousarray(X[:, :, r * c:(r + 1) * c].transpose(2, 1, 0)) for r in range(world)]

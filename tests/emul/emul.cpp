@@ -53,6 +53,8 @@ static KParams<AT> mk_params(int nfft, int inverse, const void* in, void* out, l
                              long long out_dist, long long in_stride, const void* tw, const void* stw)
 {
     KParams<AT> P;
+    P.ncols = 0;
+    P.in_pdist = P.out_pdist = 0;
     P.in = (const CT*)in;
     P.out = (CT*)out;
     P.howmany = howmany;
@@ -113,12 +115,24 @@ struct Entry {
 #define KF_FUSED_ALL(PT) { PT::D.N, { run_fused<PT, kC2C>, run_fused<PT, kC2CCol>, run_fused<PT, kR2C>, run_fused<PT, kC2R> } }
 #define KF_FUSED_C2C(PT) { PT::D.N, { run_fused<PT, kC2C>, nullptr, nullptr, nullptr } }
 #define KF_FUSED_C2C_REAL(PT) { PT::D.N, { run_fused<PT, kC2C>, nullptr, run_fused<PT, kR2C>, run_fused<PT, kC2R> } }
+#define KF_FUSED_C2C_COL(PT) { PT::D.N, { run_fused<PT, kC2C>, run_fused<PT, kC2CCol>, nullptr, nullptr } }
+#define KF_FUSED_COL(PT) { PT::D.N, { nullptr, run_fused<PT, kC2CCol>, nullptr, nullptr } }
+#define KF_FUSED_R2C(PT) { PT::D.N, { nullptr, nullptr, run_fused<PT, kR2C>, nullptr } }
+#define KF_FUSED_C2R(PT) { PT::D.N, { nullptr, nullptr, nullptr, run_fused<PT, kC2R> } }
+#define KF_FUSED_REAL(PT) { PT::D.N, { nullptr, nullptr, run_fused<PT, kR2C>, run_fused<PT, kC2R> } }
 #define KF_ROW(tag, modes) KF_FUSED_##modes(tag),
 static const Entry kTable[] = { KF_PLAN_LIST(KF_ROW) };
 
 extern "C" int emul_num_plans(void) { return (int)(sizeof(kTable) / sizeof(kTable[0])); }
 extern "C" int emul_plan_nfft(int i) { return kTable[i].N; }
-extern "C" int emul_plan_has_mode(int i, int mode) { return kTable[i].fn[mode] != nullptr; }
+// first table entry that serves (N, mode) wins, exactly like find_fused in kf_launch.cu
+extern "C" int emul_plan_has_mode(int i, int mode)
+{
+    if (!kTable[i].fn[mode]) return 0;
+    for (int j = 0; j < i; ++j)
+        if (kTable[j].N == kTable[i].N && kTable[j].fn[mode]) return 0;
+    return 1;
+}
 
 // returns the number of leading rows processed (the launcher sends the rest to the run-time kernel), or -1 when no
 // fused plan is registered for (nfft, mode)

@@ -7,7 +7,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 EMUL = os.path.join(HERE, "emul")
-FLAGS = {"float": "-Dkiss_fft_scalar=float", "double": "-Dkiss_fft_scalar=double", "int16_t": "-DFIXED_POINT=16",
+FLAGS = {"float": "-Dkiss_fft_scalar=float", "double": "-Dkiss_fft_scalar=double -DKF_IS_DOUBLE", "int16_t": "-DFIXED_POINT=16",
          "int32_t": "-DFIXED_POINT=32"}
 C2C, C2C_COL, R2C, C2R = range(4)
 
@@ -26,7 +26,7 @@ def build(tname):
     if _stale(lib):
         os.makedirs(os.path.dirname(lib), exist_ok=True)
         gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-        subprocess.run([gxx, "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", FLAGS[tname],
+        subprocess.run([gxx, "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", *FLAGS[tname].split(),
                         os.path.join(EMUL, "emul.cpp"), "-o", lib], check=True)
     return lib
 

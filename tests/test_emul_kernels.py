@@ -104,3 +104,32 @@ def test_generic_columns_and_real(env):
         y = np.zeros((howmany, n), xr.dtype)
         em.generic(nc, C2R, 1, o.factor(nc), spec, y, howmany, nc + 1, nc, 1, o.twiddles(nc, 1), o.super_twiddles(nc, 1))
         check(tname, y, o.fftri(spec), n)
+
+
+def test_q15_full_scale_wraparound():
+    """Q15 inputs at full scale (including -32768) make the reference's int16 stores wrap; the kernels re-create the
+    truncation exactly where a wrapped value feeds a multiply or a shift, so they must still agree bit for bit."""
+    tname = "int16_t"
+    o, em = Oracle(tname), Emulator(tname)
+    rng = np.random.default_rng(5)
+    for nfft in (64, 256, 1000, 1024, 1155, 2048):
+        howmany = 4
+        x = rng.integers(-32768, 32768, size=(howmany, nfft, 2), dtype=np.int64).astype(np.int16)
+        x[0, :8] = -32768
+        x[1, :8] = 32767
+        out = np.zeros_like(x)
+        em.fused(nfft, C2C, 0, x, out, howmany, nfft, nfft, 1, o.twiddles(nfft, 0), factors=o.factor(nfft))
+        assert np.array_equal(out, o.fft(x, 0)), nfft
+        out2 = np.zeros_like(x)
+        em.generic(nfft, C2C, 0, o.factor(nfft), x, out2, howmany, nfft, nfft, 1, o.twiddles(nfft, 0))
+        assert np.array_equal(out2, o.fft(x, 0)), nfft
+    for n in (128, 2000, 4096):
+        nc = n // 2
+        xr = rng.integers(-32768, 32768, size=(3, n), dtype=np.int64).astype(np.int16)
+        X = np.zeros((3, nc + 1, 2), np.int16)
+        em.fused(nc, R2C, 0, xr, X, 3, nc, nc + 1, 1, o.twiddles(nc, 0), o.super_twiddles(nc, 0), factors=o.factor(nc))
+        assert np.array_equal(X, o.fftr(xr)), n
+        S = rng.integers(-32768, 32768, size=(3, nc + 1, 2), dtype=np.int64).astype(np.int16)
+        y = np.zeros((3, n), np.int16)
+        em.fused(nc, C2R, 1, S, y, 3, nc + 1, nc, 1, o.twiddles(nc, 1), o.super_twiddles(nc, 1), factors=o.factor(nc))
+        assert np.array_equal(y, o.fftri(S)), n

@@ -15,6 +15,7 @@ typedef kf::Arith<kiss_fft_scalar> AT;
 typedef AT::C CT;
 
 struct TuneEntry {
+    long long (*rows_ok)(const kf::KParams<AT>&);
     std::string label;
     int threads, tpc;
     size_t smem;
@@ -52,6 +53,7 @@ static TuneEntry make_entry(const char* label)
     e.kernel = (const void*)kf::kf_fused_kernel<AT, PT, MODE>;
     e.launch = launch_variant<PT, MODE>;
     e.prepare = prepare_variant<PT>;
+    e.rows_ok = kf::fused_rows<AT, PT, MODE>;
     return e;
 }
 
@@ -117,6 +119,8 @@ static int tune_main(int argc, char** argv, std::vector<TuneEntry>& vars, int nf
         CK(cudaMemcpy(d_in, h.data(), sizeof(CT) * h.size(), cudaMemcpyHostToDevice));
     }
     kf::KParams<AT> P;
+    P.ncols = 0;
+    P.in_pdist = P.out_pdist = 0;
     P.in = d_in; P.out = d_out; P.howmany = batch;
     P.in_dist = in_row; P.out_dist = out_row; P.in_stride = 1;
     if (mode == kf::kC2CCol) { P.in_dist = 1; P.in_stride = batch; P.out_dist = nfft; }
@@ -139,6 +143,7 @@ static int tune_main(int argc, char** argv, std::vector<TuneEntry>& vars, int nf
     for (auto& v : vars) {
         if (filter && v.label.find(filter) == std::string::npos) continue;
         v.prepare(P, h_tw.data(), &d_gtw);
+        if (v.rows_ok(P) != P.howmany) { printf("{\"variant\": \"%s\", \"error\": \"alignment rules\"}\n", v.label.c_str()); continue; }
         if (cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem) != cudaSuccess) {
             cudaGetLastError();
             printf("{\"variant\": \"%s\", \"error\": \"smem %zu too large\"}\n", v.label.c_str(), v.smem);

@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "tools", "_build")
-TYPEFLAGS = {"float": "-Dkiss_fft_scalar=float", "double": "-Dkiss_fft_scalar=double", "int16_t": "-DFIXED_POINT=16",
+TYPEFLAGS = {"float": "-Dkiss_fft_scalar=float", "double": "-Dkiss_fft_scalar=double -DKF_IS_DOUBLE", "int16_t": "-DFIXED_POINT=16",
              "int32_t": "-DFIXED_POINT=32"}
 NVCC = ["nvcc", "-std=c++20", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
         "-ccbin", "/usr/bin/g++", "-Xptxas", "-v"]
@@ -47,11 +47,11 @@ def gen(spec):
         for j, v in enumerate(chunk):
             idx = ci + j
             src += "struct V%d { static constexpr PlanDesc D = make_plan(%d, %s, %s, %d, %d, %d, %d, %d); };\n" % (
-                idx, spec["nfft"], lst(spec["radices"]), lst(v["groups"]), v["team"], v["tpc"], v["logpad"], v["minblocks"], v.get("nstage", 0))
+                idx, spec["nfft"], lst(v.get("radices", spec["radices"])), lst(v["groups"]), v["team"], v["tpc"], v["logpad"], v["minblocks"], v.get("nstage", 0))
         src += "void register_chunk_%d(std::vector<TuneEntry>& out) {\n" % (ci // nper)
         for j, v in enumerate(chunk):
             idx = ci + j
-            label = "g%s_t%d_c%d_p%d_b%d_s%d" % ("".join(map(str, v["groups"])), v["team"], v["tpc"], v["logpad"], v["minblocks"], v.get("nstage", 0))
+            label = "r%s_g%s_t%d_c%d_p%d_b%d_s%d" % ("".join(map(str, v.get("radices", spec["radices"]))), "".join(map(str, v["groups"])), v["team"], v["tpc"], v["logpad"], v["minblocks"], v.get("nstage", 0))
             src += '    out.push_back(make_entry<V%d, k%s>("%s"));\n' % (idx, spec["mode"], label)
         src += "}\n"
         path = os.path.join(BUILD, "tune_%s_%d.cu" % (name, ci // nper))
@@ -78,7 +78,7 @@ def build(spec):
 
     def cc(fo):
         f, o = fo
-        r = subprocess.run(NVCC + [tf, "-c", f, "-o", o], capture_output=True, text=True)
+        r = subprocess.run(NVCC + tf.split() + ["-c", f, "-o", o], capture_output=True, text=True)
         if r.returncode:
             print(r.stdout[-3000:], r.stderr[-3000:])
             raise SystemExit("compile failed: " + f)
