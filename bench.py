@@ -217,6 +217,9 @@ def run_ours(args, w, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dist = None
+    # keep stdout to the single JSON line: the image exports NCCL_DEBUG=VERSION, which makes NCCL print its banner there
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     if world > 1:
         import torch.distributed as dist_
         dist = dist_

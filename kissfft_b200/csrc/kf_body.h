@@ -120,7 +120,8 @@ struct FusedLayout {
     static constexpr PlanDesc D = PT::D;
     static constexpr bool kRing = D.nstage > 0 && MODE != kC2CCol;
     static constexpr int kRowIn = (MODE == kC2R) ? D.N + 1 : D.N;   // complex elements per input row
-    static constexpr size_t kExchBytes = (D.G >= 2 || MODE == kR2C || MODE == kC2R) ? (size_t)2 * D.tpc * D.pitch() * sizeof(typename A::C) : 0;
+    static_assert(D.nbuf == 2 || (D.nbuf == 1 && D.G == 2 && (MODE == kC2C || MODE == kC2CCol)), "single exchange buffer: two-group C2C/column plans only");
+    static constexpr size_t kExchBytes = (D.G >= 2 || MODE == kR2C || MODE == kC2R) ? (size_t)D.nbuf * D.tpc * D.pitch() * sizeof(typename A::C) : 0;
     static constexpr size_t kRingOff = (kExchBytes + 127) / 128 * 128;
     static constexpr size_t kStageBytes = ((size_t)D.tpc * kRowIn * sizeof(typename A::C) + 127) / 128 * 128;
     static constexpr size_t kBarOff = kRingOff + (kRing ? D.nstage * kStageBytes : 0);
@@ -152,7 +153,7 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
     constexpr int kRowIn = LY::kRowIn;
     // two exchange buffers of tpc * pitch elements each
     C* const bufA = smem;
-    C* const bufB = smem + D.tpc * kPitch;
+    C* const bufB = (D.nbuf == 2) ? smem + D.tpc * kPitch : smem;
 
     const int tid = env.tid();
     const int team = tid / D.team, t = tid % D.team;              // standard mapping: a team owns a transform
@@ -276,6 +277,8 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             run_groups<A, D, 0>(env, t, active, src, dst, b1, b0, tw, P.pc, P.inverse);
             par ^= D.G & 1;
         }
+        // single exchange buffer: the next tile's first group overwrites what the last group just read
+        if constexpr (D.nbuf == 1) env.sync();
     }
 }
 

@@ -40,6 +40,8 @@ struct PlanDesc {
     int logpad;             // shared-memory skew: phys(a) = a + (a >> logpad); >= 31 disables it
     int minblocks;          // __launch_bounds__ min CTAs per SM
     int nstage;             // depth of the bulk-async (TMA) input ring; 0 = first group loads directly from global
+    int nbuf;               // exchange buffers: 2 = ping-pong (default); 1 = single buffer + one extra barrier per tile,
+                            // only for two-group plans in the C2C / column modes (halves shared memory => wider column tiles)
 
     KF_CE int F(int s) const
     {

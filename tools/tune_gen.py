@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "tools", "_build")
 TYPEFLAGS = {"float": "-Dkiss_fft_scalar=float", "double": "-Dkiss_fft_scalar=double -DKF_IS_DOUBLE", "int16_t": "-DFIXED_POINT=16",
              "int32_t": "-DFIXED_POINT=32"}
-NVCC = ["nvcc", "-std=c++20", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
+NVCC = ["nvcc", "-std=c++20", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a", "-O3",
         "-ccbin", "/usr/bin/g++", "-Xptxas", "-v"]
 
 HEAD = r'''
@@ -46,12 +46,12 @@ def gen(spec):
         src = HEAD % {"root": ROOT}
         for j, v in enumerate(chunk):
             idx = ci + j
-            src += "struct V%d { static constexpr PlanDesc D = make_plan(%d, %s, %s, %d, %d, %d, %d, %d); };\n" % (
-                idx, spec["nfft"], lst(v.get("radices", spec["radices"])), lst(v["groups"]), v["team"], v["tpc"], v["logpad"], v["minblocks"], v.get("nstage", 0))
+            src += "struct V%d { static constexpr PlanDesc D = make_plan(%d, %s, %s, %d, %d, %d, %d, %d, %d); };\n" % (
+                idx, spec["nfft"], lst(v.get("radices", spec["radices"])), lst(v["groups"]), v["team"], v["tpc"], v["logpad"], v["minblocks"], v.get("nstage", 0), v.get("nbuf", 2))
         src += "void register_chunk_%d(std::vector<TuneEntry>& out) {\n" % (ci // nper)
         for j, v in enumerate(chunk):
             idx = ci + j
-            label = "r%s_g%s_t%d_c%d_p%d_b%d_s%d" % ("".join(map(str, v.get("radices", spec["radices"]))), "".join(map(str, v["groups"])), v["team"], v["tpc"], v["logpad"], v["minblocks"], v.get("nstage", 0))
+            label = "r%s_g%s_t%d_c%d_p%d_b%d_s%d_n%d" % ("".join(map(str, v.get("radices", spec["radices"]))), "".join(map(str, v["groups"])), v["team"], v["tpc"], v["logpad"], v["minblocks"], v.get("nstage", 0), v.get("nbuf", 2))
             src += '    out.push_back(make_entry<V%d, k%s>("%s"));\n' % (idx, spec["mode"], label)
         src += "}\n"
         path = os.path.join(BUILD, "tune_%s_%d.cu" % (name, ci // nper))
