@@ -38,6 +38,7 @@ struct KParams {
     const typename A::C* stw;    // ncfft/2 split twiddles (kiss_fftr.c:53-59), real modes only
     const typename A::C* gtw;    // per-group stage-twiddle tables of the fused plan (kf_twtab.h), unused by the generic kernel
     cx<typename A::R> g0tw[kMaxG0Slots];   // group 0's stage twiddles (plan constants -> constant bank)
+    cx<typename A::R> ctw[kMaxCtw];        // split-twiddle constants (PlanDesc::twmode == 1)
     PlanConsts<A> pc;
     int inverse;
 };
@@ -157,7 +158,7 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
 
     const int tid = env.tid();
     const int team = tid / D.team, t = tid % D.team;              // standard mapping: a team owns a transform
-    const TwTab<A> tw{P.tw, P.gtw, P.g0tw};
+    const TwTab<A> tw{P.tw, P.gtw, P.g0tw, P.ctw};
     const long long ntiles = (P.howmany + D.tpc - 1) / D.tpc;
     int par = 0;   // parity of the exchange buffer sequence, carried across tiles (see run_groups)
 
@@ -228,17 +229,22 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             } else {
                 env.sync();
                 if (active) {
-                    constexpr int nc = D.N;
+                    // split post pass (kiss_fftr.c:88-116), one bin pair (k, nc-k) per step; fully unrolled so the
+                    // shared-memory reads, twiddle fetches and stores of different pairs overlap
+                    constexpr int nc = PT::D.N, kPairs = nc / 2 + 1, kIt = (kPairs + PT::D.team - 1) / PT::D.team;
                     C* out = P.out + b * P.out_dist;
-                    for (int k = t; k <= nc / 2; k += D.team) {
-                        X Tk = A::load(tb[k]);
-                        X Tnk = (k == 0) ? Tk : A::load(tb[nc - k]);
-                        X st = (k == 0) ? Tk : A::load(TwTab<A>::ro_load_c(P.stw + (k - 1)));
-                        X ok, onk;
-                        fftr_post_pair<A>(k, nc, Tk, Tnk, st, ok, onk);
-                        out[k] = A::store(ok);
-                        out[nc - k] = A::store(onk);
-                    }
+                    static_for<kIt>([&](auto I) {
+                        const int k = t + decltype(I)::value * PT::D.team;
+                        if ((decltype(I)::value + 1) * PT::D.team <= kPairs || k < kPairs) {
+                            X Tk = A::load(tb[k]);
+                            X Tnk = (k == 0) ? Tk : A::load(tb[nc - k]);
+                            X st = (k == 0) ? Tk : A::load(TwTab<A>::ro_load_c(P.stw + (k - 1)));
+                            X ok, onk;
+                            fftr_post_pair<A>(k, nc, Tk, Tnk, st, ok, onk);
+                            out[k] = A::store(ok);
+                            out[nc - k] = A::store(onk);
+                        }
+                    });
                 }
                 par ^= D.G & 1;   // G exchanges were used (G-1 between groups + the T[] buffer)
             }
@@ -258,16 +264,21 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             constexpr int nc = D.N;
             // split pre pass writes T[] (natural order) into b1, group 0 then reads it from shared memory
             if (active) {
+                // split pre pass (kiss_fftr.c:131-153), unrolled like the post pass
                 const C* in = kRing ? srow : P.in + b * P.in_dist;
-                for (int k = t; k <= nc / 2; k += D.team) {
-                    X Fk = A::load(kRing ? in[k] : ld_stream(in + k));
-                    X Fnk = A::load(kRing ? in[nc - k] : ld_stream(in + (nc - k)));
-                    X st = (k == 0) ? Fk : A::load(TwTab<A>::ro_load_c(P.stw + (k - 1)));
-                    X Tk, Tnk;
-                    fftri_pre_pair<A>(k, Fk, Fnk, st, Tk, Tnk);
-                    b1[k] = A::store(Tk);
-                    if (k != 0) b1[nc - k] = A::store(Tnk);
-                }
+                constexpr int kPairs = nc / 2 + 1, kIt = (kPairs + PT::D.team - 1) / PT::D.team;
+                static_for<kIt>([&](auto I) {
+                    const int k = t + decltype(I)::value * PT::D.team;
+                    if ((decltype(I)::value + 1) * PT::D.team <= kPairs || k < kPairs) {
+                        X Fk = A::load(LY::kRing ? in[k] : ld_stream(in + k));
+                        X Fnk = A::load(LY::kRing ? in[nc - k] : ld_stream(in + (nc - k)));
+                        X st = (k == 0) ? Fk : A::load(TwTab<A>::ro_load_c(P.stw + (k - 1)));
+                        X Tk, Tnk;
+                        fftri_pre_pair<A>(k, Fk, Fnk, st, Tk, Tnk);
+                        b1[k] = A::store(Tk);
+                        if (k != 0) b1[nc - k] = A::store(Tnk);
+                    }
+                });
             }
             env.sync();
             recycle();
@@ -329,7 +340,7 @@ KF_HD void generic_body(const GParams<A>& G, Env& env)
     const int N = G.plan.N, L = G.plan.L, tpc = G.tpc, mode = G.mode;
     C* const buf0 = reinterpret_cast<C*>(env.smem());
     C* const buf1 = buf0 + (size_t)tpc * N;
-    const TwTab<A> tw{P.tw, nullptr, nullptr};
+    const TwTab<A> tw{P.tw, nullptr, nullptr, nullptr};
     const int nthr = env.nthreads(), tid = env.tid();
     const long long ntiles = (P.howmany + tpc - 1) / tpc;
 

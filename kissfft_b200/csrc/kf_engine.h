@@ -44,6 +44,7 @@ struct TwTab {
     const C* tw;    // N entries, tw[i] = exp(-+2 pi j i/N) generated on the host exactly like kiss_fft.c:361-367
     const C* gtw;   // per-group stage-twiddle tables [g][slot][work item] (PlanDesc::slot), exact copies of tw[] entries
     const X* g0;    // group 0's slots (kernel parameter space)
+    const X* ctw;   // split-twiddle constants (kernel parameter space), PlanDesc::cslot
     KF_HD X get(int idx) const
     {
         // all storage complexes are plain {S r, i}; load as one vector
@@ -174,7 +175,17 @@ KF_HD void run_stage(cx<typename A::R>* v, int kp, int w, const TwTab<A>& tw, co
             X x[p];
             static_for<p>([&](auto Q) { constexpr int q = decltype(Q)::value; x[q] = v[e + q * Ws]; });
             constexpr int sl = D.slot(g, s, e);
-            auto T = [&](int q) { return stage_tw<A, D, g>(tw, sl + q - 1, w); };
+            constexpr int up = e / (Ws * p);
+            // split mode: twiddle(q) = [table entry of the upper == 0 butterfly of this stage] * [plan constant]
+            constexpr bool kSplit = !A::kFixed && D.twmode == 1 && g > 0 && up > 0;
+            auto T = [&](int q) {
+                if constexpr (kSplit) {
+                    constexpr int sl0 = D.slot(g, s, e - D.upper_base(g, s, up));
+                    return A::cmul(stage_tw<A, D, g>(tw, sl0 + q - 1, w), tw.ctw[D.cslot(g, s, up, 1) + q - 1]);
+                } else {
+                    return stage_tw<A, D, g>(tw, sl + q - 1, w);
+                }
+            };
             if constexpr (p == 2) {
                 bfly2<A, kTw1>(x, kTw1 ? X{} : T(1));
             } else if constexpr (p == 4) {

@@ -28,6 +28,7 @@ namespace kf {
 constexpr int kMaxStages = 16;
 constexpr int kMaxGroups = 8;
 constexpr int kMaxG0Slots = 64;   // stage twiddles of group 0 carried in the kernel parameters
+constexpr int kMaxCtw = 96;       // split-twiddle constants carried in the kernel parameters
 
 struct PlanDesc {
     int N;                  // transform length
@@ -40,6 +41,10 @@ struct PlanDesc {
     int logpad;             // shared-memory skew: phys(a) = a + (a >> logpad); >= 31 disables it
     int minblocks;          // __launch_bounds__ min CTAs per SM
     int nstage;             // depth of the bulk-async (TMA) input ring; 0 = first group loads directly from global
+    int twmode;             // 0: every stage twiddle is fetched from the tables (exact copies of the reference's entries; always
+                            //    the case in fixed point); 1 (float/double only): a butterfly whose already-transformed upper
+                            //    digits are non-zero derives its twiddles as tw[q*F*k'] * tw[q*F*kabove] -- the first factor is the
+                            //    table entry of the upper==0 butterfly (shared by the whole stage), the second a plan constant
     int nbuf;               // exchange buffers: 2 = ping-pong (default); 1 = single buffer + one extra barrier per tile,
                             // only for two-group plans in the C2C / column modes (halves shared memory => wider column tiles)
 
@@ -118,6 +123,25 @@ struct PlanDesc {
         return n;
     }
     KF_CE int gtw_total() const { return gtw_offset(G); }
+    // constants tw[q*F_s*kabove] of the split-twiddle mode: one per (group >= 1, stage, non-zero upper combination, q)
+    KF_CE int nctw_stage(int g, int s) const { return (nupper(g, s) - 1) * (p[s] - 1); }
+    KF_CE int cslot(int g, int s, int up, int q) const   // up >= 1, q >= 1
+    {
+        int n = 0;
+        for (int gg = 1; gg < g; ++gg)
+            for (int j = s_lo(gg); j <= s_hi(gg); ++j) n += nctw_stage(gg, j);
+        for (int j = s_hi(g); j > s; --j) n += nctw_stage(g, j);
+        return n + (up - 1) * (p[s] - 1) + (q - 1);
+    }
+    KF_CE int nctw() const
+    {
+        int n = 0;
+        for (int gg = 1; gg < G; ++gg)
+            for (int j = s_lo(gg); j <= s_hi(gg); ++j) n += nctw_stage(gg, j);
+        return n;
+    }
+    // register index of the first element whose upper digits (stages above s) form combination `up`
+    KF_CE int upper_base(int g, int s, int up) const { return up * W(g, s) * p[s]; }
     KF_CE int phys(int a) const { return logpad >= 31 ? a : a + (a >> logpad); }
     // phys(base + delta) == phys(base) + phys(delta) for every work item of group g?  (no carry out of the low
     // logpad bits).  Reads: base = kp*Flo*R + off (off < Flo), delta = e*Flo.  Writes: base = kp*Flo + off
@@ -143,7 +167,7 @@ struct PlanDesc {
         int prod = 1, sum = 0;
         for (int s = 0; s < L; ++s) prod *= p[s];
         for (int g = 0; g < G; ++g) sum += glen[g];
-        return prod == N && sum == L && L <= kMaxStages && G <= kMaxGroups && team > 0 && tpc > 0 && nslots(0) <= kMaxG0Slots;
+        return prod == N && sum == L && L <= kMaxStages && G <= kMaxGroups && team > 0 && tpc > 0 && nslots(0) <= kMaxG0Slots && (twmode == 0 || nctw() <= kMaxCtw);
     }
 };
 

@@ -42,6 +42,14 @@ void fill_g0tw(KParams<A>& P, const typename A::C* h_tw)
             for (int q = 1; q < D.p[s]; ++q)
                 P.g0tw[D.slot(0, s, e) + q - 1] = A::load(h_tw[(long long)q * D.F(s) * D.kabove(0, s, e)]);
         }
+    // split-twiddle constants tw[q * F_s * kabove] for every non-zero upper-digit combination
+    if (D.twmode == 1)
+        for (int g = 1; g < D.G; ++g)
+            for (int s = D.s_hi(g); s >= D.s_lo(g); --s)
+                for (int up = 1; up < D.nupper(g, s); ++up)
+                    for (int q = 1; q < D.p[s]; ++q)
+                        P.ctw[D.cslot(g, s, up, q)] =
+                            A::load(h_tw[(long long)q * D.F(s) * D.kabove(g, s, D.upper_base(g, s, up))]);
 }
 
 // How many leading rows of a call may go through the fused kernel of plan PT (the rest, if any, must take the
