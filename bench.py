@@ -323,13 +323,16 @@ def run_ours(args, w, rank, world, local_rank):
     launches = lib.launch_count() - l0
     total_ms = ev[0][0].elapsed_time(ev[-1][-1])
     per_kernel_ms = [float(np.mean([ev[s][j].elapsed_time(ev[s][j + 1]) for s in range(args.steps)])) for j in range(len(kernels))]
-    if clocks:
-        t_end = time.perf_counter() + 1.2
-        while time.perf_counter() < t_end:
-            for _ in range(20):
-                for _, k in kernels:
-                    k()
-            torch.cuda.synchronize()
+    # continuation for the clock sampler: every rank runs the SAME number of extra steps (the slab workload contains
+    # collectives, so a rank-0-only or time-based loop would deadlock); count derived from the max-over-ranks step time
+    tcont = torch.tensor([total_ms / args.steps], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tcont, op=dist.ReduceOp.MAX)
+    ncont = int(min(20000, max(1, 1200.0 / max(float(tcont[0]), 1e-3))))
+    for _ in range(ncont):
+        for _, k in kernels:
+            k()
+    barrier()
     clk = clocks.stop() if clocks else None
 
     # end to end through the host-pointer API (pinned host buffers, copies inside the timed region)

@@ -81,6 +81,9 @@ long long KISS_FFT_API kiss_fft_cuda_launch_count(void);
 int KISS_FFT_API kiss_fft_cuda_plan_kind(int nfft);
 /* testing aid: route every length through the run-time shared-memory kernel (1) or restore the default (0) */
 void KISS_FFT_API kiss_fft_cuda_force_generic(int on);
+/* cap the number of CTAs of the fused kernels launched after this call (0 = fill the device).  Used by the slab
+ * transform so that its NVLink-bound peer-store launches share the SMs with HBM-bound launches on another stream. */
+void KISS_FFT_API kiss_fft_cuda_set_grid_limit(int max_ctas);
 /* sizeof(kiss_fft_scalar) of this build (4 float, 8 double, 2 Q15, 4 Q31) and 1 for fixed point */
 int KISS_FFT_API kiss_fft_cuda_scalar_bytes(void);
 int KISS_FFT_API kiss_fft_cuda_is_fixed_point(void);

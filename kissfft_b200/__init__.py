@@ -24,7 +24,7 @@ API_SYMBOLS = (
     "kiss_fft_batch_dev", "kiss_fftr_batch_dev", "kiss_fftri_batch_dev", "kiss_fftnd_dev", "kiss_fft_axis_pass_dev", "kiss_fft_planes_pass_dev",
     "kiss_fftndr_dev", "kiss_fftndri_dev", "kiss_fft_batch", "kiss_fftr_batch", "kiss_fftri_batch",
     "kiss_fft_cuda_last_error", "kiss_fft_cuda_launch_count", "kiss_fft_cuda_plan_kind", "kiss_fft_cuda_scalar_bytes",
-    "kiss_fft_cuda_is_fixed_point", "kiss_fft_cuda_force_generic",
+    "kiss_fft_cuda_is_fixed_point", "kiss_fft_cuda_force_generic", "kiss_fft_cuda_set_grid_limit",
 )
 
 
@@ -92,6 +92,8 @@ class KissFFT:
         L.kiss_fft_cuda_plan_kind.argtypes = [ci]
         L.kiss_fft_cuda_force_generic.argtypes = [ci]
         L.kiss_fft_cuda_force_generic.restype = None
+        L.kiss_fft_cuda_set_grid_limit.argtypes = [ci]
+        L.kiss_fft_cuda_set_grid_limit.restype = None
         self._libc = ctypes.CDLL(None)
         self._libc.free.argtypes = [vp]
         if L.kiss_fft_cuda_scalar_bytes() != np.dtype(self.dtype).itemsize:
@@ -207,6 +209,9 @@ class KissFFT:
 
     def force_generic(self, on):
         self.lib.kiss_fft_cuda_force_generic(int(bool(on)))
+
+    def set_grid_limit(self, max_ctas):
+        self.lib.kiss_fft_cuda_set_grid_limit(int(max_ctas))
 
     def last_error(self):
         msg = self.lib.kiss_fft_cuda_last_error()

@@ -968,6 +968,7 @@ void kiss_fftndri(kiss_fftndr_cfg st, const kiss_fft_cpx *freqdata, kiss_fft_sca
 }
 
 void kiss_fft_cuda_force_generic(int on) { kfcu_force_generic(on); }
+void kiss_fft_cuda_set_grid_limit(int max_ctas) { kfcu_set_grid_limit(max_ctas); }
 
 int kiss_fft_cuda_plan_kind(int nfft)
 {

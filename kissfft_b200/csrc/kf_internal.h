@@ -52,6 +52,9 @@ int kfcu_generic_max_nfft(void);
 long long kfcu_launch_count(void);
 /* force the generic kernel even when a fused plan exists (testing aid; 0 = default) */
 void kfcu_force_generic(int on);
+/* cap the persistent grid of the fused kernels launched after this call (0 = no cap): lets a link-bound launch
+ * (peer-memory stores of the slab exchange) share the SMs with an HBM-bound one on another stream */
+void kfcu_set_grid_limit(int max_ctas);
 
 #define KFCU_EINVAL (-1)
 #define KFCU_ETOOBIG (-2)

@@ -26,6 +26,7 @@ static_assert(sizeof(CT) == sizeof(kiss_fft_cpx), "storage complex must match ki
 
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_force_generic{0};
+static std::atomic<int> g_grid_limit{0};   // 0 = fill the device; > 0 caps the persistent grid (lets two kernels share the SMs)
 
 struct DeviceInfo {
     int sms = 0;
@@ -132,6 +133,7 @@ static int launch_fused(kfcu_plan* pl, KParams<AT>& P, cudaStream_t st)
     const long long ntiles = (P.howmany + D.tpc - 1) / D.tpc;
     long long grid = (long long)device_info().sms * blocks_per_sm[dev];
     if (grid > ntiles) grid = ntiles;
+    if (const int lim = g_grid_limit.load(std::memory_order_relaxed); lim > 0 && grid > lim) grid = lim;
     if (grid < 1) return 0;
     kern<<<(unsigned)grid, D.threads(), smem, st>>>(P);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -261,3 +263,4 @@ extern "C" int kfcu_generic_max_nfft(void)
 
 extern "C" long long kfcu_launch_count(void) { return g_launches.load(); }
 extern "C" void kfcu_force_generic(int on) { g_force_generic.store(on); }
+extern "C" void kfcu_set_grid_limit(int max_ctas) { g_grid_limit.store(max_ctas > 0 ? max_ctas : 0); }

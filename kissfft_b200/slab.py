@@ -99,6 +99,10 @@ class SlabFFT3D:
         self.backend = backend
         self.p2p = bool(p2p) and world > 1
         self._symm = None
+        self._side = None
+        import os
+        self.chunks = int(os.environ.get("KISSFFT_SLAB_CHUNKS", "8"))
+        self.remote_ctas = int(os.environ.get("KISSFFT_SLAB_REMOTE_CTAS", "48"))
 
     # ---- buffers ----
     def alloc(self):
@@ -124,22 +128,56 @@ class SlabFFT3D:
     def forward(self, x, send, recv, out, stream=0):
         """x is overwritten by step A (in place, like kiss_fft with fin == fout)."""
         g, be = self.geo, self.backend
-        be.rows_inplace(x, stream)                                   # A
         if g.world == 1:
+            be.rows_inplace(x, stream)                               # A
             be.planes_cols(x, recv, dst_rank=None, stream=stream)    # B: whole plane, no exchange
         elif self.p2p:
-            # B + X fused: every destination's block is stored straight into that rank's receive buffer
-            self._symm.barrier()      # peers are done reading their receive buffer (step C of the previous call)
-            for s in range(g.world):
-                peer = self._symm.get_buffer(s, recv.shape, recv.dtype)
-                be.planes_cols(x, peer, dst_rank=s, stream=stream, dst_block=g.rank)
-            self._symm.barrier()
+            self._forward_p2p(x, recv, stream)
         else:
+            be.rows_inplace(x, stream)                               # A
             for s in range(g.world):
                 be.planes_cols(x, send, dst_rank=s, stream=stream, dst_block=s)
             self.dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)     # X
         be.axis0(recv, out, stream)                                  # C
         return out
+
+    def _forward_p2p(self, x, recv, stream):
+        """steps A, B and the exchange fused and overlapped.
+
+        The slab is cut into chunks of planes.  For every chunk the rows (A) and the column pass for this rank's own
+        block (B, local) run on the main stream; the column passes whose output rows belong to other ranks store
+        STRAIGHT INTO THE PEERS' RECEIVE BUFFERS over NVLink and run on a second stream with a capped grid, so the
+        link-bound stores of chunk c overlap the HBM-bound passes of chunk c+1.  Two device-side barriers bracket the
+        peer stores (peers finished reading their buffer / all blocks have landed); no staging buffer, no collective."""
+        g, be, torch = self.geo, self.backend, self.torch
+        main = torch.cuda.ExternalStream(stream) if stream else torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        side = self._side
+        nchunks = max(1, min(self.chunks, g.planes))
+        bounds = [g.planes * c // nchunks for c in range(nchunks + 1)]
+        with torch.cuda.stream(main):
+            self._symm.barrier()          # peers are done reading their receive buffer (step C of the previous call)
+        peers = [self._symm.get_buffer(s, recv.shape, recv.dtype) for s in range(g.world)]
+        for c in range(nchunks):
+            p0, p1 = bounds[c], bounds[c + 1]
+            if p1 == p0:
+                continue
+            be.rows_inplace(x, main.cuda_stream, p0, p1)                                      # A on this chunk
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            be.set_grid_limit(self.remote_ctas)
+            for d in range(1, g.world):                                                       # B -> peers, rotated
+                s = (g.rank + d) % g.world
+                be.planes_cols(x, peers[s], dst_rank=s, stream=side.cuda_stream, dst_block=g.rank, p0=p0, p1=p1)
+            be.set_grid_limit(0)
+            be.planes_cols(x, recv, dst_rank=g.rank, stream=main.cuda_stream, dst_block=g.rank, p0=p0, p1=p1)   # B, own block
+        done = torch.cuda.Event()
+        done.record(side)
+        main.wait_event(done)
+        with torch.cuda.stream(main):
+            self._symm.barrier()          # every rank's blocks have landed in every receive buffer
 
     def gather_natural(self, out):
         """collects the distributed transposed result into the natural-order [d0][d1][d2][2] array on every rank (testing aid)"""
@@ -169,21 +207,28 @@ class CudaBackend:
     def empty(self, shape):
         return self.torch.empty(shape, dtype=self.torch_dtype, device=self.device)
 
-    def rows_inplace(self, x, stream):
-        g = self.geo
-        self.lib.fft_batch_dev(self.cfg2, x, x, g.planes * g.d1, g.d2, g.d2, 1, stream)
+    def set_grid_limit(self, n):
+        self.lib.set_grid_limit(n)
 
-    def planes_cols(self, x, dst, dst_rank, stream, dst_block=0):
-        """axis 1 of every local plane; k2 columns of destination rank `dst_rank` (all if None) -> dst block"""
+    def rows_inplace(self, x, stream, p0=0, p1=None):
         g = self.geo
+        p1 = g.planes if p1 is None else p1
+        esz = x.element_size() * 2
+        ptr = x.data_ptr() + p0 * g.d1 * g.d2 * esz
+        self.lib.fft_batch_dev(self.cfg2, ptr, ptr, (p1 - p0) * g.d1, g.d2, g.d2, 1, stream)
+
+    def planes_cols(self, x, dst, dst_rank, stream, dst_block=0, p0=0, p1=None):
+        """axis 1 of local planes [p0, p1); k2 columns of destination rank `dst_rank` (all if None) -> dst block"""
+        g = self.geo
+        p1 = g.planes if p1 is None else p1
         esz = x.element_size() * 2
         if dst_rank is None:
             self.lib.planes_pass_dev(self.cfg1, x, dst, g.planes, g.d2, g.d2, g.d1 * g.d2, g.d2 * g.d1, stream)
             return
         c0, _ = g.col_range(dst_rank)
-        src_ptr = x.data_ptr() + c0 * esz
-        dst_ptr = dst.data_ptr() + dst_block * g.block_elems * esz
-        self.lib.planes_pass_dev(self.cfg1, src_ptr, dst_ptr, g.planes, g.cols, g.d2, g.d1 * g.d2, g.cols * g.d1, stream)
+        src_ptr = x.data_ptr() + (p0 * g.d1 * g.d2 + c0) * esz
+        dst_ptr = dst.data_ptr() + (dst_block * g.block_elems + p0 * g.cols * g.d1) * esz
+        self.lib.planes_pass_dev(self.cfg1, src_ptr, dst_ptr, p1 - p0, g.cols, g.d2, g.d1 * g.d2, g.cols * g.d1, stream)
 
     def axis0(self, recv, out, stream):
         g = self.geo

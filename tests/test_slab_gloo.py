@@ -34,17 +34,22 @@ class NumpyBackend:
         t[..., 0] = torch.from_numpy(np.ascontiguousarray(c.real))
         t[..., 1] = torch.from_numpy(np.ascontiguousarray(c.imag))
 
-    def rows_inplace(self, x, stream):
-        self._put(x, np.fft.fft(self._c(x), axis=2))
+    def set_grid_limit(self, n):
+        pass
 
-    def planes_cols(self, x, dst, dst_rank, stream, dst_block=0):
+    def rows_inplace(self, x, stream, p0=0, p1=None):
+        p1 = self.geo.planes if p1 is None else p1
+        self._put(x[p0:p1], np.fft.fft(self._c(x[p0:p1]), axis=2))
+
+    def planes_cols(self, x, dst, dst_rank, stream, dst_block=0, p0=0, p1=None):
         g = self.geo
-        y = np.fft.fft(self._c(x), axis=1).transpose(0, 2, 1)          # [P][d2][d1]
+        p1 = g.planes if p1 is None else p1
+        y = np.fft.fft(self._c(x[p0:p1]), axis=1).transpose(0, 2, 1)   # [p1-p0][d2][d1]
         if dst_rank is None:
             self._put(dst[0], y)
             return
         c0, c1 = g.col_range(dst_rank)
-        self._put(dst[dst_block], y[:, c0:c1, :])
+        self._put(dst[dst_block][p0:p1], y[:, c0:c1, :])
 
     def axis0(self, recv, out, stream):
         g = self.geo
