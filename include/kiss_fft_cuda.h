@@ -63,6 +63,15 @@ int KISS_FFT_API kiss_fft_planes_pass_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *
                                           size_t ncols, size_t col_stride, size_t in_plane_dist, size_t out_plane_dist,
                                           void *stream);
 
+/* the fused "column pass + all-to-all" of the slab transform: as kiss_fft_planes_pass_dev with
+ * ncols = npeers*cols_per_peer, but column block s of every plane is written through d_peers[s] -- pointers into the
+ * receive buffers of the other GPUs mapped into this process (CUDA peer / symmetric memory), so the transposed rows
+ * travel over NVLink as the kernel produces them: row (plane p, local column c) lands at
+ * d_peers[s][p*out_plane_dist + c*nfft + k].  npeers <= 16. */
+int KISS_FFT_API kiss_fft_planes_pass_peers_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *const *d_peers,
+                                                int npeers, size_t nplanes, size_t cols_per_peer, size_t col_stride,
+                                                size_t in_plane_dist, size_t out_plane_dist, void *stream);
+
 /* kiss_fftndr / kiss_fftndri on device buffers (kiss_fftndr.c:86-132) */
 int KISS_FFT_API kiss_fftndr_dev(kiss_fftndr_cfg cfg, const kiss_fft_scalar *d_time, kiss_fft_cpx *d_freq, void *stream);
 int KISS_FFT_API kiss_fftndri_dev(kiss_fftndr_cfg cfg, const kiss_fft_cpx *d_freq, kiss_fft_scalar *d_time, void *stream);

@@ -21,7 +21,7 @@ API_SYMBOLS = (
     "kiss_fftr_alloc", "kiss_fftr", "kiss_fftri",
     "kiss_fftnd_alloc", "kiss_fftnd",
     "kiss_fftndr_alloc", "kiss_fftndr", "kiss_fftndri",
-    "kiss_fft_batch_dev", "kiss_fftr_batch_dev", "kiss_fftri_batch_dev", "kiss_fftnd_dev", "kiss_fft_axis_pass_dev", "kiss_fft_planes_pass_dev",
+    "kiss_fft_batch_dev", "kiss_fftr_batch_dev", "kiss_fftri_batch_dev", "kiss_fftnd_dev", "kiss_fft_axis_pass_dev", "kiss_fft_planes_pass_dev", "kiss_fft_planes_pass_peers_dev",
     "kiss_fftndr_dev", "kiss_fftndri_dev", "kiss_fft_batch", "kiss_fftr_batch", "kiss_fftri_batch",
     "kiss_fft_cuda_last_error", "kiss_fft_cuda_launch_count", "kiss_fft_cuda_plan_kind", "kiss_fft_cuda_scalar_bytes",
     "kiss_fft_cuda_is_fixed_point", "kiss_fft_cuda_force_generic", "kiss_fft_cuda_set_grid_limit",
@@ -82,6 +82,7 @@ class KissFFT:
         L.kiss_fftnd_dev.argtypes = [vp, vp, vp, vp, vp]
         L.kiss_fft_axis_pass_dev.argtypes = [vp, vp, vp, sz, sz, vp]
         L.kiss_fft_planes_pass_dev.argtypes = [vp, vp, vp, sz, sz, sz, sz, sz, vp]
+        L.kiss_fft_planes_pass_peers_dev.argtypes = [vp, vp, ctypes.POINTER(vp), ci, sz, sz, sz, sz, sz, vp]
         L.kiss_fftndr_dev.argtypes = [vp, vp, vp, vp]
         L.kiss_fftndri_dev.argtypes = [vp, vp, vp, vp]
         L.kiss_fft_batch.argtypes = [vp, vp, vp, sz]
@@ -161,6 +162,13 @@ class KissFFT:
     def planes_pass_dev(self, cfg, d_in, d_out, nplanes, ncols, col_stride, in_plane_dist, out_plane_dist, stream=0):
         self._check(self.lib.kiss_fft_planes_pass_dev(cfg, _ptr(d_in), _ptr(d_out), nplanes, ncols, col_stride, in_plane_dist,
                                                       out_plane_dist, ctypes.c_void_p(stream)), "kiss_fft_planes_pass_dev")
+
+    def planes_pass_peers_dev(self, cfg, d_in, peer_ptrs, nplanes, cols_per_peer, col_stride, in_plane_dist, out_plane_dist,
+                              stream=0):
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        self._check(self.lib.kiss_fft_planes_pass_peers_dev(cfg, _ptr(d_in), arr, len(peer_ptrs), nplanes, cols_per_peer,
+                                                            col_stride, in_plane_dist, out_plane_dist,
+                                                            ctypes.c_void_p(stream)), "kiss_fft_planes_pass_peers_dev")
 
     def fftndr_dev(self, cfg, d_time, d_freq, stream=0):
         self._check(self.lib.kiss_fftndr_dev(cfg, _ptr(d_time), _ptr(d_freq), ctypes.c_void_p(stream)), "kiss_fftndr_dev")

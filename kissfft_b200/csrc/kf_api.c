@@ -515,6 +515,22 @@ int kiss_fft_planes_pass_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_ff
     return 0;
 }
 
+int kiss_fft_planes_pass_peers_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *const *d_peers, int npeers,
+                                   size_t nplanes, size_t cols_per_peer, size_t col_stride, size_t in_plane_dist,
+                                   size_t out_plane_dist, void *stream)
+{
+    if (!cfg || cfg->magic != KF_MAGIC_1D || !d_in || !d_peers || npeers < 1 || npeers > 16 || col_stride < 1) {
+        KF_ERROR("kiss_fft_planes_pass_peers_dev: bad argument");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    const kf_devplan *dp;
+    KF_CHECK(kf_get_devplan(cfg, NULL, &dp));
+    KF_CHECK(kfcu_exec_planes_peers((kfcu_plan *)&dp->plan, d_in, (void *const *)d_peers, npeers, (long long)nplanes,
+                                    (long long)cols_per_peer, (long long)col_stride, (long long)in_plane_dist,
+                                    (long long)out_plane_dist, stream));
+    return 0;
+}
+
 static int kf_real_args_ok(const void *d_real, size_t real_dist)
 {
     return ((uintptr_t)d_real % (2 * sizeof(kiss_fft_scalar))) == 0 && (real_dist % 2) == 0;

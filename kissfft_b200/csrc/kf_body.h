@@ -32,8 +32,19 @@ struct KParams {
     // column mode only: transforms are numbered plane-major, `ncols` columns per plane; plane p starts at
     // in + p*in_pdist / out + p*out_pdist and column c of it at + c*in_dist / + c*out_dist.  ncols == 0: one plane.
     long long ncols, in_pdist, out_pdist;
+    // column mode, fused exchange: when npeers > 0 the columns of a plane are split into npeers blocks of `cols_per_peer`
+    // and block s is written through peer[s] (a mapped pointer into rank s's receive buffer: NVLink peer stores)
+    typename A::C* peer[16];
+    long long cols_per_peer;
+    int npeers;
     KF_HD long long in_off(long long b) const { return ncols > 0 ? (b / ncols) * in_pdist + (b % ncols) * in_dist : b * in_dist; }
     KF_HD long long out_off(long long b) const { return ncols > 0 ? (b / ncols) * out_pdist + (b % ncols) * out_dist : b * out_dist; }
+    KF_HD typename A::C* out_ptr(long long b) const
+    {
+        if (npeers <= 0) return out + out_off(b);
+        const long long pl = b / ncols, col = b % ncols;
+        return peer[col / cols_per_peer] + pl * out_pdist + (col % cols_per_peer) * out_dist;
+    }
     const typename A::C* tw;     // N twiddles (kR2C/kC2R: of the ncfft-point sub-transform)
     const typename A::C* stw;    // ncfft/2 split twiddles (kiss_fftr.c:53-59), real modes only
     const typename A::C* gtw;    // per-group stage-twiddle tables of the fused plan (kf_twtab.h), unused by the generic kernel
@@ -254,7 +265,7 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             const int cteam = tid % D.tpc, ct = tid / D.tpc;
             const long long cb = tile * D.tpc + cteam;
             SrcGlobal<A, false> src{P.in + P.in_off(cb), P.in_stride};
-            DstGlobal<A> dst{P.out + P.out_off(b)};
+            DstGlobal<A> dst{P.out_ptr(b)};
             C* cb1 = (par ? bufA : bufB) + cteam * kPitch;
             run_group<A, D, 0, SrcGlobal<A, false>, DstGlobal<A>>(ct, cb < P.howmany, src, dst, nullptr, cb1, tw, P.pc, P.inverse);
             env.sync();
@@ -422,7 +433,7 @@ KF_HD void generic_body(const GParams<A>& G, Env& env)
         } else {
             for (int i = tid; i < nb * N; i += nthr) {
                 const int bl = i / N, k = i % N;
-                P.out[P.out_off(bbase + bl) + k] = rd[i];
+                P.out_ptr(bbase + bl)[k] = rd[i];
             }
         }
         env.sync();

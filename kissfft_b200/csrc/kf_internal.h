@@ -40,6 +40,11 @@ int kfcu_exec(int mode, kfcu_plan *plan, const void *d_in, void *d_out, long lon
 int kfcu_exec_planes(kfcu_plan *plan, const void *d_in, void *d_out, long long nplanes, long long ncols, long long col_stride,
                      long long in_pdist, long long out_pdist, void *stream);
 
+/* kfcu_exec_planes with the ncols = npeers*cols_per_peer columns of every plane scattered to npeers destination
+ * buffers: column block s is written through peers[s] (+ p*out_pdist + c_local*nfft) */
+int kfcu_exec_planes_peers(kfcu_plan *plan, const void *d_in, void *const *peers, int npeers, long long nplanes,
+                           long long cols_per_peer, long long col_stride, long long in_pdist, long long out_pdist, void *stream);
+
 /* out[c][r] = in[r][c] for a rows x cols array of complex elements (kiss_fftndr's bin-major <-> row-major
  * scatter loops, kiss_fftndr.c:101-102, 107-108) */
 int kfcu_transpose(const void *d_in, void *d_out, long long rows, long long cols, void *stream);

@@ -51,6 +51,8 @@ static KParams<AT> make_params(const kfcu_plan* pl, const void* d_in, void* d_ou
     KParams<AT> P;
     P.ncols = 0;
     P.in_pdist = P.out_pdist = 0;
+    P.npeers = 0;
+    P.cols_per_peer = 0;
     P.in = (const CT*)d_in;
     P.out = (CT*)d_out;
     P.howmany = howmany;
@@ -230,6 +232,25 @@ extern "C" int kfcu_exec_planes(kfcu_plan* plan, const void* d_in, void* d_out, 
     P.ncols = ncols;
     P.in_pdist = in_pdist;
     P.out_pdist = out_pdist;
+    if (const FusedEntry* fe = find_fused(plan->nfft, kC2CCol)) return fe->fn[kC2CCol](plan, P, (cudaStream_t)stream);
+    return launch_generic(kC2CCol, plan, P, (cudaStream_t)stream);
+}
+
+// the same pass with the columns of every plane split into npeers blocks; block s goes through peers[s]
+extern "C" int kfcu_exec_planes_peers(kfcu_plan* plan, const void* d_in, void* const* peers, int npeers, long long nplanes,
+                                      long long cols_per_peer, long long col_stride, long long in_pdist, long long out_pdist,
+                                      void* stream)
+{
+    if (!plan || !d_in || !peers || npeers < 1 || npeers > 16 || nplanes < 0 || cols_per_peer < 1) return KFCU_EINVAL;
+    if (nplanes == 0) return 0;
+    const long long ncols = cols_per_peer * npeers;
+    KParams<AT> P = make_params(plan, d_in, peers[0], nplanes * ncols, 1, plan->nfft, col_stride);
+    P.ncols = ncols;
+    P.in_pdist = in_pdist;
+    P.out_pdist = out_pdist;
+    P.npeers = npeers;
+    P.cols_per_peer = cols_per_peer;
+    for (int s = 0; s < npeers; ++s) P.peer[s] = (CT*)peers[s];
     if (const FusedEntry* fe = find_fused(plan->nfft, kC2CCol)) return fe->fn[kC2CCol](plan, P, (cudaStream_t)stream);
     return launch_generic(kC2CCol, plan, P, (cudaStream_t)stream);
 }

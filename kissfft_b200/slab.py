@@ -101,8 +101,8 @@ class SlabFFT3D:
         self._symm = None
         self._side = None
         import os
-        self.chunks = int(os.environ.get("KISSFFT_SLAB_CHUNKS", "8"))
-        self.remote_ctas = int(os.environ.get("KISSFFT_SLAB_REMOTE_CTAS", "48"))
+        self.chunks = int(os.environ.get("KISSFFT_SLAB_CHUNKS", "4"))
+        self.remote_ctas = int(os.environ.get("KISSFFT_SLAB_REMOTE_CTAS", "0"))
 
     # ---- buffers ----
     def alloc(self):
@@ -144,10 +144,10 @@ class SlabFFT3D:
     def _forward_p2p(self, x, recv, stream):
         """steps A, B and the exchange fused and overlapped.
 
-        The slab is cut into chunks of planes.  For every chunk the rows (A) and the column pass for this rank's own
-        block (B, local) run on the main stream; the column passes whose output rows belong to other ranks store
-        STRAIGHT INTO THE PEERS' RECEIVE BUFFERS over NVLink and run on a second stream with a capped grid, so the
-        link-bound stores of chunk c overlap the HBM-bound passes of chunk c+1.  Two device-side barriers bracket the
+        The slab is cut into chunks of planes.  For every chunk the rows (A) run on the main stream; the column pass
+        (B) is ONE launch on a second stream (kiss_fft_planes_pass_peers_dev) whose output rows are stored STRAIGHT INTO
+        THE RECEIVE BUFFERS of their destination ranks over NVLink (peer stores; its own block locally), so the
+        link-bound stores of chunk c overlap the HBM-bound rows of chunk c+1.  Two device-side barriers bracket the
         peer stores (peers finished reading their buffer / all blocks have landed); no staging buffer, no collective."""
         g, be, torch = self.geo, self.backend, self.torch
         main = torch.cuda.ExternalStream(stream) if stream else torch.cuda.current_stream()
@@ -159,6 +159,7 @@ class SlabFFT3D:
         with torch.cuda.stream(main):
             self._symm.barrier()          # peers are done reading their receive buffer (step C of the previous call)
         peers = [self._symm.get_buffer(s, recv.shape, recv.dtype) for s in range(g.world)]
+        esz = x.element_size() * 2
         for c in range(nchunks):
             p0, p1 = bounds[c], bounds[c + 1]
             if p1 == p0:
@@ -167,12 +168,12 @@ class SlabFFT3D:
             ev = torch.cuda.Event()
             ev.record(main)
             side.wait_event(ev)
+            # B + exchange in ONE launch: column block s of every plane goes through the mapped pointer into rank s's
+            # receive buffer (its own block for s == rank)
+            ptrs = [peers[s].data_ptr() + (g.rank * g.block_elems + p0 * g.cols * g.d1) * esz for s in range(g.world)]
             be.set_grid_limit(self.remote_ctas)
-            for d in range(1, g.world):                                                       # B -> peers, rotated
-                s = (g.rank + d) % g.world
-                be.planes_cols(x, peers[s], dst_rank=s, stream=side.cuda_stream, dst_block=g.rank, p0=p0, p1=p1)
+            be.planes_cols_peers(x, ptrs, side.cuda_stream, p0, p1)
             be.set_grid_limit(0)
-            be.planes_cols(x, recv, dst_rank=g.rank, stream=main.cuda_stream, dst_block=g.rank, p0=p0, p1=p1)   # B, own block
         done = torch.cuda.Event()
         done.record(side)
         main.wait_event(done)
@@ -229,6 +230,12 @@ class CudaBackend:
         src_ptr = x.data_ptr() + (p0 * g.d1 * g.d2 + c0) * esz
         dst_ptr = dst.data_ptr() + (dst_block * g.block_elems + p0 * g.cols * g.d1) * esz
         self.lib.planes_pass_dev(self.cfg1, src_ptr, dst_ptr, p1 - p0, g.cols, g.d2, g.d1 * g.d2, g.cols * g.d1, stream)
+
+    def planes_cols_peers(self, x, ptrs, stream, p0, p1):
+        g = self.geo
+        esz = x.element_size() * 2
+        src_ptr = x.data_ptr() + p0 * g.d1 * g.d2 * esz
+        self.lib.planes_pass_peers_dev(self.cfg1, src_ptr, ptrs, p1 - p0, g.cols, g.d2, g.d1 * g.d2, g.cols * g.d1, stream)
 
     def axis0(self, recv, out, stream):
         g = self.geo

@@ -55,6 +55,8 @@ static KParams<AT> mk_params(int nfft, int inverse, const void* in, void* out, l
     KParams<AT> P;
     P.ncols = 0;
     P.in_pdist = P.out_pdist = 0;
+    P.npeers = 0;
+    P.cols_per_peer = 0;
     P.in = (const CT*)in;
     P.out = (CT*)out;
     P.howmany = howmany;

@@ -51,6 +51,9 @@ class NumpyBackend:
         c0, c1 = g.col_range(dst_rank)
         self._put(dst[dst_block][p0:p1], y[:, c0:c1, :])
 
+    def planes_cols_peers(self, x, ptrs, stream, p0, p1):
+        raise NotImplementedError("peer-memory path is CUDA-only")
+
     def axis0(self, recv, out, stream):
         g = self.geo
         a = self._c(recv).reshape(g.d0, g.cols, g.d1)

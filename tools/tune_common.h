@@ -121,6 +121,8 @@ static int tune_main(int argc, char** argv, std::vector<TuneEntry>& vars, int nf
     kf::KParams<AT> P;
     P.ncols = 0;
     P.in_pdist = P.out_pdist = 0;
+    P.npeers = 0;
+    P.cols_per_peer = 0;
     P.in = d_in; P.out = d_out; P.howmany = batch;
     P.in_dist = in_row; P.out_dist = out_row; P.in_stride = 1;
     if (mode == kf::kC2CCol) { P.in_dist = 1; P.in_stride = batch; P.out_dist = nfft; }
