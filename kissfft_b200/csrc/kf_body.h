@@ -93,15 +93,53 @@ struct SrcShared {
     const typename A::C* base;   // natural order, unpadded
     KF_HD cx<typename A::R> load(int i) const { return A::load(base[i]); }
 };
+// kiss_fftri's split pre pass (kiss_fftr.c:131-153) fused into the first group's loads: element k of the packed
+// complex input T[] of the inverse transform is computed on the fly from the half spectrum F[k], F[nc-k] and the
+// split twiddle.  Every T[k] is produced independently (the reference produces T[k] and T[nc-k] together; here
+// the thread that needs T[nc-k] recomputes the pair) -- same operands, same roundings, no T[] round trip.
+template <class A, bool SHARED>
+struct SrcC2RFused {
+    const typename A::C* row;   // F[0..nc]: landed stage (SHARED) or global memory
+    const typename A::C* stw;
+    int nc;
+    KF_HD cx<typename A::R> f(int i) const
+    {
+        if constexpr (SHARED) return A::load(row[i]);
+        else return A::load(ld_stream(row + i));
+    }
+    KF_HD cx<typename A::R> load(int k) const
+    {
+        typedef cx<typename A::R> X;
+        const bool lo = 2 * k < nc;          // k == nc/2 takes the second assignment, which wins in the reference
+        const int ks = lo ? k : nc - k;
+        const X Fa = f(ks), Fb = f(nc - ks);
+        const X st = (ks == 0) ? Fa : A::load(TwTab<A>::ro_load_c(stw + (ks - 1)));
+        X Tk, Tnk;
+        fftri_pre_pair<A>(ks, Fa, Fb, st, Tk, Tnk);
+        return lo ? Tk : Tnk;
+    }
+};
+
+// Destinations of the last group: put<it, e>(k, v) receives output element k, produced from register e of the
+// thread's it-th work item.
 template <class A>
 struct DstGlobal {
     typename A::C* base;
-    KF_HD void store(int k, const cx<typename A::R>& v) const { base[k] = A::store(v); }
+    template <int IT_, int E_>
+    KF_HD void put(int k, const cx<typename A::R>& v) const { base[k] = A::store(v); }
 };
 template <class A>
 struct DstShared {
     typename A::C* base;         // natural order, unpadded
-    KF_HD void store(int k, const cx<typename A::R>& v) const { base[k] = A::store(v); }
+    template <int IT_, int E_>
+    KF_HD void put(int k, const cx<typename A::R>& v) const { base[k] = A::store(v); }
+};
+// keeps the outputs in the caller's registers (kiss_fftr post pass by warp shuffles)
+template <class A, int R_>
+struct DstRegs {
+    cx<typename A::R>* regs;
+    template <int IT_, int E_>
+    KF_HD void put(int, const cx<typename A::R>& v) const { regs[IT_ * R_ + E_] = v; }
 };
 struct NoSrc {
     template <class T = int>
@@ -109,15 +147,15 @@ struct NoSrc {
 };
 
 // ---- group sequencing: group g reads exchange buffer (x0+g-1)&1 and writes (x0+g)&1; one barrier per exchange ----
-template <class A, PlanDesc D, int g, class Src, class Dst, class Env>
+template <class A, PlanDesc D, int g, class Src, class Dst, class Env, int GEND = D.G>
 KF_HD void run_groups(Env& env, int t, bool active, const Src& src, const Dst& dst, typename A::C* buf0,
                       typename A::C* buf1, const TwTab<A>& tw, const PlanConsts<A>& pc, int inverse)
 {
-    // buf0 is read by this group (unused for g == 0), buf1 is written (unused for the last group)
-    run_group<A, D, g, Src, Dst>(t, active, src, dst, buf0, buf1, tw, pc, inverse);
-    if constexpr (g + 1 < D.G) {
-        env.sync();
-        run_groups<A, D, g + 1, Src, Dst>(env, t, active, src, dst, buf1, buf0, tw, pc, inverse);
+    // buf0 is read by this group (unused for g == 0), buf1 is written (unused for the last group); groups g..GEND-1
+    if constexpr (g < GEND) {
+        run_group<A, D, g, Src, Dst>(t, active, src, dst, buf0, buf1, tw, pc, inverse);
+        if constexpr (g + 1 < D.G) env.sync();
+        if constexpr (g + 1 < GEND) run_groups<A, D, g + 1, Src, Dst, Env, GEND>(env, t, active, src, dst, buf1, buf0, tw, pc, inverse);
     }
 }
 
@@ -133,7 +171,10 @@ struct FusedLayout {
     static constexpr bool kRing = D.nstage > 0 && MODE != kC2CCol;
     static constexpr int kRowIn = (MODE == kC2R) ? D.N + 1 : D.N;   // complex elements per input row
     static_assert(D.nbuf == 2 || (D.nbuf == 1 && D.G == 2 && (MODE == kC2C || MODE == kC2CCol)), "single exchange buffer: two-group C2C/column plans only");
-    static constexpr size_t kExchBytes = (D.G >= 2 || MODE == kR2C || MODE == kC2R) ? (size_t)D.nbuf * D.tpc * D.pitch() * sizeof(typename A::C) : 0;
+    // kiss_fftr post pass by warp shuffles instead of a T[] round trip through shared memory: needs whole warps per
+    // team and the last group's work items to divide evenly (PlanDesc::shfl_post asks for it)
+    static constexpr bool kShflPost = MODE == kR2C && D.shfl_post && D.team % 32 == 0 && D.items(D.G - 1) % D.team == 0;
+    static constexpr size_t kExchBytes = (D.G >= 2 || (MODE == kR2C && !kShflPost)) ? (size_t)D.nbuf * D.tpc * D.pitch() * sizeof(typename A::C) : 0;
     static constexpr size_t kRingOff = (kExchBytes + 127) / 128 * 128;
     static constexpr size_t kStageBytes = ((size_t)D.tpc * kRowIn * sizeof(typename A::C) + 127) / 128 * 128;
     static constexpr size_t kBarOff = kRingOff + (kRing ? D.nstage * kStageBytes : 0);
@@ -215,7 +256,70 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             }
         };
 
-        if constexpr (MODE == kC2C || MODE == kR2C) {
+        if constexpr (MODE == kR2C && LY::kShflPost) {
+            // ---- kiss_fftr with the split post pass (kiss_fftr.c:88-116) done in registers ---------------------------
+            // The last group keeps its outputs T[k] in registers.  Output k needs T[k] and T[nc-k]; with M = N/R work
+            // items, T[kp + j*M]'s partner is register R-1-j of work item M-kp.  The last group's threads are
+            // renumbered so that the two owners of a pair sit in lanes l and 31-l of one warp, and the partner values
+            // travel by warp shuffle -- no T[] buffer, no extra barrier.  Thread 0 and thread team/2 pair with
+            // themselves.
+            constexpr int gl = PT::D.G - 1, R = PT::D.R(gl), M = PT::D.items(gl), IT = PT::D.iters(gl), T = PT::D.team;
+            constexpr int nc = PT::D.N;
+            const int lane = tid & 31, wq = t >> 5;
+            int tl = (lane < 16) ? 16 * wq + lane : T - (16 * wq + 31 - lane);
+            if (tl == T) tl = T / 2;
+            X treg[IT * R];
+            DstRegs<A, R> dstr{treg};
+            auto run_all = [&](auto src) {
+                typedef decltype(src) S;
+                if constexpr (PT::D.G == 1) {
+                    run_group<A, PT::D, 0, S, DstRegs<A, R>>(tl, active, src, dstr, b0, b1, tw, P.pc, P.inverse);
+                    if constexpr (LY::kRing) env.sync();
+                    recycle();
+                } else {
+                    run_group<A, PT::D, 0, S, DstRegs<A, R>>(t, active, src, dstr, b0, b1, tw, P.pc, P.inverse);
+                    env.sync();
+                    recycle();
+                    // middle groups, then the last one under the pairing-friendly thread numbering
+                    run_groups<A, PT::D, 1, S, DstRegs<A, R>, Env, gl>(env, t, active, src, dstr, b1, b0, tw, P.pc, P.inverse);
+                    run_group<A, PT::D, gl, S, DstRegs<A, R>>(tl, active, src, dstr, (gl & 1) ? b1 : b0, nullptr, tw, P.pc, P.inverse);
+                }
+            };
+            if constexpr (kRing) run_all(SrcShared<A>{srow});
+            else run_all(SrcGlobal<A, true>{P.in + b * P.in_dist, 1});
+            if (active) {
+                const bool is0 = (tl == 0), self = is0 || (tl == T / 2);
+                const int srcl = self ? lane : 31 - lane;
+                C* out = P.out + b * P.out_dist;
+                static_for<IT>([&](auto ITER) {
+                    static_for<R>([&](auto E) {
+                        constexpr int it = decltype(ITER)::value, e = decltype(E)::value;
+                        constexpr int j = PT::D.kout(gl, e) / M;
+                        constexpr int pe = PT::D.reg_of_j(gl, R - 1 - j), pit = IT - 1 - it;           // general partner
+                        constexpr int p0e = (it == 0) ? PT::D.reg_of_j(gl, (R - j) % R) : pe;        // thread 0's partner
+                        constexpr int p0it = (IT - it) % IT;
+                        X pg{env.shfl(treg[pit * R + pe].r, srcl), env.shfl(treg[pit * R + pe].i, srcl)};
+                        const X partner = is0 ? treg[p0it * R + p0e] : pg;
+                        const X own = treg[it * R + e];
+                        const int k = tl + it * T + j * M;
+                        if (it == 0 && j == 0 && is0) {
+                            X ok, onk;
+                            fftr_post_pair<A>(0, nc, own, own, own, ok, onk);      // DC and Nyquist bins
+                            out[0] = A::store(ok);
+                            out[nc] = A::store(onk);
+                        } else {
+                            const bool lo = 2 * k < nc;             // k == nc/2: the reference's second assignment wins
+                            const int ks = lo ? k : nc - k;
+                            const X st = A::load(TwTab<A>::ro_load_c(P.stw + (ks - 1)));
+                            X ok, onk;
+                            fftr_post_pair<A>(ks, nc, lo ? own : partner, lo ? partner : own, st, ok, onk);
+                            out[k] = A::store(lo ? ok : onk);
+                        }
+                    });
+                });
+            }
+            if constexpr (D.G >= 2) par ^= (D.G - 1) & 1;
+        } else if constexpr (MODE == kC2C || MODE == kR2C || MODE == kC2R) {
             // kR2C: the real row is read as ncfft packed complex (kiss_fftr.c:77); the last group leaves T[] in
             // natural order in the next exchange buffer for the split pass
             C* tb = (((D.G - 1) & 1) ? b0 : b1);
@@ -230,12 +334,16 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
                 if constexpr (PT::D.G >= 2) run_groups<A, PT::D, 1, S, Dd>(env, t, active, src, dst, b1, b0, tw, P.pc, P.inverse);
             };
             auto with_dst = [&](auto src) {
-                if constexpr (MODE == kC2C) run_from(src, dstg);
-                else run_from(src, dsts);
+                if constexpr (MODE == kR2C) run_from(src, dsts);
+                else run_from(src, dstg);
             };
-            if constexpr (kRing) with_dst(SrcShared<A>{srow});
+            if constexpr (MODE == kC2R) {
+                // kiss_fftri: the split pre pass is evaluated inside the first group's loads (SrcC2RFused)
+                if constexpr (kRing) with_dst(SrcC2RFused<A, true>{srow, P.stw, PT::D.N});
+                else with_dst(SrcC2RFused<A, false>{P.in + b * P.in_dist, P.stw, PT::D.N});
+            } else if constexpr (kRing) with_dst(SrcShared<A>{srow});
             else with_dst(SrcGlobal<A, true>{P.in + b * P.in_dist, 1});   // contiguous rows (other strides: generic kernel)
-            if constexpr (MODE == kC2C) {
+            if constexpr (MODE != kR2C) {
                 if constexpr (D.G >= 2) par ^= (D.G - 1) & 1;
             } else {
                 env.sync();
@@ -271,33 +379,6 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             env.sync();
             run_groups<A, D, 1>(env, t, active, src, dst, b1, b0, tw, P.pc, P.inverse);
             par ^= (D.G - 1) & 1;
-        } else {   // kC2R
-            constexpr int nc = D.N;
-            // split pre pass writes T[] (natural order) into b1, group 0 then reads it from shared memory
-            if (active) {
-                // split pre pass (kiss_fftr.c:131-153), unrolled like the post pass
-                const C* in = kRing ? srow : P.in + b * P.in_dist;
-                constexpr int kPairs = nc / 2 + 1, kIt = (kPairs + PT::D.team - 1) / PT::D.team;
-                static_for<kIt>([&](auto I) {
-                    const int k = t + decltype(I)::value * PT::D.team;
-                    if ((decltype(I)::value + 1) * PT::D.team <= kPairs || k < kPairs) {
-                        X Fk = A::load(LY::kRing ? in[k] : ld_stream(in + k));
-                        X Fnk = A::load(LY::kRing ? in[nc - k] : ld_stream(in + (nc - k)));
-                        X st = (k == 0) ? Fk : A::load(TwTab<A>::ro_load_c(P.stw + (k - 1)));
-                        X Tk, Tnk;
-                        fftri_pre_pair<A>(k, Fk, Fnk, st, Tk, Tnk);
-                        b1[k] = A::store(Tk);
-                        if (k != 0) b1[nc - k] = A::store(Tnk);
-                    }
-                });
-            }
-            env.sync();
-            recycle();
-            SrcShared<A> src{b1};
-            DstGlobal<A> dst{P.out + b * P.out_dist};
-            // group 0 reads b1 (via src) and writes b0; g1 reads b0 writes b1 ...
-            run_groups<A, D, 0>(env, t, active, src, dst, b1, b0, tw, P.pc, P.inverse);
-            par ^= D.G & 1;
         }
         // single exchange buffer: the next tile's first group overwrites what the last group just read
         if constexpr (D.nbuf == 1) env.sync();

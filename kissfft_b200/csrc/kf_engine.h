@@ -249,7 +249,7 @@ KF_HD void run_group(int t, bool active, const Src& src, const Dst& dst, const t
             const int wbase = kLast ? kp : phys_rt(kp * Flo + off, D.logpad);
             static_for<R>([&](auto E) {
                 constexpr int e = decltype(E)::value;
-                if constexpr (kLast) dst.store(wbase + D.kout(g, e), v[e]);
+                if constexpr (kLast) dst.template put<it, e>(wbase + D.kout(g, e), v[e]);
                 else if constexpr (kLinWr) wr[wbase + D.phys(D.kout(g, e) * Flo)] = A::store(v[e]);
                 else wr[phys_rt((kp + D.kout(g, e)) * Flo + off, D.logpad)] = A::store(v[e]);
             });

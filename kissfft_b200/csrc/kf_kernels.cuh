@@ -15,6 +15,8 @@ struct DeviceEnv {
     __device__ __forceinline__ long long nblocks() const { return (long long)gridDim.x; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
     __device__ __forceinline__ unsigned char* smem() const { return smem_; }
+    template <class V>
+    __device__ __forceinline__ V shfl(V v, int src_lane) const { return __shfl_sync(0xffffffffu, v, src_lane); }
 
     // ---- mbarrier + bulk asynchronous copy (TMA engine, SASS: UBLKCP / SYNCS) ----
     static __device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

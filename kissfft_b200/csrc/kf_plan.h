@@ -45,6 +45,7 @@ struct PlanDesc {
                             //    the case in fixed point); 1 (float/double only): a butterfly whose already-transformed upper
                             //    digits are non-zero derives its twiddles as tw[q*F*k'] * tw[q*F*kabove] -- the first factor is the
                             //    table entry of the upper==0 butterfly (shared by the whole stage), the second a plan constant
+    int shfl_post;          // kiss_fftr: split post pass in registers via warp shuffles (needs team % 32 == 0)
     int nbuf;               // exchange buffers: 2 = ping-pong (default); 1 = single buffer + one extra barrier per tile,
                             // only for two-group plans in the C2C / column modes (halves shared memory => wider column tiles)
 
@@ -142,6 +143,13 @@ struct PlanDesc {
     }
     // register index of the first element whose upper digits (stages above s) form combination `up`
     KF_CE int upper_base(int g, int s, int up) const { return up * W(g, s) * p[s]; }
+    // last group only (F_lo == 1): register that holds output k' + j*items(g)
+    KF_CE int reg_of_j(int g, int j) const
+    {
+        for (int e = 0; e < R(g); ++e)
+            if (kout(g, e) == j * items(g)) return e;
+        return -1;
+    }
     KF_CE int phys(int a) const { return logpad >= 31 ? a : a + (a >> logpad); }
     // phys(base + delta) == phys(base) + phys(delta) for every work item of group g?  (no carry out of the low
     // logpad bits).  Reads: base = kp*Flo*R + off (off < Flo), delta = e*Flo.  Writes: base = kp*Flo + off

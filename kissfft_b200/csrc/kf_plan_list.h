@@ -14,7 +14,7 @@
 namespace kf {
 
 constexpr PlanDesc make_plan(int N, std::initializer_list<int> radices, std::initializer_list<int> groups, int team, int tpc,
-                             int logpad, int minblocks, int nstage = 0, int nbuf = 2, int twmode = 0)
+                             int logpad, int minblocks, int nstage = 0, int nbuf = 2, int twmode = 0, int shfl_post = 0)
 {
     PlanDesc d{};
     d.N = N;
@@ -29,6 +29,7 @@ constexpr PlanDesc make_plan(int N, std::initializer_list<int> radices, std::ini
     d.nstage = nstage;
     d.nbuf = nbuf;
     d.twmode = twmode;
+    d.shfl_post = shfl_post;
     return d;
 }
 
@@ -70,7 +71,7 @@ KF_PLAN(kP4096,    4096, {4, 4, 4, 4, 4, 4}, {2, 2, 2}, 256, 1,          4,  1, 
 
 #if defined(FIXED_POINT) && (FIXED_POINT == 16)
 // ---- Q15: 4-byte complex, integer-issue bound -------------------------------------------------------------
-KF_PLAN(kP1024,    1024, {4, 4, 4, 4, 4},    {2, 2, 1}, 64,  2, 4, 4, 2);
+KF_PLAN(kP1024,    1024, {4, 4, 4, 4, 4},    {2, 2, 1}, 64,  2, 4, 4, 2, 2, 0, 1);
 KF_PLAN(kP2048,    2048, {4, 4, 4, 4, 4, 2}, {2, 2, 2}, 128, 1, 4, 2, 1);
 KF_PLAN(kP1000,    1000, {4, 2, 5, 5, 5},    {2, 2, 1}, 50,  4, 4, 1, 2);
 KF_PLAN(kP1155,    1155, {3, 5, 7, 11},      {1, 1, 2}, 105, 2, 4, 1, 0);
@@ -104,8 +105,8 @@ KF_PLAN(kP2048col, 2048, {4, 4, 4, 4, 4, 2}, {2, 2, 2},    128, 2, 4, 1, 0);
 KF_PLAN(kP1024,    1024, {2, 4, 4, 4, 4, 2},    {3, 3},    32,  4, 5, 3, 1, 2, 1);
 KF_PLAN(kP2048,    2048, {4, 2, 4, 4, 4, 4},    {2, 2, 2}, 128, 1, 4, 3, 1, 2, 1);
 // kiss_fftr / kiss_fftri nfft = 4096 (packed complex length 2048): separately tuned per direction
-KF_PLAN(kP2048r2c, 2048, {4, 2, 4, 4, 4, 4},    {2, 2, 2}, 128, 1, 4, 4, 1, 2, 1);
-KF_PLAN(kP2048c2r, 2048, {4, 2, 4, 4, 4, 4},    {2, 2, 2}, 128, 2, 4, 2, 1, 2, 1);
+KF_PLAN(kP2048r2c, 2048, {2, 2, 4, 4, 2, 4, 4}, {2, 2, 3}, 128, 1, 4, 3, 1, 2, 1);
+KF_PLAN(kP2048c2r, 2048, {4, 2, 4, 4, 4, 4},    {2, 2, 2}, 128, 2, 4, 3, 1, 2, 1);
 KF_PLAN(kP1000,    1000, {5, 5, 5, 4, 2},       {3, 2},    40,  2, 5, 4, 1);
 KF_PLAN(kP1155,    1155, {3, 11, 5, 7},         {2, 2},    35,  2, 5, 5, 1);
 // kiss_fftnd axis pass: 16 adjacent columns per CTA (128-byte row segments), single exchange buffer

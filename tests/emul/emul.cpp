@@ -9,7 +9,9 @@
 #include <barrier>
 #include <cstdint>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -33,6 +35,23 @@ struct EmuEnv {
     long long nblocks() const { return nblocks_; }
     void sync() const { bar_->arrive_and_wait(); }
     unsigned char* smem() const { return smem_; }
+    // emulated warp shuffle: per-warp mailbox + per-warp barrier (all lanes of a warp call it convergently)
+    struct WarpBox { unsigned long long slot[32]; std::barrier<>* bar; };
+    WarpBox* boxes_;
+    template <class V>
+    V shfl(V v, int src_lane) const
+    {
+        WarpBox& wb = boxes_[tid_ / 32];
+        unsigned long long raw = 0;
+        std::memcpy(&raw, &v, sizeof(V));
+        wb.slot[tid_ % 32] = raw;
+        wb.bar->arrive_and_wait();
+        raw = wb.slot[src_lane];
+        wb.bar->arrive_and_wait();
+        V r;
+        std::memcpy(&r, &raw, sizeof(V));
+        return r;
+    }
     // emulated mbarrier: the 8 bytes hold a completion counter; the "bulk copy" is an immediate memcpy
     static std::atomic<unsigned long long>* ctr(void* bar) { return reinterpret_cast<std::atomic<unsigned long long>*>(bar); }
     void mbar_init(void* bar) const { ctr(bar)->store(0); }
@@ -82,11 +101,18 @@ static void run_cta_grid(int nthreads, long long nblocks, size_t smem_bytes, F&&
         std::vector<unsigned char> smem_store(smem_bytes + 256, 0xCD);
         unsigned char* smem_al = (unsigned char*)(((uintptr_t)smem_store.data() + 127) & ~(uintptr_t)127);
         std::barrier<> bar(nthreads);
+        const int nwarps = (nthreads + 31) / 32;
+        std::vector<EmuEnv::WarpBox> boxes(nwarps);
+        std::vector<std::unique_ptr<std::barrier<>>> wbars;
+        for (int w = 0; w < nwarps; ++w) {
+            wbars.emplace_back(new std::barrier<>(std::min(32, nthreads - 32 * w)));
+            boxes[w].bar = wbars.back().get();
+        }
         std::vector<std::thread> th;
         th.reserve(nthreads);
         for (int t = 0; t < nthreads; ++t)
             th.emplace_back([&, t]() {
-                EmuEnv env{t, nthreads, b, nblocks, smem_al, &bar};
+                EmuEnv env{t, nthreads, b, nblocks, smem_al, &bar, boxes.data()};
                 body(env);
             });
         for (auto& x : th) x.join();
