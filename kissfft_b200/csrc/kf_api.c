@@ -748,6 +748,7 @@ static int kf_host_pipeline(kf_chunk_fn fn, void *cfg, const void *in, void *out
     /* chunk so that one chunk moves ~32 MiB each way (PCIe-efficient, still >= 6 chunks for the big batches) */
     size_t rows = (size_t)(32u << 20) / (in_row_bytes > out_row_bytes ? in_row_bytes : out_row_bytes);
     if (rows < 1) rows = 1;
+    if (rows >= 64) rows &= ~(size_t)63; /* whole tiles for every fused plan (tpc <= 16) and 16-byte aligned chunk sizes */
     if (rows > howmany) rows = howmany;
     void *din[NS], *dout[NS];
     for (int s = 0; s < NS && !rc; ++s) {
