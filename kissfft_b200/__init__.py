@@ -21,6 +21,7 @@ API_SYMBOLS = (
     "kiss_fftr_alloc", "kiss_fftr", "kiss_fftri",
     "kiss_fftnd_alloc", "kiss_fftnd",
     "kiss_fftndr_alloc", "kiss_fftndr", "kiss_fftndri",
+    "kfc_fft", "kfc_ifft", "kfc_cleanup",
     "kiss_fft_batch_dev", "kiss_fftr_batch_dev", "kiss_fftri_batch_dev", "kiss_fftnd_dev", "kiss_fft_axis_pass_dev", "kiss_fft_planes_pass_dev", "kiss_fft_planes_pass_peers_dev",
     "kiss_fftndr_dev", "kiss_fftndri_dev", "kiss_fft_batch", "kiss_fftr_batch", "kiss_fftri_batch",
     "kiss_fft_cuda_last_error", "kiss_fft_cuda_launch_count", "kiss_fft_cuda_plan_kind", "kiss_fft_cuda_scalar_bytes",
@@ -75,6 +76,10 @@ class KissFFT:
         L.kiss_fft_stride.restype = None
         L.kiss_fft_stride.argtypes = [vp, vp, vp, ci]
         L.kiss_fft_cleanup.restype = None
+        for name in ("kfc_fft", "kfc_ifft"):
+            getattr(L, name).restype = None
+            getattr(L, name).argtypes = [ci, vp, vp]
+        L.kfc_cleanup.restype = None
         L.kiss_fft_next_fast_size.argtypes = [ci]
         L.kiss_fft_batch_dev.argtypes = [vp, vp, vp, sz, sz, sz, ci, vp]
         L.kiss_fftr_batch_dev.argtypes = [vp, vp, vp, sz, sz, sz, vp]

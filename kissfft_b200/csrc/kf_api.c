@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "../../include/kfc.h"
 #include "../../include/kiss_fft_cuda.h"
 #include "kf_internal.h"
 
@@ -325,8 +326,9 @@ static kf_devplan *g_plans = NULL;
 
 /* scratch pool (per process, used under g_stage_lock by the host-pointer entry points) */
 static pthread_mutex_t g_stage_lock = PTHREAD_MUTEX_INITIALIZER;
+static pthread_mutex_t g_mp_lock = PTHREAD_MUTEX_INITIALIZER; /* work buffers of the multi-pass path (slots 8-10) */
 typedef struct { void *ptr; size_t bytes; int device; } kf_buf;
-#define KF_NSLOTS 8
+#define KF_NSLOTS 11
 static kf_buf g_dev_bufs[KF_NSLOTS];
 static cudaStream_t g_streams[4];
 static int g_streams_dev = -1;
@@ -389,6 +391,7 @@ void kiss_fft_cleanup(void)
 {
     int cur = 0;
     cudaGetDevice(&cur);
+    pthread_mutex_lock(&g_mp_lock);
     pthread_mutex_lock(&g_stage_lock);
     pthread_mutex_lock(&g_lock);
     for (kf_devplan *e = g_plans; e;) {
@@ -419,6 +422,7 @@ void kiss_fft_cleanup(void)
     cudaSetDevice(cur);
     pthread_mutex_unlock(&g_lock);
     pthread_mutex_unlock(&g_stage_lock);
+    pthread_mutex_unlock(&g_mp_lock);
 }
 
 /* scratch slot `i`, at least `bytes` large, on the current device (caller holds g_stage_lock) */
@@ -470,6 +474,63 @@ static int kf_is_device_ptr(const void *p)
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+/* ---- execution: shared-memory kernels, or the multi-pass path for lengths that do not fit them --------------- */
+/* One radix stage per launch, ping-ponging between two dense work buffers (slots 8, 9); the real modes add a work
+ * buffer for the packed-complex array (slot 10) and a stand-alone split pass.  The work buffers are shared, so the
+ * call holds g_mp_lock and waits for the stream before releasing it. */
+static int kf_exec_multipass(int mode, const kf_devplan *dp, const void *d_in, void *d_out, long long howmany, long long in_dist,
+                             long long out_dist, long long in_stride, void *stream)
+{
+    const kfcu_plan *pl = &dp->plan;
+    const int N = pl->nfft, L = pl->nstages;
+    const size_t dense = sizeof(kiss_fft_cpx) * (size_t)N * (size_t)howmany;
+    pthread_mutex_lock(&g_mp_lock);
+    void *w0 = NULL, *w1 = NULL, *wt = NULL;
+    int rc = kf_scratch(8, dense, &w0);
+    if (!rc) rc = kf_scratch(9, dense, &w1);
+    if (!rc && (mode == KFCU_R2C || mode == KFCU_C2R)) rc = kf_scratch(10, dense, &wt);
+    const void *src = d_in;
+    void *dst_final = d_out;
+    long long sdist = in_dist, sstride = in_stride, ddist = out_dist;
+    if (!rc && mode == KFCU_C2R) {          /* F -> T (dense), then the inverse complex transform of T */
+        rc = kfcu_realpass(pl, 0, d_in, wt, howmany, in_dist, N, stream);
+        src = wt;
+        sdist = N;
+        sstride = 1;
+    }
+    if (!rc && mode == KFCU_R2C) {          /* complex transform into T (dense), split pass afterwards */
+        dst_final = wt;
+        ddist = N;
+    }
+    const void *cur = src;
+    for (int s = L - 1; !rc && s >= 0; --s) {
+        const int first = (s == L - 1), last = (s == 0);
+        void *out = last ? dst_final : ((cur == w0) ? w1 : w0);
+        if (last && L == 1 && cur == dst_final) {   /* single stage, in place: go through a work buffer */
+            rc = kfcu_stage(pl, s, cur, w0, howmany, sdist, N, sstride, first, 0, stream);
+            if (!rc)
+                rc = (int)cudaMemcpy2DAsync(dst_final, sizeof(kiss_fft_cpx) * (size_t)ddist, w0, sizeof(kiss_fft_cpx) * (size_t)N,
+                                            sizeof(kiss_fft_cpx) * (size_t)N, (size_t)howmany, cudaMemcpyDeviceToDevice,
+                                            (cudaStream_t)stream);
+            break;
+        }
+        rc = kfcu_stage(pl, s, cur, out, howmany, first ? sdist : N, last ? ddist : N, first ? sstride : 1, first, last, stream);
+        cur = out;
+    }
+    if (!rc && mode == KFCU_R2C) rc = kfcu_realpass(pl, 1, wt, d_out, howmany, N, out_dist, stream);
+    if (!rc) rc = (int)cudaStreamSynchronize((cudaStream_t)stream);
+    pthread_mutex_unlock(&g_mp_lock);
+    return rc;
+}
+
+static int kf_exec(int mode, const kf_devplan *dp, const void *d_in, void *d_out, long long howmany, long long in_dist,
+                   long long out_dist, long long in_stride, void *stream)
+{
+    int rc = kfcu_exec(mode, (kfcu_plan *)&dp->plan, d_in, d_out, howmany, in_dist, out_dist, in_stride, stream);
+    if (rc == KFCU_ETOOBIG) rc = kf_exec_multipass(mode, dp, d_in, d_out, howmany, in_dist, out_dist, in_stride, stream);
+    return rc;
+}
+
 /* ---- device-pointer batched entry points ---------------------------------------------------------------- */
 
 int kiss_fft_batch_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, size_t howmany, size_t in_dist,
@@ -481,7 +542,7 @@ int kiss_fft_batch_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx 
     }
     const kf_devplan *dp;
     KF_CHECK(kf_get_devplan(cfg, NULL, &dp));
-    KF_CHECK(kfcu_exec(KFCU_C2C, (kfcu_plan *)&dp->plan, d_in, d_out, (long long)howmany, (long long)in_dist, (long long)out_dist,
+    KF_CHECK(kf_exec(KFCU_C2C, dp, d_in, d_out, (long long)howmany, (long long)in_dist, (long long)out_dist,
                        (long long)in_stride, stream));
     return 0;
 }
@@ -497,7 +558,7 @@ int kiss_fft_axis_pass_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_
     KF_CHECK(kf_get_devplan(cfg, NULL, &dp));
     /* column i: elements d_in[i + j*col_stride]; written as row i: d_out[i*nfft + k]  (kiss_fftnd.c:176-177) */
     const int mode = (col_stride == 1 && ncols == 1) ? KFCU_C2C : KFCU_C2C_COL;
-    KF_CHECK(kfcu_exec(mode, (kfcu_plan *)&dp->plan, d_in, d_out, (long long)ncols, 1, (long long)cfg->nfft, (long long)col_stride, stream));
+    KF_CHECK(kf_exec(mode, dp, d_in, d_out, (long long)ncols, 1, (long long)cfg->nfft, (long long)col_stride, stream));
     return 0;
 }
 
@@ -553,7 +614,7 @@ int kiss_fftr_batch_dev(kiss_fftr_cfg cfg, const kiss_fft_scalar *d_time, kiss_f
     }
     const kf_devplan *dp;
     KF_CHECK(kf_get_devplan(cfg->substate, cfg->super_twiddles, &dp));
-    KF_CHECK(kfcu_exec(KFCU_R2C, (kfcu_plan *)&dp->plan, d_time, d_freq, (long long)howmany, (long long)(time_dist / 2),
+    KF_CHECK(kf_exec(KFCU_R2C, dp, d_time, d_freq, (long long)howmany, (long long)(time_dist / 2),
                        (long long)freq_dist, 1, stream));
     return 0;
 }
@@ -575,7 +636,7 @@ int kiss_fftri_batch_dev(kiss_fftr_cfg cfg, const kiss_fft_cpx *d_freq, kiss_fft
     }
     const kf_devplan *dp;
     KF_CHECK(kf_get_devplan(cfg->substate, cfg->super_twiddles, &dp));
-    KF_CHECK(kfcu_exec(KFCU_C2R, (kfcu_plan *)&dp->plan, d_freq, d_time, (long long)howmany, (long long)freq_dist,
+    KF_CHECK(kf_exec(KFCU_C2R, dp, d_freq, d_time, (long long)howmany, (long long)freq_dist,
                        (long long)(time_dist / 2), 1, stream));
     return 0;
 }
@@ -992,4 +1053,63 @@ int kiss_fft_cuda_plan_kind(int nfft)
     if (nfft <= 0) return -1;
     if (kfcu_has_fused(nfft, KFCU_C2C)) return 1;
     return nfft <= kfcu_generic_max_nfft() ? 0 : -1;
+}
+
+/* ---- kfc: cfg cache (reference kfc.c:13-83) --------------------------------------------------------------- */
+typedef struct kfc_entry {
+    int nfft, inverse;
+    kiss_fft_cfg cfg;
+    struct kfc_entry *next;
+} kfc_entry;
+static kfc_entry *g_kfc = NULL;
+static pthread_mutex_t g_kfc_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static kiss_fft_cfg kfc_find(int nfft, int inverse)
+{
+    pthread_mutex_lock(&g_kfc_lock);
+    kfc_entry *e;
+    for (e = g_kfc; e; e = e->next)
+        if (e->nfft == nfft && e->inverse == inverse) break;
+    if (!e) {
+        e = (kfc_entry *)malloc(sizeof(*e));
+        if (e) {
+            e->nfft = nfft;
+            e->inverse = inverse;
+            e->cfg = kiss_fft_alloc(nfft, inverse, NULL, NULL);
+            if (!e->cfg) {
+                free(e);
+                e = NULL;
+            } else {
+                e->next = g_kfc;
+                g_kfc = e;
+            }
+        }
+    }
+    pthread_mutex_unlock(&g_kfc_lock);
+    return e ? e->cfg : NULL;
+}
+
+void kfc_fft(int nfft, const kiss_fft_cpx *fin, kiss_fft_cpx *fout)
+{
+    kiss_fft_cfg cfg = kfc_find(nfft, 0);
+    if (cfg) kiss_fft(cfg, fin, fout);
+}
+
+void kfc_ifft(int nfft, const kiss_fft_cpx *fin, kiss_fft_cpx *fout)
+{
+    kiss_fft_cfg cfg = kfc_find(nfft, 1);
+    if (cfg) kiss_fft(cfg, fin, fout);
+}
+
+void kfc_cleanup(void)
+{
+    pthread_mutex_lock(&g_kfc_lock);
+    for (kfc_entry *e = g_kfc; e;) {
+        kfc_entry *n = e->next;
+        kiss_fft_free(e->cfg);
+        free(e);
+        e = n;
+    }
+    g_kfc = NULL;
+    pthread_mutex_unlock(&g_kfc_lock);
 }

@@ -521,4 +521,111 @@ KF_HD void generic_body(const GParams<A>& G, Env& env)
     }
 }
 
+// =========================================================================================================
+// Multi-pass path for lengths whose exchange buffers do not fit in shared memory: one radix stage of the same
+// Stockham recurrence per launch, levels kept in global memory (autosort layout, dense rows of N elements in the
+// work buffers; the first stage reads the caller's rows with their stride/distance, the last stage writes the
+// caller's output rows).  Slow (2*L passes over HBM) but it makes every nfft the reference accepts work.
+// =========================================================================================================
+template <class A>
+struct StageParams {
+    const typename A::C* in;
+    typename A::C* out;
+    long long batch, in_dist, out_dist, in_stride;   // only used by the first (in_*) / last (out_dist) stage
+    int N, p, m, F;                                  // stage: radix p, span m, twiddle stride F = prod of outer radices
+    int first, last;
+    const typename A::C* tw;
+    PlanConsts<A> pc;
+    int inverse;
+};
+
+template <class A, class Env>
+KF_HD void stage_body(const StageParams<A>& S, Env& env)
+{
+    typedef typename A::C C;
+    typedef cx<typename A::R> X;
+    const TwTab<A> tw{S.tw, nullptr, nullptr, nullptr};
+    const int N = S.N, p = S.p, m = S.m, F = S.F;
+    const bool small = (p == 2 || p == 3 || p == 4 || p == 5);
+    const long long per = small ? N / p : N;
+    const long long total = S.batch * per;
+    const long long step = env.nblocks() * env.nthreads();
+    for (long long i = env.bid() * env.nthreads() + env.tid(); i < total; i += step) {
+        const long long b = i / per;
+        const int j = (int)(i % per);
+        const C* in = S.first ? S.in + b * S.in_dist : S.in + b * N;
+        const long long istr = S.first ? S.in_stride : 1;
+        C* out = S.last ? S.out + b * S.out_dist : S.out + b * N;
+        if (small) {
+            const int k = j / F, off = j % F;
+            X v[5];
+            for (int q = 0; q < p; ++q) v[q] = A::load(in[(long long)((k * p + q) * F + off) * istr]);
+            if (p == 2) bfly2<A, false>(v, tw.get(F * k));
+            else if (p == 4) bfly4<A, false>(v, tw.get(F * k), tw.get(2 * F * k), tw.get(3 * F * k), A::sign_of(S.inverse));
+            else if (p == 3) bfly3<A, false>(v, tw.get(F * k), tw.get(2 * F * k), S.pc.epi3.i);
+            else bfly5<A, false>(v, tw.get(F * k), tw.get(2 * F * k), tw.get(3 * F * k), tw.get(4 * F * k), S.pc.ya, S.pc.yb);
+            for (int q = 0; q < p; ++q) out[(k + q * m) * F + off] = A::store(v[q]);
+        } else {
+            // one output of kf_bfly_generic (kiss_fft.c:192-233) per thread
+            const int k = j / F, off = j % F;
+            const int q1 = k / m, u = k % m;
+            const int stepw = (int)(((long long)F * (u + q1 * m)) % N);
+            int twidx = 0;
+            X s0 = A::load(in[(long long)((u * p) * F + off) * istr]);
+            X acc{A::divk_rt(s0.r, p), A::divk_rt(s0.i, p)};
+            for (int q = 1; q < p; ++q) {
+                twidx += stepw;
+                if (twidx >= N) twidx -= N;
+                X sq = A::load(in[(long long)((u * p + q) * F + off) * istr]);
+                sq = X{A::divk_rt(sq.r, p), A::divk_rt(sq.i, p)};
+                acc = cadd<A>(acc, A::cmul_bf(sq, tw.get(twidx)));
+            }
+            out[j] = A::store(cwrap<A>(acc));
+        }
+    }
+}
+
+// split passes of the real transforms as stand-alone passes (multi-pass path only)
+template <class A>
+struct RealPassParams {
+    const typename A::C* in;
+    typename A::C* out;
+    long long batch, in_dist, out_dist;
+    int nc;          // packed complex length
+    int post;        // 1: kiss_fftr post pass T[nc] -> F[nc+1]; 0: kiss_fftri pre pass F[nc+1] -> T[nc]
+    const typename A::C* stw;
+};
+
+template <class A, class Env>
+KF_HD void realpass_body(const RealPassParams<A>& S, Env& env)
+{
+    typedef typename A::C C;
+    typedef cx<typename A::R> X;
+    const int nc = S.nc, pairs = nc / 2 + 1;
+    const long long total = S.batch * pairs;
+    const long long step = env.nblocks() * env.nthreads();
+    for (long long i = env.bid() * env.nthreads() + env.tid(); i < total; i += step) {
+        const long long b = i / pairs;
+        const int k = (int)(i % pairs);
+        const C* in = S.in + b * S.in_dist;
+        C* out = S.out + b * S.out_dist;
+        if (S.post) {
+            X Tk = A::load(in[k]);
+            X Tnk = (k == 0) ? Tk : A::load(in[nc - k]);
+            X st = (k == 0) ? Tk : A::load(S.stw[k - 1]);
+            X ok, onk;
+            fftr_post_pair<A>(k, nc, Tk, Tnk, st, ok, onk);
+            if (k != nc - k) out[k] = A::store(ok);
+            out[nc - k] = A::store(onk);
+        } else {
+            X Fk = A::load(in[k]), Fnk = A::load(in[nc - k]);
+            X st = (k == 0) ? Fk : A::load(S.stw[k - 1]);
+            X Tk, Tnk;
+            fftri_pre_pair<A>(k, Fk, Fnk, st, Tk, Tnk);
+            if (k != nc - k) out[k] = A::store(Tk);
+            if (k != 0) out[nc - k] = A::store(Tnk);
+        }
+    }
+}
+
 }   // namespace kf

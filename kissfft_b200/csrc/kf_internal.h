@@ -45,6 +45,14 @@ int kfcu_exec_planes(kfcu_plan *plan, const void *d_in, void *d_out, long long n
 int kfcu_exec_planes_peers(kfcu_plan *plan, const void *d_in, void *const *peers, int npeers, long long nplanes,
                            long long cols_per_peer, long long col_stride, long long in_pdist, long long out_pdist, void *stream);
 
+/* Multi-pass path: stage s of the plan as one launch over global memory (levels in autosort layout, dense rows of nfft
+ * in the work buffers).  first: read the caller's rows (in_dist / in_stride); last: write the caller's rows (out_dist). */
+int kfcu_stage(const kfcu_plan *plan, int s, const void *d_in, void *d_out, long long batch, long long in_dist,
+               long long out_dist, long long in_stride, int first, int last, void *stream);
+/* stand-alone split pass of the real transforms: post != 0: T[nc] -> F[nc+1] (kiss_fftr.c:88-116), else F -> T */
+int kfcu_realpass(const kfcu_plan *plan, int post, const void *d_in, void *d_out, long long batch, long long in_dist,
+                  long long out_dist, void *stream);
+
 /* out[c][r] = in[r][c] for a rows x cols array of complex elements (kiss_fftndr's bin-major <-> row-major
  * scatter loops, kiss_fftndr.c:101-102, 107-108) */
 int kfcu_transpose(const void *d_in, void *d_out, long long rows, long long cols, void *stream);

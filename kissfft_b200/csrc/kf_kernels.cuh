@@ -74,6 +74,20 @@ __global__ void __launch_bounds__(256) kf_generic_kernel(const __grid_constant__
     generic_body<A>(G, env);
 }
 
+template <class A>
+__global__ void __launch_bounds__(256) kf_stage_kernel(const __grid_constant__ StageParams<A> S)
+{
+    DeviceEnv env{nullptr};
+    stage_body<A>(S, env);
+}
+
+template <class A>
+__global__ void __launch_bounds__(256) kf_realpass_kernel(const __grid_constant__ RealPassParams<A> S)
+{
+    DeviceEnv env{nullptr};
+    realpass_body<A>(S, env);
+}
+
 // tiled transpose of a rows x cols array of storage complexes (32 x 32 tiles, +1 column of padding)
 template <class C>
 __global__ void __launch_bounds__(256) kf_transpose_kernel(const C* __restrict__ in, C* __restrict__ out, long long rows,

@@ -255,6 +255,64 @@ extern "C" int kfcu_exec_planes_peers(kfcu_plan* plan, const void* d_in, void* c
     return launch_generic(kC2CCol, plan, P, (cudaStream_t)stream);
 }
 
+// ---- multi-pass path (lengths beyond the shared-memory kernels) -------------------------------------------------
+extern "C" int kfcu_stage(const kfcu_plan* plan, int s, const void* d_in, void* d_out, long long batch, long long in_dist,
+                          long long out_dist, long long in_stride, int first, int last, void* stream)
+{
+    if (!plan || !d_in || !d_out || s < 0 || s >= plan->nstages) return KFCU_EINVAL;
+    if (batch <= 0) return 0;
+    KParams<AT> P = make_params(plan, d_in, d_out, batch, in_dist, out_dist, in_stride);
+    StageParams<AT> S;
+    S.in = (const CT*)d_in;
+    S.out = (CT*)d_out;
+    S.batch = batch;
+    S.in_dist = in_dist;
+    S.out_dist = out_dist;
+    S.in_stride = in_stride;
+    S.N = plan->nfft;
+    S.p = plan->p[s];
+    S.m = plan->m[s];
+    int F = 1;
+    for (int j = 0; j < s; ++j) F *= plan->p[j];
+    S.F = F;
+    S.first = first;
+    S.last = last;
+    S.tw = P.tw;
+    S.pc = P.pc;
+    S.inverse = plan->inverse;
+    const bool small = (S.p == 2 || S.p == 3 || S.p == 4 || S.p == 5);
+    const long long work = batch * (small ? plan->nfft / S.p : plan->nfft);
+    long long grid = (work + 255) / 256;
+    const long long cap = (long long)device_info().sms * 16;
+    if (grid > cap) grid = cap;
+    kf_stage_kernel<AT><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(S);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int kfcu_realpass(const kfcu_plan* plan, int post, const void* d_in, void* d_out, long long batch, long long in_dist,
+                             long long out_dist, void* stream)
+{
+    if (!plan || !d_in || !d_out || (!plan->d_stw && plan->nfft > 1)) return KFCU_EINVAL;
+    if (batch <= 0) return 0;
+    RealPassParams<AT> S;
+    S.in = (const CT*)d_in;
+    S.out = (CT*)d_out;
+    S.batch = batch;
+    S.in_dist = in_dist;
+    S.out_dist = out_dist;
+    S.nc = plan->nfft;
+    S.post = post;
+    S.stw = (const CT*)plan->d_stw;
+    const long long work = batch * (plan->nfft / 2 + 1);
+    long long grid = (work + 255) / 256;
+    const long long cap = (long long)device_info().sms * 16;
+    if (grid > cap) grid = cap;
+    kf_realpass_kernel<AT><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(S);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int kfcu_transpose(const void* d_in, void* d_out, long long rows, long long cols, void* stream)
 {
     if (!d_in || !d_out || rows < 0 || cols < 0) return KFCU_EINVAL;

@@ -190,3 +190,28 @@ extern "C" int emul_generic(int nfft, int mode, int inverse, const int* factors,
     run_cta_grid(nthreads, nblocks, smem, [&](EmuEnv& env) { generic_body<AT>(G, env); });
     return 0;
 }
+
+// ---- multi-pass path: one stage / one real split pass per call ------------------------------------------------
+extern "C" int emul_stage(int nfft, int inverse, int p, int m, int F, const void* in, void* out, long long batch,
+                          long long in_dist, long long out_dist, long long in_stride, int first, int last, const void* tw,
+                          int nthreads, long long nblocks)
+{
+    KParams<AT> P = mk_params(nfft, inverse, in, out, batch, in_dist, out_dist, in_stride, tw, nullptr);
+    StageParams<AT> S;
+    S.in = (const CT*)in; S.out = (CT*)out; S.batch = batch;
+    S.in_dist = in_dist; S.out_dist = out_dist; S.in_stride = in_stride;
+    S.N = nfft; S.p = p; S.m = m; S.F = F; S.first = first; S.last = last;
+    S.tw = (const CT*)tw; S.pc = P.pc; S.inverse = inverse;
+    run_cta_grid(nthreads, nblocks, 16, [&](EmuEnv& env) { stage_body<AT>(S, env); });
+    return 0;
+}
+
+extern "C" int emul_realpass(int nc, int post, const void* in, void* out, long long batch, long long in_dist, long long out_dist,
+                             const void* stw, int nthreads, long long nblocks)
+{
+    RealPassParams<AT> S;
+    S.in = (const CT*)in; S.out = (CT*)out; S.batch = batch; S.in_dist = in_dist; S.out_dist = out_dist;
+    S.nc = nc; S.post = post; S.stw = (const CT*)stw;
+    run_cta_grid(nthreads, nblocks, 16, [&](EmuEnv& env) { realpass_body<AT>(S, env); });
+    return 0;
+}

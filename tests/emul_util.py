@@ -41,6 +41,8 @@ class Emulator:
         vp, ci, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
         self.lib.emul_fused.argtypes = [ci, ci, ci, vp, vp, ll, ll, ll, ll, vp, vp, ll]
         self.lib.emul_generic.argtypes = [ci, ci, ci, vp, ci, vp, vp, ll, ll, ll, ll, vp, vp, ci, ci, ll]
+        self.lib.emul_stage.argtypes = [ci, ci, ci, ci, ci, vp, vp, ll, ll, ll, ll, ci, ci, vp, ci, ll]
+        self.lib.emul_realpass.argtypes = [ci, ci, vp, vp, ll, ll, ll, vp, ci, ll]
 
     def plans(self):
         return [(self.lib.emul_plan_nfft(i), [m for m in range(4) if self.lib.emul_plan_has_mode(i, m)])
@@ -68,3 +70,27 @@ class Emulator:
         rc = self.lib.emul_generic(nfft, mode, int(inverse), _p(fac), len(factors), _p(inp), _p(out), howmany, in_dist,
                                    out_dist, in_stride, _p(tw), _p(stw), tpc, nthreads, nblocks)
         assert rc == 0
+
+
+    def multipass(self, nfft, inverse, factors, inp, out, howmany, in_dist, out_dist, in_stride, tw):
+        """mirrors kf_api.c:kf_exec_multipass for the complex modes: one stage per call, dense work buffers"""
+        L = len(factors)
+        w = [np.zeros((howmany, nfft, 2), inp.dtype), np.zeros((howmany, nfft, 2), inp.dtype)]
+        cur, F = inp, 1
+        Fs = []
+        for p, m in factors:
+            Fs.append(F)
+            F *= p
+        wi = 0
+        for s in range(L - 1, -1, -1):
+            first, last = int(s == L - 1), int(s == 0)
+            dst = out if last else w[wi]
+            p, m = factors[s]
+            rc = self.lib.emul_stage(nfft, int(inverse), p, m, Fs[s], _p(cur), _p(dst), howmany, in_dist if first else nfft,
+                                     out_dist if last else nfft, in_stride if first else 1, first, last, _p(tw), 64, 3)
+            assert rc == 0
+            cur = dst
+            wi ^= 1
+
+    def realpass(self, nc, post, inp, out, howmany, in_dist, out_dist, stw):
+        assert self.lib.emul_realpass(nc, int(post), _p(inp), _p(out), howmany, in_dist, out_dist, _p(stw), 64, 3) == 0

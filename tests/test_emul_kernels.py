@@ -133,3 +133,35 @@ def test_q15_full_scale_wraparound():
         y = np.zeros((3, n), np.int16)
         em.fused(nc, C2R, 1, S, y, 3, nc + 1, nc, 1, o.twiddles(nc, 1), o.super_twiddles(nc, 1), factors=o.factor(nc))
         assert np.array_equal(y, o.fftri(S)), n
+
+
+@pytest.mark.parametrize("nfft", [2, 7, 12, 30, 143, 360, 1000, 1024, 1155])
+def test_multipass_stages(env, nfft):
+    """the global-memory multi-pass path (one radix stage per launch) used for lengths beyond shared memory"""
+    tname, o, em = env
+    howmany, stride = 3, 2
+    for inverse in (0, 1):
+        x = random_input(tname, (howmany, nfft * stride + 1), 600 + nfft)
+        out = np.zeros((howmany, nfft + 2, 2), x.dtype)
+        em.multipass(nfft, inverse, o.factor(nfft), x, out, howmany, nfft * stride + 1, nfft + 2, stride, o.twiddles(nfft, inverse))
+        check(tname, out[:, :nfft], o.fft(x[:, : nfft * stride], inverse, in_stride=stride, nfft=nfft), nfft)
+        assert not out[:, nfft:].any()
+
+
+def test_multipass_real(env):
+    tname, o, em = env
+    for n in (4, 30, 1000):
+        nc, howmany = n // 2, 3
+        xr = random_input(tname, (howmany, n), 700 + n, complex_=False)
+        T = np.zeros((howmany, nc, 2), xr.dtype)
+        em.multipass(nc, 0, o.factor(nc), xr, T, howmany, nc, nc, 1, o.twiddles(nc, 0))
+        X = np.zeros((howmany, nc + 1, 2), xr.dtype)
+        em.realpass(nc, 1, T, X, howmany, nc, nc + 1, o.super_twiddles(nc, 0))
+        want = o.fftr(xr)
+        check(tname, X, want, n)
+        spec = want if tname in TOL else random_input(tname, (howmany, nc + 1), 701 + n)
+        T2 = np.zeros((howmany, nc, 2), xr.dtype)
+        em.realpass(nc, 0, spec, T2, howmany, nc + 1, nc, o.super_twiddles(nc, 1))
+        y = np.zeros((howmany, n), xr.dtype)
+        em.multipass(nc, 1, o.factor(nc), T2, y, howmany, nc, nc, 1, o.twiddles(nc, 1))
+        check(tname, y, o.fftri(spec), n)

@@ -235,6 +235,54 @@ def test_reference_api_with_host_pointers(ctx):
     lib.free(cfgi)
 
 
+@pytest.mark.parametrize("nfft", [16384, 30000, 32768, 65536])
+def test_large_lengths_multipass(ctx, nfft):
+    """lengths beyond the shared-memory kernels run one radix stage per launch over global memory"""
+    tname, lib, o = ctx
+    howmany = 3
+    x = random_input(tname, (howmany, nfft), 90 + nfft)
+    for inverse in (False, True):
+        cfg = lib.alloc(nfft, inverse)
+        d_in, d_out = dev(x), dev(np.zeros_like(x))
+        lib.fft_batch_dev(cfg, d_in, d_out, howmany, nfft, nfft)
+        torch.cuda.synchronize()
+        check(tname, host(d_out), o.fft(x, inverse), nfft, "large c2c")
+        lib.fft_batch_dev(cfg, d_in, d_in, howmany, nfft, nfft)     # in place
+        torch.cuda.synchronize()
+        check(tname, host(d_in), o.fft(x, inverse), nfft, "large c2c in place")
+        lib.free(cfg)
+    n = 2 * nfft
+    xr = random_input(tname, (howmany, n), 91 + nfft, complex_=False)
+    cfg = lib.allocr(n, False)
+    d_x, d_X = dev(xr), dev(np.zeros((howmany, nfft + 1, 2), xr.dtype))
+    lib.fftr_batch_dev(cfg, d_x, d_X, howmany, n, nfft + 1)
+    torch.cuda.synchronize()
+    want = o.fftr(xr)
+    check(tname, host(d_X), want, n, "large fftr")
+    lib.free(cfg)
+    spec = want if tname in TOL else random_input(tname, (howmany, nfft + 1), 92 + nfft)
+    cfgi = lib.allocr(n, True)
+    d_S, d_y = dev(spec), dev(np.zeros((howmany, n), xr.dtype))
+    lib.fftri_batch_dev(cfgi, d_S, d_y, howmany, nfft + 1, n)
+    torch.cuda.synchronize()
+    check(tname, host(d_y), o.fftri(spec), n, "large fftri")
+    lib.free(cfgi)
+
+
+def test_kfc_cache(ctx):
+    """kfc_fft / kfc_ifft (reference kfc.c:63-83, self-test kfc.c:85-108) on host buffers"""
+    tname, lib, o = ctx
+    for nfft in (512, 360):
+        x = random_input(tname, (nfft,), 70 + nfft)
+        out = np.zeros_like(x)
+        lib.lib.kfc_fft(nfft, x.ctypes.data, out.ctypes.data)
+        check(tname, out, o.fft(x), nfft, "kfc_fft")
+        back = np.zeros_like(x)
+        lib.lib.kfc_ifft(nfft, x.ctypes.data, back.ctypes.data)
+        check(tname, back, o.fft(x, True), nfft, "kfc_ifft")
+    lib.lib.kfc_cleanup()
+
+
 def test_host_batch_pipeline(ctx):
     tname, lib, o = ctx
     nfft, howmany = 1024, 300
