@@ -31,6 +31,13 @@ def build(tname):
     return lib
 
 
+def build_all(types=("float", "double", "int16_t", "int32_t")):
+    """compile the four emulator libraries concurrently (each takes about a minute of g++ time when stale)"""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(len(types)) as ex:
+        return list(ex.map(build, types))
+
+
 def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 

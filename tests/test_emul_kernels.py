@@ -17,6 +17,12 @@ def check(tname, got, want, nfft):
         assert np.array_equal(got, want)
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _emulators_built():
+    from tests.emul_util import build_all
+    build_all()
+
+
 @pytest.fixture(scope="module", params=TYPES)
 def env(request):
     return request.param, Oracle(request.param), Emulator(request.param)
