@@ -81,6 +81,23 @@ int KISS_FFT_API kiss_fft_batch(kiss_fft_cfg cfg, const kiss_fft_cpx *in, kiss_f
 int KISS_FFT_API kiss_fftr_batch(kiss_fftr_cfg cfg, const kiss_fft_scalar *timedata, kiss_fft_cpx *freqdata, size_t howmany);
 int KISS_FFT_API kiss_fftri_batch(kiss_fftr_cfg cfg, const kiss_fft_cpx *freqdata, kiss_fft_scalar *timedata, size_t howmany);
 
+/* ---- fused fast convolution (float / double builds only, like the reference: kiss_fastfir.c:152) ------------------
+ * The overlap-scrap FIR filter of the reference's tools/kiss_fastfir.c (complex-sample build): FFT -> multiply by the
+ * filter's frequency response -> IFFT for every block, fused into ONE kernel (the spectrum never leaves the SM).
+ *   kiss_fastconv_alloc   kiss_fastfir_alloc (kiss_fastfir.c:59-165): *pnfft == 0 picks the reference's default size
+ *   kiss_fastconv_dev     kff_nocopy / fastconv1buf (kiss_fastfir.c:167-206) on device buffers: processes every complete
+ *                         nfft-sample block of the n input samples, block b reading d_in + b*ngood and writing ngood
+ *                         samples at d_out + b*ngood (ngood = nfft - n_imp_resp + 1); *nprocessed = blocks*ngood. */
+#ifndef FIXED_POINT
+typedef struct kiss_fastconv_state *kiss_fastconv_cfg;
+kiss_fastconv_cfg KISS_FFT_API kiss_fastconv_alloc(const kiss_fft_cpx *imp_resp, size_t n_imp_resp, size_t *pnfft);
+void KISS_FFT_API kiss_fastconv_free(kiss_fastconv_cfg cfg);
+size_t KISS_FFT_API kiss_fastconv_block_advance(kiss_fastconv_cfg cfg);
+size_t KISS_FFT_API kiss_fastconv_nfft(kiss_fastconv_cfg cfg);
+int KISS_FFT_API kiss_fastconv_dev(kiss_fastconv_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, size_t n,
+                                   size_t *nprocessed, void *stream);
+#endif
+
 /* ---- introspection ---------------------------------------------------------------------------------------- */
 const char KISS_FFT_API *kiss_fft_cuda_last_error(void);
 /* kernels launched by this library since it was loaded */

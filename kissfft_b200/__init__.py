@@ -29,6 +29,11 @@ API_SYMBOLS = (
 )
 
 
+# float / double builds only (the reference's fast FIR "won't work for fixed point", kiss_fastfir.c:152)
+FASTCONV_SYMBOLS = ("kiss_fastconv_alloc", "kiss_fastconv_free", "kiss_fastconv_block_advance", "kiss_fastconv_nfft",
+                    "kiss_fastconv_dev")
+
+
 def lib_path(tname):
     return os.path.join(HERE, "lib", "libkissfft-%s.so" % tname)
 
@@ -100,6 +105,16 @@ class KissFFT:
         L.kiss_fft_cuda_force_generic.restype = None
         L.kiss_fft_cuda_set_grid_limit.argtypes = [ci]
         L.kiss_fft_cuda_set_grid_limit.restype = None
+        if tname in ("float", "double"):
+            L.kiss_fastconv_alloc.restype = vp
+            L.kiss_fastconv_alloc.argtypes = [vp, sz, ctypes.POINTER(sz)]
+            L.kiss_fastconv_free.argtypes = [vp]
+            L.kiss_fastconv_free.restype = None
+            L.kiss_fastconv_block_advance.argtypes = [vp]
+            L.kiss_fastconv_block_advance.restype = sz
+            L.kiss_fastconv_nfft.argtypes = [vp]
+            L.kiss_fastconv_nfft.restype = sz
+            L.kiss_fastconv_dev.argtypes = [vp, vp, vp, sz, ctypes.POINTER(sz), vp]
         self._libc = ctypes.CDLL(None)
         self._libc.free.argtypes = [vp]
         if L.kiss_fft_cuda_scalar_bytes() != np.dtype(self.dtype).itemsize:
@@ -212,6 +227,25 @@ class KissFFT:
 
     def fftndri(self, cfg, freqdata, timedata):
         self.lib.kiss_fftndri(cfg, _ptr(freqdata), _ptr(timedata))
+
+    # ---- fused fast convolution (float / double) ----
+    def fastconv_alloc(self, imp_resp, nfft=0):
+        """imp_resp: (n, 2) array of the build's scalar type.  Returns (cfg, nfft, ngood)."""
+        imp = np.ascontiguousarray(imp_resp, dtype=self.dtype)
+        n = ctypes.c_size_t(int(nfft))
+        cfg = self.lib.kiss_fastconv_alloc(_ptr(imp), imp.shape[0], ctypes.byref(n))
+        if not cfg:
+            raise KissFFTError("kiss_fastconv_alloc failed")
+        return cfg, int(n.value), int(self.lib.kiss_fastconv_block_advance(cfg))
+
+    def fastconv_dev(self, cfg, d_in, d_out, n, stream=0):
+        done = ctypes.c_size_t(0)
+        self._check(self.lib.kiss_fastconv_dev(cfg, _ptr(d_in), _ptr(d_out), n, ctypes.byref(done), ctypes.c_void_p(stream)),
+                    "kiss_fastconv_dev")
+        return int(done.value)
+
+    def fastconv_free(self, cfg):
+        self.lib.kiss_fastconv_free(cfg)
 
     # ---- introspection ----
     def launch_count(self):

@@ -399,7 +399,7 @@ void kiss_fft_cleanup(void)
         cudaSetDevice(e->device);
         cudaFree((void *)e->plan.d_tw);
         if (e->plan.d_stw) cudaFree((void *)e->plan.d_stw);
-        for (int m = 0; m < 4; ++m)
+        for (int m = 0; m < 5; ++m)
             if (e->plan.d_gtw[m]) cudaFree(e->plan.d_gtw[m]);
         free(e->h_tw);
         free(e);
@@ -1113,3 +1113,99 @@ void kfc_cleanup(void)
     g_kfc = NULL;
     pthread_mutex_unlock(&g_kfc_lock);
 }
+
+/* ---- fast convolution (reference tools/kiss_fastfir.c, complex-sample build) ------------------------------------ */
+#ifndef FIXED_POINT
+#define KF_MAGIC_FC 0x4b464643u
+struct kiss_fastconv_state {
+    uint32_t magic;
+    int nfft, ngood;
+    kiss_fft_cfg fwd, inv;
+    kiss_fft_cpx *h_resp; /* host copy of the scaled frequency response */
+    void *d_resp;         /* device copy (current device at alloc time) */
+    int device;
+};
+
+kiss_fastconv_cfg kiss_fastconv_alloc(const kiss_fft_cpx *imp_resp, size_t n_imp_resp, size_t *pnfft)
+{
+    if (!imp_resp || n_imp_resp < 1) return NULL;
+    size_t nfft = pnfft ? *pnfft : 0;
+    if (nfft == 0) { /* next power of two at least twice the impulse response (kiss_fastfir.c:76-84) */
+        size_t i = n_imp_resp - 1;
+        nfft = 2;
+        do {
+            nfft <<= 1;
+        } while (i >>= 1);
+    }
+    if (n_imp_resp > nfft) return NULL;
+    if (pnfft) *pnfft = nfft;
+    kiss_fastconv_cfg st = (kiss_fastconv_cfg)calloc(1, sizeof(*st));
+    kiss_fft_cpx *tmp = (kiss_fft_cpx *)calloc(nfft, sizeof(kiss_fft_cpx));
+    if (!st || !tmp) { free(st); free(tmp); return NULL; }
+    st->magic = KF_MAGIC_FC;
+    st->nfft = (int)nfft;
+    st->ngood = (int)(nfft - n_imp_resp + 1);
+    st->fwd = kiss_fft_alloc((int)nfft, 0, NULL, NULL);
+    st->inv = kiss_fft_alloc((int)nfft, 1, NULL, NULL);
+    st->h_resp = (kiss_fft_cpx *)malloc(sizeof(kiss_fft_cpx) * nfft);
+    int ok = st->fwd && st->inv && st->h_resp;
+    if (ok) {
+        /* zero pad in the middle to left-rotate the impulse response: the scrap samples end up at the END of each
+         * inverse-transformed block (kiss_fastfir.c:139-147) */
+        tmp[0] = imp_resp[n_imp_resp - 1];
+        for (size_t i = 0; i + 1 < n_imp_resp; ++i) tmp[nfft - n_imp_resp + 1 + i] = imp_resp[i];
+        kiss_fft(st->fwd, tmp, st->h_resp); /* on the GPU, through the library itself */
+        const float scale = 1.0f / (float)nfft; /* kiss_fastfir.c:152-162 */
+        for (size_t i = 0; i < nfft; ++i) {
+            st->h_resp[i].r *= scale;
+            st->h_resp[i].i *= scale;
+        }
+        ok = cudaGetDevice(&st->device) == cudaSuccess && cudaMalloc(&st->d_resp, sizeof(kiss_fft_cpx) * nfft) == cudaSuccess &&
+             cudaMemcpy(st->d_resp, st->h_resp, sizeof(kiss_fft_cpx) * nfft, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    free(tmp);
+    if (!ok) {
+        kiss_fastconv_free(st);
+        return NULL;
+    }
+    return st;
+}
+
+void kiss_fastconv_free(kiss_fastconv_cfg st)
+{
+    if (!st) return;
+    if (st->d_resp) cudaFree(st->d_resp);
+    free(st->h_resp);
+    kiss_fft_free(st->fwd);
+    kiss_fft_free(st->inv);
+    free(st);
+}
+
+size_t kiss_fastconv_block_advance(kiss_fastconv_cfg st) { return st ? (size_t)st->ngood : 0; }
+size_t kiss_fastconv_nfft(kiss_fastconv_cfg st) { return st ? (size_t)st->nfft : 0; }
+
+/* kff_nocopy (kiss_fastfir.c:191-206) on device buffers: all complete blocks of the n input samples. */
+int kiss_fastconv_dev(kiss_fastconv_cfg st, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, size_t n, size_t *nprocessed,
+                      void *stream)
+{
+    if (!st || st->magic != KF_MAGIC_FC || !d_in || !d_out) {
+        KF_ERROR("kiss_fastconv_dev: bad argument");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    size_t nblocks = 0;
+    if (n >= (size_t)st->nfft) nblocks = (n - (size_t)st->nfft) / (size_t)st->ngood + 1;
+    if (nprocessed) *nprocessed = nblocks * (size_t)st->ngood;
+    if (nblocks == 0) return 0;
+    const kf_devplan *pf, *pi;
+    KF_CHECK(kf_get_devplan(st->fwd, NULL, &pf));
+    KF_CHECK(kf_get_devplan(st->inv, NULL, &pi));
+    int rc = kfcu_fastconv((kfcu_plan *)&pf->plan, (kfcu_plan *)&pi->plan, d_in, d_out, (long long)nblocks, st->ngood, st->d_resp,
+                           stream);
+    if (rc == KFCU_ETOOBIG) {
+        KF_ERROR("kiss_fastconv_dev: no fused plan for nfft=%d in this build (supported: 256, 512, 1024, 2048, 4096)", st->nfft);
+        return KISS_FFT_CUDA_ETOOBIG;
+    }
+    KF_CHECK(rc);
+    return 0;
+}
+#endif

@@ -87,11 +87,15 @@ struct SrcGlobal {
         if constexpr (UNIT) return A::load(ld_stream(base + i));
         else return A::load(ld_stream(base + (long long)i * stride));
     }
+    template <int IT_, int E_>
+    KF_HD cx<typename A::R> get(int i) const { return load(i); }
 };
 template <class A>
 struct SrcShared {
     const typename A::C* base;   // natural order, unpadded
     KF_HD cx<typename A::R> load(int i) const { return A::load(base[i]); }
+    template <int IT_, int E_>
+    KF_HD cx<typename A::R> get(int i) const { return load(i); }
 };
 // kiss_fftri's split pre pass (kiss_fftr.c:131-153) fused into the first group's loads: element k of the packed
 // complex input T[] of the inverse transform is computed on the fly from the half spectrum F[k], F[nc-k] and the
@@ -118,6 +122,8 @@ struct SrcC2RFused {
         fftri_pre_pair<A>(ks, Fa, Fb, st, Tk, Tnk);
         return lo ? Tk : Tnk;
     }
+    template <int IT_, int E_>
+    KF_HD cx<typename A::R> get(int k) const { return load(k); }
 };
 
 // Destinations of the last group: put<it, e>(k, v) receives output element k, produced from register e of the
@@ -382,6 +388,113 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
         }
         // single exchange buffer: the next tile's first group overwrites what the last group just read
         if constexpr (D.nbuf == 1) env.sync();
+    }
+}
+
+// =========================================================================================================
+// Fused fast convolution (overlap-scrap), the step either side of the transform in the reference's own flagship
+// tool (tools/kiss_fastfir.c:167-181 fastconv1buf, :191-206 kff_nocopy): for every block b of nfft input samples
+// starting at b*ngood:   out[b*ngood .. +ngood) = IFFT( FFT(in block) .* H )[0 .. ngood).
+// Three launches and two HBM round trips of the spectrum in the reference's structure; here ONE kernel: the
+// forward plan's last group keeps the spectrum in registers, multiplies by H, and hands the registers to the first
+// group of the inverse plan (same PlanDesc, conjugate twiddles) -- possible because the plan is palindromic
+// (R(last group) == R(first group)), so thread kp's forward outputs {kp + j*M} are exactly its inverse inputs.
+// HBM traffic per block: nfft reads + ngood writes (+ the L2-resident H and twiddle tables).
+// =========================================================================================================
+template <class A>
+struct FCSide {                       // one direction's tables (see KParams)
+    const typename A::C* tw;
+    const typename A::C* gtw;
+    cx<typename A::R> g0tw[kMaxG0Slots];
+    cx<typename A::R> ctw[kMaxCtw];
+    PlanConsts<A> pc;
+};
+
+template <class A>
+struct FCParams {
+    const typename A::C* in;
+    typename A::C* out;
+    long long nblocks;
+    long long ngood;                  // block advance on both sides, and the number of samples stored per block
+    const typename A::C* h;           // nfft-point frequency response, already scaled by 1/nfft (kiss_fastfir.c:149-162)
+    FCSide<A> fwd, inv;
+};
+
+template <class A, int R_, int GL_, PlanDesc D>
+struct SrcRegs {                      // inverse group 0 input element off + e*Flo == forward output kp + e*M
+    const cx<typename A::R>* regs;
+    template <int IT_, int E_>
+    KF_HD cx<typename A::R> get(int) const { return regs[IT_ * R_ + D.reg_of_j(GL_, E_)]; }
+};
+
+template <class A>
+struct DstGlobalClip {
+    typename A::C* base;
+    int ngood;
+    template <int IT_, int E_>
+    KF_HD void put(int k, const cx<typename A::R>& v) const
+    {
+        if (k < ngood) base[k] = A::store(v);
+    }
+};
+
+template <class A, class PT, class Env>
+KF_HD void fastconv_body(const FCParams<A>& P, Env& env)
+{
+    constexpr PlanDesc D = PT::D;
+    typedef typename A::C C;
+    typedef cx<typename A::R> X;
+    static_assert(!A::kFixed, "fast convolution is float/double only (reference: kiss_fastfir.c:152)");
+    static_assert(D.R(0) == D.R(D.G - 1) && D.iters(0) == D.iters(D.G - 1), "fast convolution needs a palindromic plan");
+    constexpr int GL = D.G - 1, R = D.R(GL), IT = D.iters(GL), M = D.items(GL);
+    constexpr int kPitch = D.pitch();
+    C* const smem = reinterpret_cast<C*>(env.smem());
+    C* const bufA = smem;
+    C* const bufB = smem + D.tpc * kPitch;
+    const int tid = env.tid();
+    const int team = tid / D.team, t = tid % D.team;
+    const TwTab<A> twf{P.fwd.tw, P.fwd.gtw, P.fwd.g0tw, P.fwd.ctw};
+    const TwTab<A> twi{P.inv.tw, P.inv.gtw, P.inv.g0tw, P.inv.ctw};
+    const long long ntiles = (P.nblocks + D.tpc - 1) / D.tpc;
+    // exchanges per tile: 2*(G-1), always even -> the ping-pong parity is the same for every tile
+    for (long long tile = env.bid(); tile < ntiles; tile += env.nblocks()) {
+        const long long b = tile * D.tpc + team;
+        const bool active = b < P.nblocks;
+        C* b0 = bufA + team * kPitch;
+        C* b1 = bufB + team * kPitch;
+        X spec[IT * R];
+        // ---- forward transform, spectrum left in registers ----
+        SrcGlobal<A, true> src{P.in + b * P.ngood, 1};
+        DstRegs<A, R> dstr{spec};
+        if constexpr (D.G == 1) {
+            run_group<A, D, 0, SrcGlobal<A, true>, DstRegs<A, R>>(t, active, src, dstr, b0, b1, twf, P.fwd.pc, 0);
+        } else {
+            run_groups<A, D, 0, SrcGlobal<A, true>, DstRegs<A, R>, Env, D.G>(env, t, active, src, dstr, b0, b1, twf, P.fwd.pc, 0);
+        }
+        // ---- pointwise multiply by the frequency response (fastconv1buf, kiss_fastfir.c:171-176) ----
+        if (active) {
+            static_for<IT>([&](auto ITER) {
+                static_for<R>([&](auto E) {
+                    constexpr int it = decltype(ITER)::value, e = decltype(E)::value;
+                    const int k = t + it * PT::D.team + PT::D.kout(GL, e);
+                    if ((it + 1) * PT::D.team <= M || t + it * PT::D.team < M) {
+                        const X hk = A::load(TwTab<A>::ro_load_c(P.h + k));
+                        spec[it * R + e] = A::cmul(spec[it * R + e], hk);
+                    }
+                });
+            });
+        }
+        // ---- inverse transform from the registers; only the ngood valid samples are stored ----
+        SrcRegs<A, R, GL, D> srcr{spec};
+        DstGlobalClip<A> dstc{P.out + b * P.ngood, (int)P.ngood};
+        // the forward pass used G-1 exchanges: continue the ping-pong where it stopped
+        C* r0 = ((D.G - 1) & 1) ? b1 : b0;
+        C* r1 = ((D.G - 1) & 1) ? b0 : b1;
+        if constexpr (D.G == 1) {
+            run_group<A, D, 0, SrcRegs<A, R, GL, D>, DstGlobalClip<A>>(t, active, srcr, dstc, r0, r1, twi, P.inv.pc, 1);
+        } else {
+            run_groups<A, D, 0, SrcRegs<A, R, GL, D>, DstGlobalClip<A>, Env, D.G>(env, t, active, srcr, dstc, r0, r1, twi, P.inv.pc, 1);
+        }
     }
 }
 

@@ -241,7 +241,7 @@ KF_HD void run_group(int t, bool active, const Src& src, const Dst& dst, const t
             const int rbase = kFirst ? off : phys_rt(kp * (Flo * R) + off, D.logpad);
             static_for<R>([&](auto E) {
                 constexpr int e = decltype(E)::value;
-                if constexpr (kFirst) v[e] = src.load(rbase + e * Flo);
+                if constexpr (kFirst) v[e] = src.template get<it, e>(rbase + e * Flo);
                 else if constexpr (kLinRd) v[e] = A::load(rd[rbase + D.phys(e * Flo)]);
                 else v[e] = A::load(rd[phys_rt(kp * (Flo * R) + off + e * Flo, D.logpad)]);
             });

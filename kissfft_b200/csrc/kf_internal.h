@@ -25,7 +25,8 @@ typedef struct kfcu_plan {
     const void *d_tw;  /* nfft complex twiddles in device memory */
     const void *d_stw; /* nfft/2 split twiddles (real modes) or NULL */
     const void *h_tw;  /* the same twiddles on the host (for the butterfly constants) */
-    void *d_gtw[4];    /* per-group stage-twiddle tables of the fused plan serving each mode (KFCU_C2C..KFCU_C2R);
+    void *d_gtw[5];    /* per-group stage-twiddle tables of the fused plan serving each mode (KFCU_C2C..KFCU_C2R; [4]: the
+                          fast-convolution plan);
                           created lazily by kf_launch.cu, freed by kiss_fft_cleanup together with d_tw */
 } kfcu_plan;
 
@@ -52,6 +53,13 @@ int kfcu_stage(const kfcu_plan *plan, int s, const void *d_in, void *d_out, long
 /* stand-alone split pass of the real transforms: post != 0: T[nc] -> F[nc+1] (kiss_fftr.c:88-116), else F -> T */
 int kfcu_realpass(const kfcu_plan *plan, int post, const void *d_in, void *d_out, long long batch, long long in_dist,
                   long long out_dist, void *stream);
+
+/* fused overlap-scrap fast convolution (float / double builds): block b reads nfft samples at d_in + b*ngood, writes
+ * ngood samples at d_out + b*ngood; d_h = nfft-point frequency response already scaled by 1/nfft.  KFCU_ETOOBIG when
+ * no fused plan exists for the length (the caller then composes it from three calls). */
+int kfcu_has_fastconv(int nfft);
+int kfcu_fastconv(kfcu_plan *fwd, kfcu_plan *inv, const void *d_in, void *d_out, long long nblocks, long long ngood,
+                  const void *d_h, void *stream);
 
 /* out[c][r] = in[r][c] for a rows x cols array of complex elements (kiss_fftndr's bin-major <-> row-major
  * scatter loops, kiss_fftndr.c:101-102, 107-108) */

@@ -74,6 +74,14 @@ __global__ void __launch_bounds__(256) kf_generic_kernel(const __grid_constant__
     generic_body<A>(G, env);
 }
 
+template <class A, class PT>
+__global__ void __launch_bounds__(PT::D.threads(), PT::D.minblocks) kf_fastconv_kernel(const __grid_constant__ FCParams<A> P)
+{
+    extern __shared__ __align__(16) unsigned char kf_smem_raw[];
+    DeviceEnv env{kf_smem_raw};
+    fastconv_body<A, PT>(P, env);
+}
+
 template <class A>
 __global__ void __launch_bounds__(256) kf_stage_kernel(const __grid_constant__ StageParams<A> S)
 {

@@ -255,6 +255,98 @@ extern "C" int kfcu_exec_planes_peers(kfcu_plan* plan, const void* d_in, void* c
     return launch_generic(kC2CCol, plan, P, (cudaStream_t)stream);
 }
 
+// ---- fused fast convolution (float / double) ------------------------------------------------------------------
+#if !defined(FIXED_POINT)
+typedef int (*fc_launch_fn)(kfcu_plan*, kfcu_plan*, const void*, void*, long long, long long, const void*, cudaStream_t);
+
+template <class PT>
+static int ensure_gtw(kfcu_plan* pl, int slot)
+{
+    constexpr PlanDesc D = PT::D;
+    if (D.gtw_total() > 0 && !pl->d_gtw[slot]) {
+        std::lock_guard<std::mutex> lk(g_gtw_mutex);
+        if (!pl->d_gtw[slot]) {
+            std::vector<CT> tab = build_gtw<AT, PT>((const CT*)pl->h_tw);
+            void* d = nullptr;
+            cudaError_t e = cudaMalloc(&d, tab.size() * sizeof(CT));
+            if (e != cudaSuccess) return (int)e;
+            e = cudaMemcpy(d, tab.data(), tab.size() * sizeof(CT), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { cudaFree(d); return (int)e; }
+            pl->d_gtw[slot] = d;
+        }
+    }
+    return 0;
+}
+
+template <class PT>
+static int launch_fastconv(kfcu_plan* fwd, kfcu_plan* inv, const void* d_in, void* d_out, long long nblocks, long long ngood,
+                           const void* d_h, cudaStream_t st)
+{
+    constexpr PlanDesc D = PT::D;
+    auto kern = kf_fastconv_kernel<AT, PT>;
+    constexpr size_t smem = (D.G >= 2) ? (size_t)2 * D.tpc * D.pitch() * sizeof(CT) : 0;
+    static_assert(smem <= 232448, "fast-convolution plan exceeds shared memory");
+    // the fast-convolution plan has its own slot (4) in the per-plan table cache
+    int rc = ensure_gtw<PT>(fwd, 4);
+    if (!rc) rc = ensure_gtw<PT>(inv, 4);
+    if (rc) return rc;
+    FCParams<AT> P;
+    P.in = (const CT*)d_in;
+    P.out = (CT*)d_out;
+    P.nblocks = nblocks;
+    P.ngood = ngood;
+    P.h = (const CT*)d_h;
+    fill_fc_side<AT, PT>(P.fwd, (const CT*)fwd->h_tw, (const CT*)fwd->d_tw, (const CT*)fwd->d_gtw[4]);
+    fill_fc_side<AT, PT>(P.inv, (const CT*)inv->h_tw, (const CT*)inv->d_tw, (const CT*)inv->d_gtw[4]);
+    static int blocks_per_sm[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (blocks_per_sm[dev] == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, D.threads(), smem);
+        if (e != cudaSuccess) return (int)e;
+        if (nb < 1) return (int)cudaErrorLaunchOutOfResources;
+        blocks_per_sm[dev] = nb;
+    }
+    const long long ntiles = (nblocks + D.tpc - 1) / D.tpc;
+    long long grid = (long long)device_info().sms * blocks_per_sm[dev];
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) return 0;
+    kern<<<(unsigned)grid, D.threads(), smem, st>>>(P);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+struct FCEntry { int N; fc_launch_fn fn; };
+#define KF_FC_ROW(tag) { tag::D.N, launch_fastconv<tag> },
+static const FCEntry kFCTable[] = { KF_FASTCONV_LIST(KF_FC_ROW) };
+#endif
+
+extern "C" int kfcu_has_fastconv(int nfft)
+{
+#if !defined(FIXED_POINT)
+    for (const FCEntry& e : kFCTable)
+        if (e.N == nfft) return 1;
+#endif
+    (void)nfft;
+    return 0;
+}
+
+extern "C" int kfcu_fastconv(kfcu_plan* fwd, kfcu_plan* inv, const void* d_in, void* d_out, long long nblocks, long long ngood,
+                             const void* d_h, void* stream)
+{
+#if !defined(FIXED_POINT)
+    if (!fwd || !inv || !d_in || !d_out || !d_h || fwd->nfft != inv->nfft || ngood < 1 || ngood > fwd->nfft) return KFCU_EINVAL;
+    if (nblocks <= 0) return 0;
+    for (const FCEntry& e : kFCTable)
+        if (e.N == fwd->nfft) return e.fn(fwd, inv, d_in, d_out, nblocks, ngood, d_h, (cudaStream_t)stream);
+#endif
+    return KFCU_ETOOBIG;
+}
+
 // ---- multi-pass path (lengths beyond the shared-memory kernels) -------------------------------------------------
 extern "C" int kfcu_stage(const kfcu_plan* plan, int s, const void* d_in, void* d_out, long long batch, long long in_dist,
                           long long out_dist, long long in_stride, int first, int last, void* stream)

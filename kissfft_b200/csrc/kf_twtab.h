@@ -52,6 +52,24 @@ void fill_g0tw(KParams<A>& P, const typename A::C* h_tw)
                             A::load(h_tw[(long long)q * D.F(s) * D.kabove(g, s, D.upper_base(g, s, up))]);
 }
 
+// one direction of the fused fast convolution: tables of plan PT built from that direction's twiddles
+template <class A, class PT>
+void fill_fc_side(FCSide<A>& S, const typename A::C* h_tw, const typename A::C* d_tw, const typename A::C* d_gtw)
+{
+    constexpr PlanDesc D = PT::D;
+    KParams<A> P{};
+    fill_g0tw<A, PT>(P, h_tw);
+    for (int i = 0; i < kMaxG0Slots; ++i) S.g0tw[i] = P.g0tw[i];
+    for (int i = 0; i < kMaxCtw; ++i) S.ctw[i] = P.ctw[i];
+    S.tw = d_tw;
+    S.gtw = d_gtw;
+    const int N = D.N;
+    typename A::C z{};
+    S.pc.epi3 = A::load((N % 3 == 0) ? h_tw[N / 3] : z);
+    S.pc.ya = A::load((N % 5 == 0) ? h_tw[N / 5] : z);
+    S.pc.yb = A::load((N % 5 == 0) ? h_tw[2 * (N / 5)] : z);
+}
+
 // How many leading rows of a call may go through the fused kernel of plan PT (the rest, if any, must take the
 // run-time kernel).  The bulk-async input ring needs contiguous rows, a 16-byte aligned base and tiles whose byte
 // size is a multiple of 16 (cp.async.bulk rules); a ragged last tile that breaks the size rule is peeled off.

@@ -215,3 +215,32 @@ extern "C" int emul_realpass(int nc, int post, const void* in, void* out, long l
     run_cta_grid(nthreads, nblocks, 16, [&](EmuEnv& env) { realpass_body<AT>(S, env); });
     return 0;
 }
+
+// ---- fused fast convolution (float / double) -------------------------------------------------------------------------
+#if !defined(FIXED_POINT)
+template <class PT>
+static int run_fastconv(const void* in, void* out, long long nblocks, long long ngood, const void* h, const void* tw_f,
+                        const void* tw_i, long long grid)
+{
+    constexpr PlanDesc D = PT::D;
+    std::vector<CT> gf = build_gtw<AT, PT>((const CT*)tw_f), gi = build_gtw<AT, PT>((const CT*)tw_i);
+    FCParams<AT> P;
+    P.in = (const CT*)in; P.out = (CT*)out; P.nblocks = nblocks; P.ngood = ngood; P.h = (const CT*)h;
+    fill_fc_side<AT, PT>(P.fwd, (const CT*)tw_f, (const CT*)tw_f, gf.data());
+    fill_fc_side<AT, PT>(P.inv, (const CT*)tw_i, (const CT*)tw_i, gi.data());
+    const size_t smem = (D.G >= 2) ? (size_t)2 * D.tpc * D.pitch() * sizeof(CT) : 16;
+    run_cta_grid(D.threads(), grid, smem, [&](EmuEnv& env) { fastconv_body<AT, PT>(P, env); });
+    return 0;
+}
+typedef int (*fc_fn)(const void*, void*, long long, long long, const void*, const void*, const void*, long long);
+struct FCEntry { int N; fc_fn fn; };
+#define KF_FC_ROW(tag) { tag::D.N, run_fastconv<tag> },
+static const FCEntry kFCTable[] = { KF_FASTCONV_LIST(KF_FC_ROW) };
+extern "C" int emul_fastconv(int nfft, const void* in, void* out, long long nblocks, long long ngood, const void* h,
+                             const void* tw_f, const void* tw_i, long long grid)
+{
+    for (const FCEntry& e : kFCTable)
+        if (e.N == nfft) return e.fn(in, out, nblocks, ngood, h, tw_f, tw_i, grid);
+    return -1;
+}
+#endif

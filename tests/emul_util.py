@@ -50,6 +50,8 @@ class Emulator:
         self.lib.emul_generic.argtypes = [ci, ci, ci, vp, ci, vp, vp, ll, ll, ll, ll, vp, vp, ci, ci, ll]
         self.lib.emul_stage.argtypes = [ci, ci, ci, ci, ci, vp, vp, ll, ll, ll, ll, ci, ci, vp, ci, ll]
         self.lib.emul_realpass.argtypes = [ci, ci, vp, vp, ll, ll, ll, vp, ci, ll]
+        if hasattr(self.lib, "emul_fastconv"):
+            self.lib.emul_fastconv.argtypes = [ci, vp, vp, ll, ll, vp, vp, vp, ll]
 
     def plans(self):
         return [(self.lib.emul_plan_nfft(i), [m for m in range(4) if self.lib.emul_plan_has_mode(i, m)])
@@ -101,3 +103,7 @@ class Emulator:
 
     def realpass(self, nc, post, inp, out, howmany, in_dist, out_dist, stw):
         assert self.lib.emul_realpass(nc, int(post), _p(inp), _p(out), howmany, in_dist, out_dist, _p(stw), 64, 3) == 0
+
+    def fastconv(self, nfft, inp, out, nblocks, ngood, h, tw_f, tw_i, grid=2):
+        rc = self.lib.emul_fastconv(nfft, _p(inp), _p(out), nblocks, ngood, _p(h), _p(tw_f), _p(tw_i), grid)
+        assert rc == 0, "no fast-convolution plan for nfft=%d" % nfft

@@ -171,3 +171,30 @@ def test_multipass_real(env):
         y = np.zeros((howmany, n), xr.dtype)
         em.multipass(nc, 1, o.factor(nc), T2, y, howmany, nc, nc, 1, o.twiddles(nc, 1))
         check(tname, y, o.fftri(spec), n)
+
+
+@pytest.mark.parametrize("tname", ["float", "double"])
+@pytest.mark.parametrize("nfft,nimp", [(256, 33), (512, 100), (1024, 129), (2048, 513), (4096, 1000)])
+def test_fused_fast_convolution_emulated(tname, nfft, nimp):
+    """fastconv_body (FFT -> .*H -> IFFT in one kernel, spectrum handed over in registers) vs the oracle pipeline"""
+    o, em = Oracle(tname), Emulator(tname)
+    rng = np.random.default_rng(3)
+    imp = rng.uniform(-1, 1, size=(nimp, 2)).astype(o.dtype) / nimp
+    ngood = nfft - nimp + 1
+    nblocks = 9
+    x = random_input(tname, ((nblocks - 1) * ngood + nfft,), 17)
+    rot = np.zeros((nfft, 2), o.dtype)
+    rot[0] = imp[nimp - 1]
+    rot[nfft - nimp + 1:] = imp[: nimp - 1]
+    H = (o.fft(rot) * np.float32(1.0 / nfft)).astype(o.dtype)
+    out = np.zeros_like(x)
+    em.fastconv(nfft, x, out, nblocks, ngood, H, o.twiddles(nfft, 0), o.twiddles(nfft, 1))
+    blocks = np.stack([x[b * ngood: b * ngood + nfft] for b in range(nblocks)])
+    X = o.fft(blocks).astype(np.float64)
+    Hc = H.astype(np.float64)
+    Y = np.empty_like(X)
+    Y[..., 0] = X[..., 0] * Hc[:, 0] - X[..., 1] * Hc[:, 1]
+    Y[..., 1] = X[..., 0] * Hc[:, 1] + X[..., 1] * Hc[:, 0]
+    y = o.fft(Y.astype(o.dtype), True)[:, :ngood].reshape(-1, 2)
+    assert rel_rms(out[: nblocks * ngood], y) <= 3 * TOL[tname] * np.log2(nfft)
+    assert not out[nblocks * ngood:].any()

@@ -487,3 +487,43 @@ def test_slab_single_rank_and_planes_pass():
     want = np.stack([o.fft(np.ascontiguousarray(y[p].transpose(1, 0, 2))) for p in range(P)])
     check(tname, host(d_o), want, d1, "planes pass")
     lib.free(cfg)
+
+
+@pytest.mark.parametrize("tname", ["float", "double"])
+@pytest.mark.parametrize("nfft,nimp", [(256, 33), (512, 100), (1024, 129), (2048, 513), (4096, 1000), (0, 200)])
+def test_fused_fast_convolution(tname, nfft, nimp):
+    """overlap-scrap FIR filtering (reference tools/kiss_fastfir.c) fused into one kernel vs the same pipeline assembled
+    from oracle transforms: H = FFT(rotated impulse response)/nfft, per block IFFT(FFT(x) .* H), first ngood samples kept"""
+    import kissfft_b200
+    lib, o = kissfft_b200.get(tname), Oracle(tname)
+    rng = np.random.default_rng(3)
+    imp = rng.uniform(-1, 1, size=(nimp, 2)).astype(o.dtype) / nimp
+    cfg, n, ngood = lib.fastconv_alloc(imp, nfft)
+    assert ngood == n - nimp + 1 and (nfft == 0 or n == nfft)
+    nblocks = 37
+    nsamp = (nblocks - 1) * ngood + n + 5                      # 5 trailing samples that do not complete a block
+    x = random_input(tname, (nsamp,), 17)
+    d_in, d_out = dev(x), dev(np.zeros_like(x))
+    done = lib.fastconv_dev(cfg, d_in, d_out, nsamp)
+    torch.cuda.synchronize()
+    assert done == nblocks * ngood
+    # oracle pipeline
+    rot = np.zeros((n, 2), o.dtype)
+    rot[0] = imp[nimp - 1]
+    rot[n - nimp + 1:] = imp[: nimp - 1]
+    H = o.fft(rot) * np.float32(1.0 / n)
+    blocks = np.stack([x[b * ngood: b * ngood + n] for b in range(nblocks)])
+    X = o.fft(blocks).astype(np.float64)
+    Hc = H.astype(np.float64)
+    Y = np.empty_like(X)
+    Y[..., 0] = X[..., 0] * Hc[:, 0] - X[..., 1] * Hc[:, 1]
+    Y[..., 1] = X[..., 0] * Hc[:, 1] + X[..., 1] * Hc[:, 0]
+    y = o.fft(Y.astype(o.dtype), True)[:, :ngood].reshape(-1, 2)
+    got = host(d_out)
+    assert rel_rms(got[: done], y) <= 3 * TOL[tname] * np.log2(n)
+    assert not got[done:].any(), "samples beyond the processed range must stay untouched"
+    # and against the textbook answer: linear convolution with the impulse response
+    xc, hc = x[:, 0].astype(np.float64) + 1j * x[:, 1], imp[:, 0].astype(np.float64) + 1j * imp[:, 1]
+    full = np.convolve(xc, hc)[nimp - 1: nimp - 1 + done]
+    assert rel_rms(got[:done], np.stack([full.real, full.imag], -1)) <= 20 * TOL[tname] * np.log2(n)
+    lib.fastconv_free(cfg)
