@@ -23,8 +23,13 @@
 #ifndef KISS_FFT_H
 #define KISS_FFT_H
 
+/* the same four standard headers the reference's kiss_fft.h pulls in (kiss_fft.h:12-15): programs written against it
+ * rely on getting printf / memset / cos / M_PI through this header */
+#include <math.h>
 #include <stddef.h>
+#include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #ifdef KISS_FFT_SHARED
 # define KISS_FFT_API __attribute__((visibility("default")))

@@ -44,6 +44,19 @@ def build_reference():
     return True
 
 
+def build_dropin():
+    """Compile the reference's own unmodified test/tool programs against THIS repo's headers and libraries
+    (oracle/_ref/dropin/*; needs /root/reference and the built kissfft_b200/lib).  Returns True if built."""
+    if not os.path.isdir(REF_SRC):
+        return False
+    _make("dropin")
+    return True
+
+
+def dropin_path(name, tname):
+    return os.path.join(HERE, "_ref", "dropin", "%s-%s" % (name, tname))
+
+
 def oracle_lib_path(tname):
     return os.path.join(HERE, "_lib", "liboracle-%s.so" % tname)
 
