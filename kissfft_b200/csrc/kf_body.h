@@ -165,6 +165,80 @@ KF_HD void run_groups(Env& env, int t, bool active, const Src& src, const Dst& d
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// kiss_fftr, last radix stage + split post pass (kiss_fftr.c:88-116) on PAIRS of work items.
+// The last group is the single outermost stage (radix p = 2 or 4, m = nc/p butterflies, twiddle stride 1).  Butterfly
+// k' produces T[k' + r*m]; the bin pair of T[k' + r*m] is T[nc - k' - r*m] = T[(m-k') + (p-1-r)*m], an output of
+// butterfly m-k'.  A thread therefore runs butterflies u and m-u together and finds every pair (k, nc-k) of the post
+// pass complete in its registers; butterflies 0 and m/2 pair with themselves and are done by thread 0.
+// Same operands and roundings as the reference's loop over k = 1..nc/2, so fixed point stays bit-exact.
+// ---------------------------------------------------------------------------------------------------------
+template <class A, PlanDesc D>
+KF_HD void r2c_last_item(int kp, const typename A::C* rd, const TwTab<A>& tw, typename A::R sg, cx<typename A::R>* v)
+{
+    typedef cx<typename A::R> X;
+    constexpr int gl = D.G - 1, p = D.p[0];
+    static_for<p>([&](auto Q) {
+        constexpr int q = decltype(Q)::value;
+        v[q] = A::load(rd[phys_rt(kp * p + q, D.logpad)]);
+    });
+    auto T = [&](int q) { return stage_tw<A, D, gl>(tw, q - 1, kp); };
+    if constexpr (p == 2) bfly2<A, false>(v, T(1));
+    else bfly4<A, false>(v, T(1), T(2), T(3), sg);
+}
+
+template <class A>
+KF_HD void r2c_emit_pair(int ks, int nc, const cx<typename A::R>& Tk, const cx<typename A::R>& Tnk, const typename A::C* stw,
+                         typename A::C* out)
+{
+    typedef cx<typename A::R> X;
+    const X st = A::load(TwTab<A>::ro_load_c(stw + (ks - 1)));
+    X ok, onk;
+    fftr_post_pair<A>(ks, nc, Tk, Tnk, st, ok, onk);
+    if (ks != nc - ks) out[ks] = A::store(ok);     // ks == nc/2: the reference's second assignment wins
+    out[nc - ks] = A::store(onk);
+}
+
+template <class A, PlanDesc D>
+KF_HD void run_r2c_last_paired(int t, bool active, const typename A::C* rd, const TwTab<A>& tw, const typename A::C* stw,
+                               typename A::C* out, int inverse)
+{
+    typedef cx<typename A::R> X;
+    constexpr int p = D.p[0], m = D.N / p, nc = D.N, half = m / 2;
+    constexpr int kPairs = half - 1;                                    // u = 1 .. half-1
+    constexpr int kIt = (kPairs + D.team - 1) / D.team;
+    const typename A::R sg = A::sign_of(inverse);
+    if (!active) return;
+    static_for<(kIt > 0 ? kIt : 0)>([&](auto ITER) {
+        const int u = 1 + t + decltype(ITER)::value * D.team;
+        if (u < half) {
+            X a[p], b[p];
+            r2c_last_item<A, D>(u, rd, tw, sg, a);
+            r2c_last_item<A, D>(m - u, rd, tw, sg, b);
+            static_for<p / 2>([&](auto RR) {
+                constexpr int r = decltype(RR)::value;
+                r2c_emit_pair<A>(u + r * m, nc, a[r], b[p - 1 - r], stw, out);
+                r2c_emit_pair<A>((m - u) + r * m, nc, b[r], a[p - 1 - r], stw, out);
+            });
+        }
+    });
+    if (t == 0) {
+        X a[p], b[p];
+        r2c_last_item<A, D>(0, rd, tw, sg, a);          // T[r*m]
+        r2c_last_item<A, D>(half, rd, tw, sg, b);       // T[m/2 + r*m]
+        X ok, onk;
+        fftr_post_pair<A>(0, nc, a[0], a[0], a[0], ok, onk);            // DC and Nyquist bins
+        out[0] = A::store(ok);
+        out[nc] = A::store(onk);
+        static_for<p / 2>([&](auto RR) {
+            constexpr int r = decltype(RR)::value;
+            if constexpr (r >= 1) r2c_emit_pair<A>(r * m, nc, a[r], a[p - r], stw, out);
+            r2c_emit_pair<A>(half + r * m, nc, b[r], b[p - 1 - r], stw, out);
+        });
+        r2c_emit_pair<A>(nc / 2, nc, a[p / 2], a[p / 2], stw, out);       // k == nc/2 pairs with itself
+    }
+}
+
 // Shared-memory layout of one CTA of the fused kernel.
 //   [exchange buffer A][exchange buffer B]   tpc * pitch elements each (skewed autosort arrays between groups)
 //   [input ring: nstage stages]              each stage = one tile of tpc contiguous input rows, natural order,
@@ -180,6 +254,9 @@ struct FusedLayout {
     // kiss_fftr post pass by warp shuffles instead of a T[] round trip through shared memory: needs whole warps per
     // team and the last group's work items to divide evenly (PlanDesc::shfl_post asks for it)
     static constexpr bool kShflPost = MODE == kR2C && D.shfl_post && D.team % 32 == 0 && D.items(D.G - 1) % D.team == 0;
+    // kiss_fftr with the last radix-2/4 stage run on work-item pairs (k', m-k'): post pass in registers, no T[] buffer
+    static constexpr bool kPairedLast = MODE == kR2C && D.paired_last && D.G >= 2 && D.glen[D.G - 1] == 1 &&
+                                        (D.p[0] == 2 || D.p[0] == 4) && (D.N / D.p[0]) % 2 == 0;
     static constexpr size_t kExchBytes = (D.G >= 2 || (MODE == kR2C && !kShflPost)) ? (size_t)D.nbuf * D.tpc * D.pitch() * sizeof(typename A::C) : 0;
     static constexpr size_t kRingOff = (kExchBytes + 127) / 128 * 128;
     static constexpr size_t kStageBytes = ((size_t)D.tpc * kRowIn * sizeof(typename A::C) + 127) / 128 * 128;
@@ -262,7 +339,22 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             }
         };
 
-        if constexpr (MODE == kR2C && LY::kShflPost) {
+        if constexpr (MODE == kR2C && LY::kPairedLast) {
+            // ---- kiss_fftr: all groups but the last, then the last stage + split pass on work-item pairs ----
+            constexpr int gl = PT::D.G - 1;
+            DstGlobal<A> unused{nullptr};
+            auto run_all = [&](auto src) {
+                typedef decltype(src) S;
+                run_group<A, PT::D, 0, S, DstGlobal<A>>(t, active, src, unused, b0, b1, tw, P.pc, P.inverse);
+                env.sync();
+                recycle();
+                run_groups<A, PT::D, 1, S, DstGlobal<A>, Env, gl>(env, t, active, src, unused, b1, b0, tw, P.pc, P.inverse);
+            };
+            if constexpr (kRing) run_all(SrcShared<A>{srow});
+            else run_all(SrcGlobal<A, true>{P.in + b * P.in_dist, 1});
+            run_r2c_last_paired<A, PT::D>(t, active, (gl & 1) ? b1 : b0, tw, P.stw, P.out + b * P.out_dist, P.inverse);
+            par ^= (D.G - 1) & 1;
+        } else if constexpr (MODE == kR2C && LY::kShflPost) {
             // ---- kiss_fftr with the split post pass (kiss_fftr.c:88-116) done in registers ---------------------------
             // The last group keeps its outputs T[k] in registers.  Output k needs T[k] and T[nc-k]; with M = N/R work
             // items, T[kp + j*M]'s partner is register R-1-j of work item M-kp.  The last group's threads are
