@@ -157,7 +157,10 @@ class ClockSampler:
 
 
 # ---- CPU reference arm -------------------------------------------------------------------------------------
-def cpu_reference(w, reps=3, budget_rows=None):
+_CPU_INPUT = {}
+
+
+def cpu_reference(w, reps=5, budget_rows=None):
     """times the reference's own CPU implementation (oracle/_ref when compiled here, else the oracle port) on a
     bounded sample of the workload with all host threads (batch-parallel harness; cfgs are read-only, reference
     README.md:217).  Returns (gflops, info dict)."""
@@ -171,10 +174,14 @@ def cpu_reference(w, reps=3, budget_rows=None):
     s = esz(tname)
     if w["kind"] in ("real", "c2c"):
         n = w["nfft"]
-        rows = budget_rows or min(w["batch"], max(256, 512 * threads))
+        # the whole batch when one operand fits 1 GiB of host memory (true for every bench workload), else a prefix of it
+        rows = budget_rows or (min(w["batch"], max(256, (1 << 30) // (n * 2 * s))) if have_ref else min(w["batch"], 2048))
         sub = dict(w, batch=rows)
+        key = (tname, rows, n, w["kind"])
         if w["kind"] == "c2c":
-            x = loader.random_input(tname, (rows, n), 1)
+            x = _CPU_INPUT.get(key)
+            if x is None:
+                x = _CPU_INPUT.setdefault(key, loader.random_input(tname, (rows, n), 1))
             out = np.empty_like(x)
             if have_ref:
                 t = drv.run(loader.reference_lib_path(tname), loader.K_FFT, [n], 0, x, out, rows, n * 2 * s, n * 2 * s, threads, reps)
@@ -184,7 +191,9 @@ def cpu_reference(w, reps=3, budget_rows=None):
                 o.fft(x)
                 t = time.perf_counter() - t0
         else:
-            x = loader.random_input(tname, (rows, n), 1, complex_=False)
+            x = _CPU_INPUT.get(key)
+            if x is None:
+                x = _CPU_INPUT.setdefault(key, loader.random_input(tname, (rows, n), 1, complex_=False))
             X = np.empty((rows, n // 2 + 1, 2), dtype)
             y = np.empty_like(x)
             if have_ref:
@@ -414,9 +423,9 @@ def run_reference(args, w, rank, world):
     for _ in range(args.steps):
         gf, info = cpu_reference(w, reps=1)
         vals.append(gf)
-    dt = (time.perf_counter() - t0) / args.steps
     value = float(np.median(vals))
     info = dict(info, value=value)
+    dt = flops_per_step(w) / (value * 1e9)          # one full step of the workload at the measured rate
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": DTYPE_NAME[w["tname"]], "data": "synthetic",
