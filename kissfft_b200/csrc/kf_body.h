@@ -166,27 +166,13 @@ KF_HD void run_groups(Env& env, int t, bool active, const Src& src, const Dst& d
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// kiss_fftr, last radix stage + split post pass (kiss_fftr.c:88-116) on PAIRS of work items.
-// The last group is the single outermost stage (radix p = 2 or 4, m = nc/p butterflies, twiddle stride 1).  Butterfly
-// k' produces T[k' + r*m]; the bin pair of T[k' + r*m] is T[nc - k' - r*m] = T[(m-k') + (p-1-r)*m], an output of
-// butterfly m-k'.  A thread therefore runs butterflies u and m-u together and finds every pair (k, nc-k) of the post
-// pass complete in its registers; butterflies 0 and m/2 pair with themselves and are done by thread 0.
+// kiss_fftr: last group + split post pass (kiss_fftr.c:88-116) on PAIRS of work items.
+// The last group has m = nc/R work items; item u produces T[u + j*m], j < R.  The bin pair of T[u + j*m] is
+// T[nc - u - j*m] = T[(m-u) + (R-1-j)*m], an output of item m-u.  A thread therefore runs items u and m-u together
+// and finds every pair (k, nc-k) of the post pass complete in its registers: no T[] round trip through shared
+// memory.  Items 0 and m/2 pair with themselves and are taken together by the thread whose u is 0.
 // Same operands and roundings as the reference's loop over k = 1..nc/2, so fixed point stays bit-exact.
 // ---------------------------------------------------------------------------------------------------------
-template <class A, PlanDesc D>
-KF_HD void r2c_last_item(int kp, const typename A::C* rd, const TwTab<A>& tw, typename A::R sg, cx<typename A::R>* v)
-{
-    typedef cx<typename A::R> X;
-    constexpr int gl = D.G - 1, p = D.p[0];
-    static_for<p>([&](auto Q) {
-        constexpr int q = decltype(Q)::value;
-        v[q] = A::load(rd[phys_rt(kp * p + q, D.logpad)]);
-    });
-    auto T = [&](int q) { return stage_tw<A, D, gl>(tw, q - 1, kp); };
-    if constexpr (p == 2) bfly2<A, false>(v, T(1));
-    else bfly4<A, false>(v, T(1), T(2), T(3), sg);
-}
-
 template <class A>
 KF_HD void r2c_emit_pair(int ks, int nc, const cx<typename A::R>& Tk, const cx<typename A::R>& Tnk, const typename A::C* stw,
                          typename A::C* out)
@@ -199,44 +185,108 @@ KF_HD void r2c_emit_pair(int ks, int nc, const cx<typename A::R>& Tk, const cx<t
     out[nc - ks] = A::store(onk);
 }
 
-template <class A, PlanDesc D>
-KF_HD void run_r2c_last_paired(int t, bool active, const typename A::C* rd, const TwTab<A>& tw, const typename A::C* stw,
-                               typename A::C* out, int inverse)
+// `mid()` runs between the loads of the exchange buffer and the butterflies (a no-op, or the barrier + refill of the
+// in-place input stage; it contains a CTA barrier only when every thread reaches it exactly once, kIt == 1).
+template <class A, PlanDesc D, class Mid>
+KF_HD void run_r2c_last_paired(int t, bool active, const typename A::C* rd, const TwTab<A>& tw, const PlanConsts<A>& pc,
+                               const typename A::C* stw, typename A::C* out, int inverse, const Mid& mid)
 {
     typedef cx<typename A::R> X;
-    constexpr int p = D.p[0], m = D.N / p, nc = D.N, half = m / 2;
-    constexpr int kPairs = half - 1;                                    // u = 1 .. half-1
-    constexpr int kIt = (kPairs + D.team - 1) / D.team;
+    constexpr int gl = D.G - 1, R = D.R(gl), m = D.items(gl), nc = D.N, half = m / 2;
+    constexpr int kIt = (half + D.team - 1) / D.team;                   // u = 0 .. half-1
     const typename A::R sg = A::sign_of(inverse);
-    if (!active) return;
-    static_for<(kIt > 0 ? kIt : 0)>([&](auto ITER) {
-        const int u = 1 + t + decltype(ITER)::value * D.team;
-        if (u < half) {
-            X a[p], b[p];
-            r2c_last_item<A, D>(u, rd, tw, sg, a);
-            r2c_last_item<A, D>(m - u, rd, tw, sg, b);
-            static_for<p / 2>([&](auto RR) {
-                constexpr int r = decltype(RR)::value;
-                r2c_emit_pair<A>(u + r * m, nc, a[r], b[p - 1 - r], stw, out);
-                r2c_emit_pair<A>((m - u) + r * m, nc, b[r], a[p - 1 - r], stw, out);
-            });
+    static_for<kIt>([&](auto ITER) {
+        const int u = t + decltype(ITER)::value * D.team;
+        const bool on = active && u < half;
+        const int wa = on ? u : 0, wb = (on && u != 0) ? m - u : half;   // items (u, m-u); (0, m/2) for u == 0
+        X a[R], b[R];
+        if (on) {
+            item_load<A, D, gl>(wa, rd, a);
+            item_load<A, D, gl>(wb, rd, b);
+        }
+        mid();
+        if (on) {
+            item_stages<A, D, gl>(wa, a, tw, pc, sg);
+            item_stages<A, D, gl>(wb, b, tw, pc, sg);
+            if (u == 0) {
+                // a = T[j*m], b = T[m/2 + j*m]: both items pair with themselves
+                X ok, onk;
+                constexpr int e0 = D.reg_of_j(gl, 0), eh = D.reg_of_j(gl, R / 2);
+                fftr_post_pair<A>(0, nc, a[e0], a[e0], a[e0], ok, onk);        // DC and Nyquist bins
+                out[0] = A::store(ok);
+                out[nc] = A::store(onk);
+                static_for<R / 2>([&](auto JJ) {
+                    constexpr int j = decltype(JJ)::value;
+                    if constexpr (j >= 1) r2c_emit_pair<A>(j * m, nc, a[D.reg_of_j(gl, j)], a[D.reg_of_j(gl, R - j)], stw, out);
+                    r2c_emit_pair<A>(half + j * m, nc, b[D.reg_of_j(gl, j)], b[D.reg_of_j(gl, R - 1 - j)], stw, out);
+                });
+                r2c_emit_pair<A>(nc / 2, nc, a[eh], a[eh], stw, out);           // k == nc/2 pairs with itself
+            } else {
+                static_for<R / 2>([&](auto JJ) {
+                    constexpr int j = decltype(JJ)::value;
+                    constexpr int ej = D.reg_of_j(gl, j), en = D.reg_of_j(gl, R - 1 - j);
+                    r2c_emit_pair<A>(u + j * m, nc, a[ej], b[en], stw, out);
+                    r2c_emit_pair<A>((m - u) + j * m, nc, b[ej], a[en], stw, out);
+                });
+            }
         }
     });
-    if (t == 0) {
-        X a[p], b[p];
-        r2c_last_item<A, D>(0, rd, tw, sg, a);          // T[r*m]
-        r2c_last_item<A, D>(half, rd, tw, sg, b);       // T[m/2 + r*m]
-        X ok, onk;
-        fftr_post_pair<A>(0, nc, a[0], a[0], a[0], ok, onk);            // DC and Nyquist bins
-        out[0] = A::store(ok);
-        out[nc] = A::store(onk);
-        static_for<p / 2>([&](auto RR) {
-            constexpr int r = decltype(RR)::value;
-            if constexpr (r >= 1) r2c_emit_pair<A>(r * m, nc, a[r], a[p - r], stw, out);
-            r2c_emit_pair<A>(half + r * m, nc, b[r], b[p - 1 - r], stw, out);
-        });
-        r2c_emit_pair<A>(nc / 2, nc, a[p / 2], a[p / 2], stw, out);       // k == nc/2 pairs with itself
-    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kiss_fftri: split pre pass (kiss_fftr.c:131-153) + first group on PAIRS of work items -- the mirror image.
+// The first group has W = nc/R work items; item u consumes T[u + e*W], e < R, and T[nc - u - e*W] is input R-1-e of
+// item W-u.  The thread that runs items u and W-u reads every F[k], F[nc-k] and split twiddle exactly once and
+// produces both T values of the pair as the reference does (SrcC2RFused evaluates each pair twice).
+// ---------------------------------------------------------------------------------------------------------
+template <class A, class F>
+KF_HD void c2r_make_pair(int ks, int nc, const F& f, const typename A::C* stw, cx<typename A::R>& Tk, cx<typename A::R>& Tnk)
+{
+    typedef cx<typename A::R> X;
+    const X Fa = f(ks), Fb = f(nc - ks);
+    const X st = A::load(TwTab<A>::ro_load_c(stw + (ks - 1)));
+    fftri_pre_pair<A>(ks, Fa, Fb, st, Tk, Tnk);
+}
+
+template <class A, PlanDesc D, class F, class Mid>
+KF_HD void run_c2r_first_paired(int t, bool active, const F& f, typename A::C* wr, const TwTab<A>& tw, const PlanConsts<A>& pc,
+                                const typename A::C* stw, int inverse, const Mid& mid)
+{
+    typedef cx<typename A::R> X;
+    constexpr int R = D.R(0), W = D.items(0), nc = D.N, half = W / 2;
+    constexpr int kIt = (half + D.team - 1) / D.team;
+    const typename A::R sg = A::sign_of(inverse);
+    static_for<kIt>([&](auto ITER) {
+        const int u = t + decltype(ITER)::value * D.team;
+        const bool on = active && u < half;
+        const int wa = on ? u : 0, wb = (on && u != 0) ? W - u : half;
+        X a[R], b[R];
+        if (on) {
+            if (u == 0) {
+                X dummy;
+                fftri_pre_pair<A>(0, f(0), f(nc), f(0), a[0], dummy);            // T[0] from F[0], F[nc]
+                static_for<R / 2>([&](auto EE) {
+                    constexpr int e = decltype(EE)::value;
+                    if constexpr (e >= 1) c2r_make_pair<A>(e * W, nc, f, stw, a[e], a[R - e]);
+                    c2r_make_pair<A>(half + e * W, nc, f, stw, b[e], b[R - 1 - e]);
+                });
+                c2r_make_pair<A>(nc / 2, nc, f, stw, dummy, a[R / 2]);             // k == nc/2: the second assignment wins
+            } else {
+                static_for<R / 2>([&](auto EE) {
+                    constexpr int e = decltype(EE)::value;
+                    c2r_make_pair<A>(u + e * W, nc, f, stw, a[e], b[R - 1 - e]);
+                    c2r_make_pair<A>((W - u) + e * W, nc, f, stw, b[e], a[R - 1 - e]);
+                });
+            }
+        }
+        mid();
+        if (on) {
+            item_stages<A, D, 0>(wa, a, tw, pc, sg);
+            item_stages<A, D, 0>(wb, b, tw, pc, sg);
+            item_store<A, D, 0>(wa, wr, a);
+            item_store<A, D, 0>(wb, wr, b);
+        }
+    });
 }
 
 // Shared-memory layout of one CTA of the fused kernel.
@@ -250,16 +300,25 @@ struct FusedLayout {
     static constexpr PlanDesc D = PT::D;
     static constexpr bool kRing = D.nstage > 0 && MODE != kC2CCol;
     static constexpr int kRowIn = (MODE == kC2R) ? D.N + 1 : D.N;   // complex elements per input row
-    static_assert(D.nbuf == 2 || (D.nbuf == 1 && D.G == 2 && (MODE == kC2C || MODE == kC2CCol)), "single exchange buffer: two-group C2C/column plans only");
+    static_assert(D.nbuf == 2 || D.nbuf == 0 || (D.nbuf == 1 && D.G == 2 && (MODE == kC2C || MODE == kC2CCol)), "single exchange buffer: two-group C2C/column plans only");
     // kiss_fftr post pass by warp shuffles instead of a T[] round trip through shared memory: needs whole warps per
     // team and the last group's work items to divide evenly (PlanDesc::shfl_post asks for it)
     static constexpr bool kShflPost = MODE == kR2C && D.shfl_post && D.team % 32 == 0 && D.items(D.G - 1) % D.team == 0;
-    // kiss_fftr with the last radix-2/4 stage run on work-item pairs (k', m-k'): post pass in registers, no T[] buffer
-    static constexpr bool kPairedLast = MODE == kR2C && D.paired_last && D.G >= 2 && D.glen[D.G - 1] == 1 &&
-                                        (D.p[0] == 2 || D.p[0] == 4) && (D.N / D.p[0]) % 2 == 0;
+    // kiss_fftr with the last group run on work-item pairs (k', m-k'): post pass in registers, no T[] buffer
+    static constexpr bool kPairedLast = MODE == kR2C && D.paired && D.G >= 2 && D.R(D.G - 1) % 2 == 0 && D.items(D.G - 1) % 2 == 0;
+    // kiss_fftri with the split pre pass + first group run on work-item pairs: every spectrum bin is read once
+    static constexpr bool kPairedFirst = MODE == kC2R && D.paired && D.G >= 2 && D.R(0) % 2 == 0 && D.items(0) % 2 == 0;
+    // nbuf == 0: the exchange between the two groups of a paired real plan happens IN PLACE in the input stage (the
+    // team re-uses the memory its row landed in), which cuts the shared memory per transform in flight to one row
+    static constexpr bool kInPlace = D.nbuf == 0;
+    static_assert(!kInPlace || (kRing && D.G == 2 &&
+                                ((kPairedLast && D.iters(0) == 1 && D.items(1) / 2 <= D.team) ||
+                                 (kPairedFirst && D.iters(1) == 1 && D.items(0) / 2 <= D.team))),
+                  "in-place exchange: two-group paired R2C / C2R plans with an input ring and one work item per thread");
     static constexpr size_t kExchBytes = (D.G >= 2 || (MODE == kR2C && !kShflPost)) ? (size_t)D.nbuf * D.tpc * D.pitch() * sizeof(typename A::C) : 0;
     static constexpr size_t kRingOff = (kExchBytes + 127) / 128 * 128;
-    static constexpr size_t kStageBytes = ((size_t)D.tpc * kRowIn * sizeof(typename A::C) + 127) / 128 * 128;
+    static constexpr int kStageElems = (kInPlace && D.pitch() > kRowIn) ? D.tpc * D.pitch() : D.tpc * kRowIn;
+    static constexpr size_t kStageBytes = ((size_t)kStageElems * sizeof(typename A::C) + 127) / 128 * 128;
     static constexpr size_t kBarOff = kRingOff + (kRing ? D.nstage * kStageBytes : 0);
     static constexpr size_t kTotal = kRing ? kBarOff + 8 * (size_t)D.nstage : kExchBytes;
 };
@@ -339,8 +398,25 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             }
         };
 
-        if constexpr (MODE == kR2C && LY::kPairedLast) {
-            // ---- kiss_fftr: all groups but the last, then the last stage + split pass on work-item pairs ----
+        if constexpr (MODE == kR2C && LY::kPairedLast && LY::kInPlace) {
+            // ---- kiss_fftr, two groups, exchange in place in the landed input stage ----
+            constexpr int R0 = PT::D.R(0), W0 = PT::D.items(0);
+            C* const ex = stage_ptr(stg) + team * kPitch;
+            const bool on0 = active && t < W0;
+            X v[R0];
+            if (on0) {
+                static_for<R0>([&](auto E) { constexpr int e = decltype(E)::value; v[e] = A::load(srow[t + e * W0]); });
+                item_stages<A, PT::D, 0>(t, v, tw, P.pc, A::sign_of(P.inverse));
+            }
+            env.sync();                                   // every team has read its landed row
+            if (on0) item_store<A, PT::D, 0>(t, ex, v);
+            env.sync();
+            run_r2c_last_paired<A, PT::D>(t, active, ex, tw, P.pc, P.stw, P.out + b * P.out_dist, P.inverse, [&]() {
+                env.sync();                               // the exchange zone is consumed: the stage can be refilled
+                recycle();
+            });
+        } else if constexpr (MODE == kR2C && LY::kPairedLast) {
+            // ---- kiss_fftr: all groups but the last, then the last group + split pass on work-item pairs ----
             constexpr int gl = PT::D.G - 1;
             DstGlobal<A> unused{nullptr};
             auto run_all = [&](auto src) {
@@ -352,7 +428,32 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             };
             if constexpr (kRing) run_all(SrcShared<A>{srow});
             else run_all(SrcGlobal<A, true>{P.in + b * P.in_dist, 1});
-            run_r2c_last_paired<A, PT::D>(t, active, (gl & 1) ? b1 : b0, tw, P.stw, P.out + b * P.out_dist, P.inverse);
+            run_r2c_last_paired<A, PT::D>(t, active, (gl & 1) ? b1 : b0, tw, P.pc, P.stw, P.out + b * P.out_dist, P.inverse, []() {});
+            par ^= (D.G - 1) & 1;
+        } else if constexpr (MODE == kC2R && LY::kPairedFirst && LY::kInPlace) {
+            // ---- kiss_fftri, two groups, exchange in place in the landed input stage ----
+            C* const ex = stage_ptr(stg) + team * kPitch;
+            DstGlobal<A> dstg{P.out + b * P.out_dist};
+            auto f = [&](int i) { return A::load(srow[i]); };
+            run_c2r_first_paired<A, PT::D>(t, active, f, ex, tw, P.pc, P.stw, P.inverse, [&]() { env.sync(); });
+            env.sync();
+            run_group<A, PT::D, 1, NoSrc, DstGlobal<A>>(t, active, NoSrc{}, dstg, ex, nullptr, tw, P.pc, P.inverse);
+            env.sync();
+            recycle();
+        } else if constexpr (MODE == kC2R && LY::kPairedFirst) {
+            // ---- kiss_fftri: split pre pass + first group on work-item pairs, then the remaining groups ----
+            DstGlobal<A> dstg{P.out + b * P.out_dist};
+            if constexpr (kRing) {
+                auto f = [&](int i) { return A::load(srow[i]); };
+                run_c2r_first_paired<A, PT::D>(t, active, f, b1, tw, P.pc, P.stw, P.inverse, []() {});
+            } else {
+                const C* row = P.in + b * P.in_dist;
+                auto f = [&](int i) { return A::load(ld_stream(row + i)); };
+                run_c2r_first_paired<A, PT::D>(t, active, f, b1, tw, P.pc, P.stw, P.inverse, []() {});
+            }
+            env.sync();
+            recycle();
+            run_groups<A, PT::D, 1, NoSrc, DstGlobal<A>>(env, t, active, NoSrc{}, dstg, b1, b0, tw, P.pc, P.inverse);
             par ^= (D.G - 1) & 1;
         } else if constexpr (MODE == kR2C && LY::kShflPost) {
             // ---- kiss_fftr with the split post pass (kiss_fftr.c:88-116) done in registers ---------------------------

@@ -219,6 +219,46 @@ KF_HD int phys_rt(int a, int logpad) { return logpad >= 31 ? a : a + (a >> logpa
 //   Dst::store(k, v)  element k of the natural-order output                               [last group only]
 //   rd / wr           this transform's exchange buffers (already offset by team * pitch)
 // ---------------------------------------------------------------------------------------------------------
+// the R(g) registers of work item w of group g >= 1, read from the exchange buffer the previous group wrote
+template <class A, PlanDesc D, int g>
+KF_HD void item_load(int w, const typename A::C* rd, cx<typename A::R>* v)
+{
+    constexpr int R = D.R(g), Flo = D.Flo(g);
+    // When the skew phys(a) = a + (a >> logpad) cannot carry between the thread-dependent base and the
+    // register-dependent offset (true for all power-of-two plans, see PlanDesc::lin_rd/lin_wr) the offset part is
+    // a compile-time constant and folds into the LDS/STS immediate.
+    constexpr bool kLinRd = D.lin_rd(g);
+    const int off = w % Flo, kp = w / Flo;
+    const int rbase = phys_rt(kp * (Flo * R) + off, D.logpad);
+    static_for<R>([&](auto E) {
+        constexpr int e = decltype(E)::value;
+        if constexpr (kLinRd) v[e] = A::load(rd[rbase + D.phys(e * Flo)]);
+        else v[e] = A::load(rd[phys_rt(kp * (Flo * R) + off + e * Flo, D.logpad)]);
+    });
+}
+
+// the radix stages of group g on the registers of work item w
+template <class A, PlanDesc D, int g>
+KF_HD void item_stages(int w, cx<typename A::R>* v, const TwTab<A>& tw, const PlanConsts<A>& pc, typename A::R sg)
+{
+    run_stages_from<A, D, g, D.s_hi(g)>(v, w / D.Flo(g), w, tw, pc, sg);
+}
+
+// the outputs of work item w of group g < G-1, written to the exchange buffer the next group reads
+template <class A, PlanDesc D, int g>
+KF_HD void item_store(int w, typename A::C* wr, const cx<typename A::R>* v)
+{
+    constexpr int R = D.R(g), Flo = D.Flo(g);
+    constexpr bool kLinWr = D.lin_wr(g);
+    const int off = w % Flo, kp = w / Flo;
+    const int wbase = phys_rt(kp * Flo + off, D.logpad);
+    static_for<R>([&](auto E) {
+        constexpr int e = decltype(E)::value;
+        if constexpr (kLinWr) wr[wbase + D.phys(D.kout(g, e) * Flo)] = A::store(v[e]);
+        else wr[phys_rt((kp + D.kout(g, e)) * Flo + off, D.logpad)] = A::store(v[e]);
+    });
+}
+
 template <class A, PlanDesc D, int g, class Src, class Dst>
 KF_HD void run_group(int t, bool active, const Src& src, const Dst& dst, const typename A::C* rd, typename A::C* wr,
                      const TwTab<A>& tw, const PlanConsts<A>& pc, int inverse)
@@ -226,33 +266,30 @@ KF_HD void run_group(int t, bool active, const Src& src, const Dst& dst, const t
     typedef cx<typename A::R> X;
     constexpr int R = D.R(g), WI = D.items(g), IT = D.iters(g), Flo = D.Flo(g);
     constexpr bool kFirst = (g == 0), kLast = (g == D.G - 1);
-    // When the skew phys(a) = a + (a >> logpad) cannot carry between the thread-dependent base and the
-    // register-dependent offset (true for all power-of-two plans, see PlanDesc::lin_rd/lin_wr) the offset part is
-    // a compile-time constant and folds into the LDS/STS immediate.
-    constexpr bool kLinRd = D.lin_rd(g), kLinWr = D.lin_wr(g);
     const typename A::R sg = A::sign_of(inverse);
     static_for<IT>([&](auto ITER) {
         constexpr int it = decltype(ITER)::value;
         const int w = t + it * D.team;
         const bool on = active && ((it + 1) * D.team <= WI || w < WI);
         if (on) {
-            const int off = w % Flo, kp = w / Flo;
             X v[R];
-            const int rbase = kFirst ? off : phys_rt(kp * (Flo * R) + off, D.logpad);
-            static_for<R>([&](auto E) {
-                constexpr int e = decltype(E)::value;
-                if constexpr (kFirst) v[e] = src.template get<it, e>(rbase + e * Flo);
-                else if constexpr (kLinRd) v[e] = A::load(rd[rbase + D.phys(e * Flo)]);
-                else v[e] = A::load(rd[phys_rt(kp * (Flo * R) + off + e * Flo, D.logpad)]);
-            });
-            run_stages_from<A, D, g, D.s_hi(g)>(v, kp, w, tw, pc, sg);
-            const int wbase = kLast ? kp : phys_rt(kp * Flo + off, D.logpad);
-            static_for<R>([&](auto E) {
-                constexpr int e = decltype(E)::value;
-                if constexpr (kLast) dst.template put<it, e>(wbase + D.kout(g, e), v[e]);
-                else if constexpr (kLinWr) wr[wbase + D.phys(D.kout(g, e) * Flo)] = A::store(v[e]);
-                else wr[phys_rt((kp + D.kout(g, e)) * Flo + off, D.logpad)] = A::store(v[e]);
-            });
+            if constexpr (kFirst) {
+                static_for<R>([&](auto E) {
+                    constexpr int e = decltype(E)::value;
+                    v[e] = src.template get<it, e>(w % Flo + e * Flo);
+                });
+            } else {
+                item_load<A, D, g>(w, rd, v);
+            }
+            item_stages<A, D, g>(w, v, tw, pc, sg);
+            if constexpr (kLast) {
+                static_for<R>([&](auto E) {
+                    constexpr int e = decltype(E)::value;
+                    dst.template put<it, e>(w / Flo + D.kout(g, e), v[e]);
+                });
+            } else {
+                item_store<A, D, g>(w, wr, v);
+            }
         }
     });
 }

@@ -46,9 +46,11 @@ struct PlanDesc {
                             //    digits are non-zero derives its twiddles as tw[q*F*k'] * tw[q*F*kabove] -- the first factor is the
                             //    table entry of the upper==0 butterfly (shared by the whole stage), the second a plan constant
     int shfl_post;          // kiss_fftr: split post pass in registers via warp shuffles (needs team % 32 == 0)
-    int paired_last;        // kiss_fftr: the last group (one radix-2/4 stage) processes work items k' and m-k' in the same
-                            // thread, so every bin pair (k, nc-k) of the split post pass is complete in its registers
-    int nbuf;               // exchange buffers: 2 = ping-pong (default); 1 = single buffer + one extra barrier per tile,
+    int paired;             // real transforms on work-item pairs.  kiss_fftr plan: the last group runs items k' and m-k' in the
+                            // same thread, so every bin pair (k, nc-k) of the split post pass is complete in its registers;
+                            // kiss_fftri plan: the first group runs items u and W-u, reading every spectrum pair once
+    int nbuf;               // exchange buffers: 0 = in place in the input stage (two-group paired real plans);
+                            // 2 = ping-pong (default); 1 = single buffer + one extra barrier per tile,
                             // only for two-group plans in the C2C / column modes (halves shared memory => wider column tiles)
 
     KF_CE int F(int s) const

@@ -13,8 +13,19 @@ splits a d0 x d1 x d2 array into slabs of d0/G planes per rank and needs a singl
 
 The result is the 3-D DFT X[k0][k1][k2] stored as out[k2 - r*d2/G][k1][k0] on rank r ("transposed-out", distributed
 along k2) -- the usual contract of slab FFTs; `gather_natural` re-assembles the natural order for checks.  Float and
-double only agree with kiss_fftnd up to rounding because the axes run in the order 2,1,0 instead of 0,1,2; the
-fixed-point builds are bit-exact only in the single-GPU kiss_fftnd path.
+double only agree with kiss_fftnd up to rounding because the axes run in the order 2,1,0 instead of 0,1,2.
+
+Reference-order mode (`forward_reference`): kiss_fftnd sweeps the axes in the order 0,1,2
+(kiss_fftnd.c:172-178), and the Q15/Q31 results depend on that order.  Starting from slabs along the LAST axis, axes 0
+and 1 are local, one exchange completes axis 2, and the result comes out in natural order as axis-0 slabs:
+
+  A'. axis 0 of the local [d0][d1][d2/G] array   -> kiss_fft_axis_pass_dev                   [d1][d2/G][d0]
+  B'. axis 1, k0 columns of destination rank s    -> kiss_fft_planes_pass_dev per s           [G][d2/G][d0/G][d1]
+  X'. all-to-all                                                                              [d2][d0/G][d1]
+  C'. axis 2                                      -> kiss_fft_axis_pass_dev                   [d0/G][d1][d2]
+
+Same butterflies on the same operands as kiss_fftnd, so every datatype -- fixed point included -- is bit-identical to
+the single-GPU kiss_fftnd.
 
 The geometry (who owns what, exchange counts and offsets) is plain integer logic in `SlabGeometry` so that it is
 testable on CPU with the gloo backend; the compute steps call the CUDA library and fail without it.
@@ -137,9 +148,14 @@ class SlabFFT3D:
             be.rows_inplace(x, stream)                               # A
             for s in range(g.world):
                 be.planes_cols(x, send, dst_rank=s, stream=stream, dst_block=s)
-            self.dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)     # X
+            self._exchange(recv, send)                               # X
         be.axis0(recv, out, stream)                                  # C
         return out
+
+    def _exchange(self, recv, send):
+        """block s of `send` goes to rank s; moved as bytes so that every datatype (Q15 included) is a type NCCL knows"""
+        u8 = self.torch.uint8
+        self.dist.all_to_all_single(recv.view(-1).view(u8), send.view(-1).view(u8), group=self.group)
 
     def _forward_p2p(self, x, recv, stream):
         """steps A, B and the exchange fused and overlapped.
@@ -179,6 +195,40 @@ class SlabFFT3D:
         main.wait_event(done)
         with torch.cuda.stream(main):
             self._symm.barrier()          # every rank's blocks have landed in every receive buffer
+
+    # ---- reference axis order 0,1,2 (bit-exact with kiss_fftnd for every datatype) ----
+    def alloc_reference(self):
+        """(local input [d0][d1][d2/G][2], work [d1][d2/G][d0][2], send and recv [G][d2/G][d0/G][d1][2], out [d0/G][d1][d2][2])"""
+        g, be = self.geo, self.backend
+        x = be.empty((g.d0, g.d1, g.cols, 2))
+        work = be.empty((g.d1, g.cols, g.d0, 2))
+        send = be.empty((g.world, g.cols, g.planes, g.d1, 2)) if g.world > 1 else None
+        recv = be.empty((g.world, g.cols, g.planes, g.d1, 2))
+        out = be.empty((g.planes, g.d1, g.d2, 2))
+        return x, work, send, recv, out
+
+    def forward_reference(self, x, work, send, recv, out, stream=0):
+        """x: this rank's slab x[:, :, r*d2/G:(r+1)*d2/G] (not modified); out: X[r*d0/G:(r+1)*d0/G, :, :] in natural order"""
+        g, be = self.geo, self.backend
+        be.ref_axis0(x, work, stream)                                # A'
+        if g.world == 1:
+            be.ref_axis1(work, recv, 0, stream)                      # B' (whole array)
+        else:
+            for s in range(g.world):
+                be.ref_axis1(work, send, s, stream)                  # B'
+            self._exchange(recv, send)                               # X'
+        be.ref_axis2(recv, out, stream)                              # C'
+        return out
+
+    def gather_reference(self, out):
+        """natural-order [d0][d1][d2][2] array on every rank from the axis-0 slabs of forward_reference (testing aid)"""
+        g, torch, dist = self.geo, self.torch, self.dist
+        if g.world == 1:
+            return out
+        mine = out.contiguous().view(-1).view(torch.uint8)
+        parts = [torch.empty_like(mine) for _ in range(g.world)]
+        dist.all_gather(parts, mine, group=self.group)
+        return torch.cat([p.view(out.dtype).view(out.shape) for p in parts], dim=0)
 
     def gather_natural(self, out):
         """collects the distributed transposed result into the natural-order [d0][d1][d2][2] array on every rank (testing aid)"""
@@ -241,6 +291,26 @@ class CudaBackend:
         g = self.geo
         ncols = g.cols * g.d1
         self.lib.axis_pass_dev(self.cfg0, recv, out, ncols, ncols, stream)
+
+    # reference-order steps
+    def ref_axis0(self, x, work, stream):
+        g = self.geo
+        ncols = g.d1 * g.cols                       # [d0][d1*d2l] -> [d1*d2l][d0]
+        self.lib.axis_pass_dev(self.cfg0, x, work, ncols, ncols, stream)
+
+    def ref_axis1(self, work, dst, dst_rank, stream):
+        """work [d1][d2l][d0]: plane = i2l (distance d0), row = i1 (stride d2l*d0), columns = the k0 slab of dst_rank;
+        output block [d2l][d0/G][d1]"""
+        g = self.geo
+        esz = work.element_size() * 2
+        src_ptr = work.data_ptr() + dst_rank * g.planes * esz
+        dst_ptr = dst.data_ptr() + dst_rank * g.block_elems * esz
+        self.lib.planes_pass_dev(self.cfg1, src_ptr, dst_ptr, g.cols, g.planes, g.cols * g.d0, g.d0, g.planes * g.d1, stream)
+
+    def ref_axis2(self, recv, out, stream):
+        g = self.geo
+        ncols = g.planes * g.d1                     # [d2][d0l*d1] -> [d0l*d1][d2]
+        self.lib.axis_pass_dev(self.cfg2, recv, out, ncols, ncols, stream)
 
 
 def reference_slab_numpy(x_full, world):

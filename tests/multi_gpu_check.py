@@ -24,11 +24,16 @@ def main():
     ap.add_argument("--p2p", action="store_true")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--reference-order", action="store_true",
+                    help="axis order 0,1,2 from last-axis slabs; checked BIT-EXACT against the single-GPU kiss_fftnd_dev")
+    ap.add_argument("--tname", default="float", choices=["float", "double", "int16_t", "int32_t"])
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dims = tuple(args.dims)
+    if args.reference_order:
+        return reference_order(args, dims, rank, world)
     plan = SlabFFT3D(dims, tname="float", p2p=args.p2p)
     g = plan.geo
     x, send, recv, out = plan.alloc()
@@ -73,6 +78,51 @@ def main():
                           "a2a_bytes_per_rank": g.a2a_bytes_per_rank(8)}))
         if err is not None:
             assert max(errs) <= 1e-6 * np.log2(n), errs
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def reference_order(args, dims, rank, world):
+    """SlabFFT3D.forward_reference on `world` GPUs must equal kiss_fftnd_dev on one GPU bit for bit (all datatypes)"""
+    import kissfft_b200
+    tname = args.tname
+    plan = SlabFFT3D(dims, tname=tname)
+    g = plan.geo
+    x, work, send, recv, out = plan.alloc_reference()
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)                                     # every rank generates the same full array
+    if tname in ("float", "double"):
+        full = (torch.rand(dims + (2,), generator=gen, device="cuda", dtype=torch.float64) * 2 - 1).to(x.dtype)
+    else:
+        half = (32767 if tname == "int16_t" else 2147483647) // 2
+        full = torch.randint(-half, half + 1, dims + (2,), generator=gen, device="cuda", dtype=torch.int64).to(x.dtype)
+    c0, c1 = g.col_range()
+    x.copy_(full[:, :, c0:c1])
+    stream = torch.cuda.current_stream().cuda_stream
+    plan.forward_reference(x, work, send, recv, out, stream)
+    torch.cuda.synchronize()
+    lib = kissfft_b200.get(tname)
+    cfg = lib.allocnd(list(dims), False)
+    want = torch.empty_like(full)
+    lib.fftnd_dev(cfg, full, want, None, stream)
+    torch.cuda.synchronize()
+    p0, p1 = g.plane_range()
+    exact = bool(torch.equal(out, want[p0:p1]))
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.iters):
+        plan.forward_reference(x, work, send, recv, out, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / args.iters], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    flags = [None] * world
+    dist.all_gather_object(flags, exact)
+    if rank == 0:
+        print(json.dumps({"mode": "reference-order", "tname": tname, "dims": dims, "world": world, "ms": float(ms[0]),
+                          "bit_exact_vs_single_gpu_fftnd_per_rank": flags}))
+        assert all(flags), flags
     dist.barrier()
     dist.destroy_process_group()
 

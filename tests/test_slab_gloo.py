@@ -60,6 +60,84 @@ class NumpyBackend:
         self._put(out, np.fft.fft(a, axis=0).transpose(1, 2, 0))
 
 
+    # reference-order steps (same layouts as CudaBackend.ref_*)
+    def ref_axis0(self, x, work, stream):
+        self._put(work, np.fft.fft(self._c(x), axis=0).transpose(1, 2, 0))
+
+    def ref_axis1(self, work, dst, dst_rank, stream):
+        g = self.geo
+        k0, k1 = g.plane_range(dst_rank)
+        y = np.fft.fft(self._c(work)[:, :, k0:k1], axis=0)             # [k1][i2l][k0l]
+        self._put(dst[dst_rank], y.transpose(1, 2, 0))
+
+    def ref_axis2(self, recv, out, stream):
+        g = self.geo
+        a = self._c(recv).reshape(g.d2, g.planes, g.d1)
+        self._put(out, np.fft.fft(a, axis=0).transpose(1, 2, 0))
+
+
+class OracleBackend(NumpyBackend):
+    """the reference-order steps in Q15 with the CPU oracle: the distributed result must be bit-identical to kiss_fftnd"""
+    torch_dtype = torch.int16
+
+    def __init__(self, geo):
+        from oracle.loader import Oracle
+        self.geo = geo
+        self.o = Oracle("int16_t")
+
+    def empty(self, shape):
+        return torch.zeros(shape, dtype=torch.int16)
+
+    def _cols(self, a):
+        """1-D transforms along axis 0 of a [n][...][2] int16 array"""
+        n = a.shape[0]
+        rows = np.ascontiguousarray(np.moveaxis(a, 0, -2).reshape(-1, n, 2))
+        y = self.o.fft(rows, 0).reshape(a.shape[1:-1] + (n, 2))
+        return y                                                       # [...][n][2]
+
+    def ref_axis0(self, x, work, stream):
+        work.copy_(torch.from_numpy(self._cols(x.numpy())))
+
+    def ref_axis1(self, work, dst, dst_rank, stream):
+        k0, k1 = self.geo.plane_range(dst_rank)
+        dst[dst_rank].copy_(torch.from_numpy(self._cols(np.ascontiguousarray(work.numpy()[:, :, k0:k1]))))
+
+    def ref_axis2(self, recv, out, stream):
+        g = self.geo
+        out.copy_(torch.from_numpy(self._cols(recv.numpy().reshape(g.d2, g.planes, g.d1, 2))))
+
+
+def _worker_reference(rank, world, port, dims, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.loader import Oracle, random_input
+        geo = SlabGeometry(*dims, world, rank)
+        c0, c1 = geo.col_range()
+        # float64 geometry check against numpy
+        rng = np.random.default_rng(11)
+        full = rng.standard_normal(dims) + 1j * rng.standard_normal(dims)
+        plan = SlabFFT3D(dims, tname="double", backend=NumpyBackend(geo))
+        x, work, send, recv, out = plan.alloc_reference()
+        NumpyBackend._put(x, full[:, :, c0:c1])
+        plan.forward_reference(x, work, send, recv, out)
+        nat = NumpyBackend._c(plan.gather_reference(out))
+        want = np.fft.fftn(full)
+        err = float(np.abs(nat - want).max() / np.abs(want).max())
+        # Q15: bit-exact against the oracle's kiss_fftnd
+        fullq = random_input("int16_t", dims, 5)
+        plan = SlabFFT3D(dims, tname="int16_t", backend=OracleBackend(geo))
+        x, work, send, recv, out = plan.alloc_reference()
+        x.copy_(torch.from_numpy(np.ascontiguousarray(fullq[:, :, c0:c1])))
+        plan.forward_reference(x, work, send, recv, out)
+        natq = plan.gather_reference(out).numpy()
+        exact = bool(np.array_equal(natq, Oracle("int16_t").fftnd(fullq)))
+        q.put((rank, err, exact))
+    finally:
+        dist.destroy_process_group()
+
+
 def _worker(rank, world, port, dims, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -106,6 +184,24 @@ def test_slab_exchange_gloo(world, dims):
     assert [r[0] for r in res] == list(range(world))
     for _, e1, e2 in res:
         assert e1 < 1e-12 and e2 < 1e-12
+
+
+@pytest.mark.parametrize("world,dims", [(2, (4, 6, 8)), (2, (8, 5, 6)), (4, (8, 3, 12))])
+def test_slab_reference_order_gloo(world, dims):
+    """axis order 0,1,2 from last-axis slabs: natural-order axis-0 slabs, bit-identical to kiss_fftnd in Q15"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_reference, args=(r, world, port, dims, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=5) for _ in range(world))
+    assert [r[0] for r in res] == list(range(world))
+    for _, err, exact in res:
+        assert err < 1e-12 and exact
 
 
 def test_geometry_and_batch_shard():
