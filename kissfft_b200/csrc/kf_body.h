@@ -300,7 +300,9 @@ struct FusedLayout {
     static constexpr PlanDesc D = PT::D;
     static constexpr bool kRing = D.nstage > 0 && MODE != kC2CCol;
     static constexpr int kRowIn = (MODE == kC2R) ? D.N + 1 : D.N;   // complex elements per input row
-    static_assert(D.nbuf == 2 || D.nbuf == 0 || (D.nbuf == 1 && D.G == 2 && (MODE == kC2C || MODE == kC2CCol)), "single exchange buffer: two-group C2C/column plans only");
+    static_assert(D.nbuf == 2 || (D.nbuf == 1 && D.G == 2 && (MODE == kC2C || MODE == kC2CCol)) ||
+                      (D.nbuf == 1 && D.G == 3 && D.nstage == 1 && D.paired && (MODE == kR2C || MODE == kC2R)),
+                  "single exchange buffer: two-group C2C/column plans, or three-group paired real plans with a one-stage input ring");
     // kiss_fftr post pass by warp shuffles instead of a T[] round trip through shared memory: needs whole warps per
     // team and the last group's work items to divide evenly (PlanDesc::shfl_post asks for it)
     static constexpr bool kShflPost = MODE == kR2C && D.shfl_post && D.team % 32 == 0 && D.items(D.G - 1) % D.team == 0;
@@ -308,16 +310,20 @@ struct FusedLayout {
     static constexpr bool kPairedLast = MODE == kR2C && D.paired && D.G >= 2 && D.R(D.G - 1) % 2 == 0 && D.items(D.G - 1) % 2 == 0;
     // kiss_fftri with the split pre pass + first group run on work-item pairs: every spectrum bin is read once
     static constexpr bool kPairedFirst = MODE == kC2R && D.paired && D.G >= 2 && D.R(0) % 2 == 0 && D.items(0) % 2 == 0;
-    // nbuf == 0: the exchange between the two groups of a paired real plan happens IN PLACE in the input stage (the
-    // team re-uses the memory its row landed in), which cuts the shared memory per transform in flight to one row
-    static constexpr bool kInPlace = D.nbuf == 0;
-    static_assert(!kInPlace || (kRing && D.G == 2 &&
-                                ((kPairedLast && D.iters(0) == 1 && D.items(1) / 2 <= D.team) ||
-                                 (kPairedFirst && D.iters(1) == 1 && D.items(0) / 2 <= D.team))),
-                  "in-place exchange: two-group paired R2C / C2R plans with an input ring and one work item per thread");
+    // nbuf == 1 on a three-group paired real plan: ONE exchange buffer, and the input stage (consumed by the first
+    // group) doubles as the second one.  Shared memory per transform in flight drops from 3 rows to 2, so more CTAs
+    // are resident; the stage is refilled once the last group has read it (no refill under the butterflies).
+    static constexpr bool kStageExch = D.nbuf == 1 && kRing && D.nstage == 1 && D.G == 3 &&
+                                       ((kPairedLast && D.items(2) / 2 <= D.team) || kPairedFirst);
     static constexpr size_t kExchBytes = (D.G >= 2 || (MODE == kR2C && !kShflPost)) ? (size_t)D.nbuf * D.tpc * D.pitch() * sizeof(typename A::C) : 0;
     static constexpr size_t kRingOff = (kExchBytes + 127) / 128 * 128;
-    static constexpr int kStageElems = (kInPlace && D.pitch() > kRowIn) ? D.tpc * D.pitch() : D.tpc * kRowIn;
+    // rows whose byte size is not a multiple of 16 (kiss_fftri: ncfft+1 elements): a tile then starts off the 16-byte
+    // grid cp.async.bulk needs, so the copy starts at the aligned address below it and is rounded up to 16 bytes --
+    // the tile lands kMis elements into the stage (and up to 15 bytes of the following row come along)
+    static constexpr int kE16 = 16 / (int)sizeof(typename A::C) > 0 ? 16 / (int)sizeof(typename A::C) : 1;
+    static constexpr bool kSlackRing = kRing && ((size_t)D.tpc * kRowIn * sizeof(typename A::C)) % 16 != 0;
+    static constexpr int kLandElems = D.tpc * kRowIn + (kSlackRing ? kE16 : 0);
+    static constexpr int kStageElems = (kStageExch && D.tpc * D.pitch() > kLandElems) ? D.tpc * D.pitch() : kLandElems;
     static constexpr size_t kStageBytes = ((size_t)kStageElems * sizeof(typename A::C) + 127) / 128 * 128;
     static constexpr size_t kBarOff = kRingOff + (kRing ? D.nstage * kStageBytes : 0);
     static constexpr size_t kTotal = kRing ? kBarOff + 8 * (size_t)D.nstage : kExchBytes;
@@ -359,10 +365,20 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
     // ---- input ring ----
     auto stage_ptr = [&](int s) { return reinterpret_cast<C*>(smem_raw + LY::kRingOff + (size_t)s * LY::kStageBytes); };
     auto bar_ptr = [&](int s) { return smem_raw + LY::kBarOff + 8 * (size_t)s; };
+    auto tile_mis = [&](long long tl) -> int {   // elements between the 16-byte grid and the start of tile tl
+        if constexpr (LY::kSlackRing) return (int)((tl * PT::D.tpc * LY::kRowIn) % LY::kE16);
+        else return 0;
+    };
     auto issue = [&](int s, long long tl) {   // elected thread only
         const long long row0 = tl * D.tpc;
         const long long rows = (P.howmany - row0) < D.tpc ? (P.howmany - row0) : D.tpc;
-        env.bulk_load(bar_ptr(s), stage_ptr(s), P.in + row0 * kRowIn, (unsigned)(rows * kRowIn * sizeof(C)));
+        if constexpr (LY::kSlackRing) {
+            const int mis = tile_mis(tl);
+            const long long elems = (rows * kRowIn + mis + LY::kE16 - 1) / LY::kE16 * LY::kE16;
+            env.bulk_load(bar_ptr(s), stage_ptr(s), P.in + row0 * kRowIn - mis, (unsigned)(elems * sizeof(C)));
+        } else {
+            env.bulk_load(bar_ptr(s), stage_ptr(s), P.in + row0 * kRowIn, (unsigned)(rows * kRowIn * sizeof(C)));
+        }
     };
     if constexpr (kRing) {
         if (tid == 0)
@@ -386,7 +402,7 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
         const C* srow = nullptr;
         if constexpr (kRing) {
             env.mbar_wait(bar_ptr(stg), it / (D.nstage > 0 ? D.nstage : 1));
-            srow = stage_ptr(stg) + team * kRowIn;
+            srow = stage_ptr(stg) + tile_mis(tile) + team * kRowIn;
         }
         // after the CTA barrier that follows the last read of the stage: refill it with the tile nstage rounds ahead
         auto recycle = [&]() {
@@ -398,21 +414,18 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             }
         };
 
-        if constexpr (MODE == kR2C && LY::kPairedLast && LY::kInPlace) {
-            // ---- kiss_fftr, two groups, exchange in place in the landed input stage ----
-            constexpr int R0 = PT::D.R(0), W0 = PT::D.items(0);
-            C* const ex = stage_ptr(stg) + team * kPitch;
-            const bool on0 = active && t < W0;
-            X v[R0];
-            if (on0) {
-                static_for<R0>([&](auto E) { constexpr int e = decltype(E)::value; v[e] = A::load(srow[t + e * W0]); });
-                item_stages<A, PT::D, 0>(t, v, tw, P.pc, A::sign_of(P.inverse));
-            }
-            env.sync();                                   // every team has read its landed row
-            if (on0) item_store<A, PT::D, 0>(t, ex, v);
+        if constexpr (MODE == kR2C && LY::kStageExch) {
+            // ---- kiss_fftr, three groups: stage -> A -> stage -> paired last group ----
+            C* const exA = bufA + team * kPitch;
+            C* const exS = stage_ptr(stg) + team * kPitch;
+            DstGlobal<A> unused{nullptr};
+            typedef SrcShared<A> S;
+            run_group<A, PT::D, 0, S, DstGlobal<A>>(t, active, S{srow}, unused, nullptr, exA, tw, P.pc, P.inverse);
+            env.sync();                                   // every team has consumed its landed row
+            run_group<A, PT::D, 1, S, DstGlobal<A>>(t, active, S{srow}, unused, exA, exS, tw, P.pc, P.inverse);
             env.sync();
-            run_r2c_last_paired<A, PT::D>(t, active, ex, tw, P.pc, P.stw, P.out + b * P.out_dist, P.inverse, [&]() {
-                env.sync();                               // the exchange zone is consumed: the stage can be refilled
+            run_r2c_last_paired<A, PT::D>(t, active, exS, tw, P.pc, P.stw, P.out + b * P.out_dist, P.inverse, [&]() {
+                env.sync();                               // the stage is consumed again: refill it
                 recycle();
             });
         } else if constexpr (MODE == kR2C && LY::kPairedLast) {
@@ -430,14 +443,17 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             else run_all(SrcGlobal<A, true>{P.in + b * P.in_dist, 1});
             run_r2c_last_paired<A, PT::D>(t, active, (gl & 1) ? b1 : b0, tw, P.pc, P.stw, P.out + b * P.out_dist, P.inverse, []() {});
             par ^= (D.G - 1) & 1;
-        } else if constexpr (MODE == kC2R && LY::kPairedFirst && LY::kInPlace) {
-            // ---- kiss_fftri, two groups, exchange in place in the landed input stage ----
-            C* const ex = stage_ptr(stg) + team * kPitch;
+        } else if constexpr (MODE == kC2R && LY::kStageExch) {
+            // ---- kiss_fftri, three groups: paired first group from the stage -> A -> stage -> last group ----
+            C* const exA = bufA + team * kPitch;
+            C* const exS = stage_ptr(stg) + team * kPitch;
             DstGlobal<A> dstg{P.out + b * P.out_dist};
             auto f = [&](int i) { return A::load(srow[i]); };
-            run_c2r_first_paired<A, PT::D>(t, active, f, ex, tw, P.pc, P.stw, P.inverse, [&]() { env.sync(); });
+            run_c2r_first_paired<A, PT::D>(t, active, f, exA, tw, P.pc, P.stw, P.inverse, []() {});
+            env.sync();                                   // every team has consumed its landed row
+            run_group<A, PT::D, 1, NoSrc, DstGlobal<A>>(t, active, NoSrc{}, dstg, exA, exS, tw, P.pc, P.inverse);
             env.sync();
-            run_group<A, PT::D, 1, NoSrc, DstGlobal<A>>(t, active, NoSrc{}, dstg, ex, nullptr, tw, P.pc, P.inverse);
+            run_group<A, PT::D, 2, NoSrc, DstGlobal<A>>(t, active, NoSrc{}, dstg, exS, nullptr, tw, P.pc, P.inverse);
             env.sync();
             recycle();
         } else if constexpr (MODE == kC2R && LY::kPairedFirst) {
@@ -580,7 +596,7 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             par ^= (D.G - 1) & 1;
         }
         // single exchange buffer: the next tile's first group overwrites what the last group just read
-        if constexpr (D.nbuf == 1) env.sync();
+        if constexpr (D.nbuf == 1 && !LY::kStageExch) env.sync();
     }
 }
 

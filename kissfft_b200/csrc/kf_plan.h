@@ -49,9 +49,9 @@ struct PlanDesc {
     int paired;             // real transforms on work-item pairs.  kiss_fftr plan: the last group runs items k' and m-k' in the
                             // same thread, so every bin pair (k, nc-k) of the split post pass is complete in its registers;
                             // kiss_fftri plan: the first group runs items u and W-u, reading every spectrum pair once
-    int nbuf;               // exchange buffers: 0 = in place in the input stage (two-group paired real plans);
-                            // 2 = ping-pong (default); 1 = single buffer + one extra barrier per tile,
-                            // only for two-group plans in the C2C / column modes (halves shared memory => wider column tiles)
+    int nbuf;               // exchange buffers: 2 = ping-pong (default); 1 = single buffer: two-group plans in the C2C /
+                            // column modes (+ one barrier per tile; halves shared memory => wider column tiles), or
+                            // three-group paired real plans, where the input stage doubles as the second buffer
 
     KF_CE int F(int s) const
     {

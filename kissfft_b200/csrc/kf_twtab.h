@@ -73,6 +73,7 @@ void fill_fc_side(FCSide<A>& S, const typename A::C* h_tw, const typename A::C* 
 // How many leading rows of a call may go through the fused kernel of plan PT (the rest, if any, must take the
 // run-time kernel).  The bulk-async input ring needs contiguous rows, a 16-byte aligned base and tiles whose byte
 // size is a multiple of 16 (cp.async.bulk rules); a ragged last tile that breaks the size rule is peeled off.
+// Plans whose tiles are not a multiple of 16 bytes (FusedLayout::kSlackRing) copy from the aligned address below.
 template <class A, class PT, int MODE>
 long long fused_rows(const KParams<A>& P)
 {
@@ -81,8 +82,14 @@ long long fused_rows(const KParams<A>& P)
     if (MODE == kC2C && P.in_stride != 1) return 0;
     if (!LY::kRing) return P.howmany;
     const size_t row_bytes = (size_t)LY::kRowIn * sizeof(typename A::C);
-    if (P.in_dist != LY::kRowIn || ((size_t)P.in % 16) != 0 || (row_bytes * D.tpc) % 16 != 0) return 0;
+    if (P.in_dist != LY::kRowIn || ((size_t)P.in % 16) != 0) return 0;
     const long long rem = P.howmany % D.tpc;
+    if (LY::kSlackRing) {
+        // tiles start off the 16-byte grid and their copies are rounded up: the LAST tile may read up to 15 bytes past
+        // the end of the batch, so it is kept only when the batch ends on the grid
+        if (((size_t)P.howmany * row_bytes) % 16 == 0) return P.howmany;
+        return P.howmany - (rem ? rem : D.tpc);
+    }
     return ((size_t)rem * row_bytes) % 16 == 0 ? P.howmany : P.howmany - rem;
 }
 
