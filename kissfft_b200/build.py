@@ -39,11 +39,20 @@ def _sources():
         os.path.join(HERE, "..", "include", f) for f in sorted(os.listdir(os.path.join(HERE, "..", "include")))]
 
 
-def _stale(target):
+def _stale(target, sources=None):
     if not os.path.exists(target):
         return True
     t = os.path.getmtime(target)
-    return any(os.path.getmtime(s) > t for s in _sources())
+    return any(os.path.getmtime(s) > t for s in (sources if sources is not None else _sources()))
+
+
+def _cuda_sources():
+    """what the kernel object depends on: everything but the C host layer"""
+    return [s for s in _sources() if not s.endswith("kf_api.c")]
+
+
+def _host_sources():
+    return [s for s in _sources() if s.endswith((".c", "kf_internal.h")) or os.sep + "include" + os.sep in s]
 
 
 def _run(cmd):
@@ -62,12 +71,14 @@ def build_one(tname, force=False, verbose=False):
     tf = TYPEFLAGS[tname]
     o_cu = os.path.join(OBJDIR, "kf_launch-%s.o" % tname)
     o_c = os.path.join(OBJDIR, "kf_api-%s.o" % tname)
-    log = _run([NVCC, "-std=c++20", "--expt-relaxed-constexpr", *ARCH, "-lineinfo", "-O3", "-Xcompiler", "-fPIC,-fvisibility=hidden",
-                "-ccbin", HOSTCXX, "-Xptxas", "-v", "-DKISS_FFT_SHARED", *tf, "-c", os.path.join(CSRC, "kf_launch.cu"), "-o", o_cu])
-    if verbose:
-        print(log)
-    _run([HOSTCC, "-std=gnu11", "-O2", "-fPIC", "-fvisibility=hidden", "-Wall", "-DKISS_FFT_SHARED", *tf,
-          "-I", os.path.join(CUDA_HOME, "include"), "-c", os.path.join(CSRC, "kf_api.c"), "-o", o_c])
+    if force or _stale(o_cu, _cuda_sources()):
+        log = _run([NVCC, "-std=c++20", "--expt-relaxed-constexpr", *ARCH, "-lineinfo", "-O3", "-Xcompiler", "-fPIC,-fvisibility=hidden",
+                    "-ccbin", HOSTCXX, "-Xptxas", "-v", "-DKISS_FFT_SHARED", *tf, "-c", os.path.join(CSRC, "kf_launch.cu"), "-o", o_cu])
+        if verbose:
+            print(log)
+    if force or _stale(o_c, _host_sources()):
+        _run([HOSTCC, "-std=gnu11", "-O2", "-fPIC", "-fvisibility=hidden", "-Wall", "-DKISS_FFT_SHARED", *tf,
+              "-I", os.path.join(CUDA_HOME, "include"), "-c", os.path.join(CSRC, "kf_api.c"), "-o", o_c])
     _run([NVCC, "-shared", *ARCH, "-ccbin", HOSTCXX, o_cu, o_c, "-o", out, "-lpthread", "-lm"])
     return out
 

@@ -799,6 +799,9 @@ static int kf_chunk_c2r(void *cfg, const void *d_in, void *d_out, size_t n, void
                                 (size_t)c->nfft, stream);
 }
 
+#ifndef KF_CHUNK_MIB
+#define KF_CHUNK_MIB 32
+#endif
 static int kf_host_pipeline(kf_chunk_fn fn, void *cfg, const void *in, void *out, size_t howmany, size_t in_row_bytes,
                             size_t out_row_bytes)
 {
@@ -806,8 +809,12 @@ static int kf_host_pipeline(kf_chunk_fn fn, void *cfg, const void *in, void *out
     if (howmany == 0) return 0;
     pthread_mutex_lock(&g_stage_lock);
     int rc = kf_get_streams();
-    /* chunk so that one chunk moves ~32 MiB each way (PCIe-efficient, still >= 6 chunks for the big batches) */
-    size_t rows = (size_t)(32u << 20) / (in_row_bytes > out_row_bytes ? in_row_bytes : out_row_bytes);
+    /* chunk so that one chunk moves ~KF_CHUNK_MIB each way: large enough for PCIe efficiency, small enough that the
+     * un-overlapped first H2D and last D2H of a call stay short (KISSFFT_CHUNK_MIB overrides, for experiments) */
+    size_t chunk_mib = KF_CHUNK_MIB;
+    const char *env = getenv("KISSFFT_CHUNK_MIB");
+    if (env && atoi(env) > 0 && atoi(env) <= 1024) chunk_mib = (size_t)atoi(env);
+    size_t rows = (chunk_mib << 20) / (in_row_bytes > out_row_bytes ? in_row_bytes : out_row_bytes);
     if (rows < 1) rows = 1;
     if (rows >= 64) rows &= ~(size_t)63; /* whole tiles for every fused plan (tpc <= 16) and 16-byte aligned chunk sizes */
     if (rows > howmany) rows = howmany;
