@@ -36,7 +36,7 @@ def lib_path(tname):
 
 def _sources():
     return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [
-        os.path.join(HERE, "..", "include", f) for f in sorted(os.listdir(os.path.join(HERE, "..", "include")))]
+        os.path.join(HERE, "..", "include", f) for f in sorted(os.listdir(os.path.join(HERE, "..", "include"))) if f.endswith(".h")]
 
 
 def _stale(target, sources=None):
