@@ -160,7 +160,7 @@ class ClockSampler:
 _CPU_INPUT = {}
 
 
-def cpu_reference(w, reps=5, budget_rows=None):
+def cpu_reference(w, reps=5, budget_rows=None, detail=False):
     """times the reference's own CPU implementation (oracle/_ref when compiled here, else the oracle port) on a
     bounded sample of the workload with all host threads (batch-parallel harness; cfgs are read-only, reference
     README.md:217).  Returns (gflops, info dict)."""
@@ -207,6 +207,23 @@ def cpu_reference(w, reps=5, budget_rows=None):
                 t = time.perf_counter() - t0
         sample = "%d of %d transforms, %s" % (rows, w["batch"], "forward+inverse" if w["kind"] == "real" else "forward")
         gf = flops_per_step(sub) / t / 1e9
+        other = {}
+        if have_ref and detail:
+            # (A) the reference's OpenMP build as shipped (a <= p-way split per transform,
+            # kiss_fft.c:253-260), (B) the plain build on one thread; `value` is (C), the plain build with the batch
+            # spread over all cores by the harness.  A and B run on a 2048-row prefix.
+            r2 = min(rows, 2048)
+            f2 = flops_per_step(dict(w, batch=r2))
+            for key, lp in (("A_openmp_build_as_shipped", loader.reference_lib_path(tname, openmp=True)),
+                            ("B_plain_build_1_thread", loader.reference_lib_path(tname))):
+                if not os.path.exists(lp):
+                    continue
+                if w["kind"] == "c2c":
+                    tt = drv.run(lp, loader.K_FFT, [n], 0, x, out, r2, n * 2 * s, n * 2 * s, 1, 2)
+                else:
+                    tt = drv.run(lp, loader.K_FFTR, [n], 0, x, X, r2, n * s, (n // 2 + 1) * 2 * s, 1, 2)
+                    tt += drv.run(lp, loader.K_FFTRI, [n], 1, X, y, r2, (n // 2 + 1) * 2 * s, n * s, 1, 2)
+                other[key] = round(f2 / tt / 1e9, 3)
     else:
         dims = w["dims"]
         sdims = tuple(min(d, 128) for d in dims)       # the CPU needs minutes beyond 256^3; bounded sample
@@ -223,6 +240,8 @@ def cpu_reference(w, reps=5, budget_rows=None):
         gf = flops_per_step(dict(w, dims=sdims)) / t / 1e9
     info = {"value": gf, "unit": "GFLOP/s", "cores": threads, "kind": "reference" if have_ref else "port", "sample": sample,
             "seconds": t, "host_cores": cores}
+    if w["kind"] in ("real", "c2c") and other:
+        info["other_modes_gflops"] = other
     return gf, info
 
 
@@ -403,7 +422,7 @@ def run_ours(args, w, rank, world, local_rank):
             line["e2e"] = None
         if world == 1:
             try:
-                _, info = cpu_reference(w)
+                _, info = cpu_reference(w, detail=True)
                 line["cpu_baseline"] = info
             except Exception as exc:   # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"error": str(exc)}
