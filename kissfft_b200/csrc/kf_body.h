@@ -301,8 +301,9 @@ struct FusedLayout {
     static constexpr bool kRing = D.nstage > 0 && MODE != kC2CCol;
     static constexpr int kRowIn = (MODE == kC2R) ? D.N + 1 : D.N;   // complex elements per input row
     static_assert(D.nbuf == 2 || (D.nbuf == 1 && D.G == 2 && (MODE == kC2C || MODE == kC2CCol)) ||
-                      (D.nbuf == 1 && D.G == 3 && D.nstage == 1 && D.paired && (MODE == kR2C || MODE == kC2R)),
-                  "single exchange buffer: two-group C2C/column plans, or three-group paired real plans with a one-stage input ring");
+                      (D.nbuf == 1 && D.G == 3 && D.nstage == 1 && D.paired && (MODE == kR2C || MODE == kC2R)) ||
+                      (D.nbuf == 1 && D.G >= 3 && D.nstage == 1 && MODE == kC2C),
+                  "single exchange buffer: two-group C2C/column plans, or (one-stage input ring) C2C plans with three or more groups / three-group paired real plans");
     // kiss_fftr post pass by warp shuffles instead of a T[] round trip through shared memory: needs whole warps per
     // team and the last group's work items to divide evenly (PlanDesc::shfl_post asks for it)
     static constexpr bool kShflPost = MODE == kR2C && D.shfl_post && D.team % 32 == 0 && D.items(D.G - 1) % D.team == 0;
@@ -310,11 +311,12 @@ struct FusedLayout {
     static constexpr bool kPairedLast = MODE == kR2C && D.paired && D.G >= 2 && D.R(D.G - 1) % 2 == 0 && D.items(D.G - 1) % 2 == 0;
     // kiss_fftri with the split pre pass + first group run on work-item pairs: every spectrum bin is read once
     static constexpr bool kPairedFirst = MODE == kC2R && D.paired && D.G >= 2 && D.R(0) % 2 == 0 && D.items(0) % 2 == 0;
-    // nbuf == 1 on a three-group paired real plan: ONE exchange buffer, and the input stage (consumed by the first
-    // group) doubles as the second one.  Shared memory per transform in flight drops from 3 rows to 2, so more CTAs
+    // nbuf == 1 on a plan with three or more groups (C2C, or paired real with three): ONE exchange buffer, and the
+    // input stage (consumed by the first group) doubles as the second one.  Shared memory per transform in flight drops from 3 rows to 2, so more CTAs
     // are resident; the stage is refilled once the last group has read it (no refill under the butterflies).
-    static constexpr bool kStageExch = D.nbuf == 1 && kRing && D.nstage == 1 && D.G == 3 &&
-                                       ((kPairedLast && D.items(2) / 2 <= D.team) || kPairedFirst);
+    static constexpr bool kStageExch = D.nbuf == 1 && kRing && D.nstage == 1 &&
+                                       ((D.G == 3 && ((kPairedLast && D.items(2) / 2 <= D.team) || kPairedFirst)) ||
+                                        (D.G >= 3 && MODE == kC2C));
     static constexpr size_t kExchBytes = (D.G >= 2 || (MODE == kR2C && !kShflPost)) ? (size_t)D.nbuf * D.tpc * D.pitch() * sizeof(typename A::C) : 0;
     static constexpr size_t kRingOff = (kExchBytes + 127) / 128 * 128;
     // rows whose byte size is not a multiple of 16 (kiss_fftri: ncfft+1 elements): a tile then starts off the 16-byte
@@ -328,6 +330,26 @@ struct FusedLayout {
     static constexpr size_t kBarOff = kRingOff + (kRing ? D.nstage * kStageBytes : 0);
     static constexpr size_t kTotal = kRing ? kBarOff + 8 * (size_t)D.nstage : kExchBytes;
 };
+
+// Groups 1.. of a plan whose input stage doubles as the second exchange buffer (FusedLayout::kStageExch): group g reads
+// buffer A when g is odd and the stage when g is even, and writes the other one; the last group writes `dst`.  The
+// stage is refilled (`recycle`) right after the barrier that follows its last reader.
+template <class A, PlanDesc D, int g, class Env, class Dst, class Rec>
+KF_HD void run_groups_stage_exch(Env& env, int t, bool active, const Dst& dst, typename A::C* exA, typename A::C* exS,
+                                 const TwTab<A>& tw, const PlanConsts<A>& pc, int inverse, const Rec& recycle)
+{
+    constexpr bool kReadsStage = (g % 2 == 0);
+    constexpr bool kLastStageReader = kReadsStage && (g + 2 > D.G - 1);
+    run_group<A, D, g, NoSrc, Dst>(t, active, NoSrc{}, dst, kReadsStage ? exS : exA, kReadsStage ? exA : exS, tw, pc, inverse);
+    if constexpr (g + 1 < D.G) {
+        env.sync();
+        if constexpr (kLastStageReader) recycle();
+        run_groups_stage_exch<A, D, g + 1, Env, Dst, Rec>(env, t, active, dst, exA, exS, tw, pc, inverse, recycle);
+    } else {
+        env.sync();       // the stage (or buffer A, which the next tile's first group overwrites) has been consumed
+        if constexpr (kLastStageReader) recycle();
+    }
+}
 
 // PT is a tag type carrying the plan as `static constexpr PlanDesc D`.
 // Env abstracts the execution environment (thread/block ids, CTA barrier, dynamic shared memory, bulk async
@@ -534,6 +556,14 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
                 });
             }
             if constexpr (D.G >= 2) par ^= (D.G - 1) & 1;
+        } else if constexpr (MODE == kC2C && LY::kStageExch) {
+            // ---- C2C, three or more groups: stage -> A -> stage -> ... -> global ----
+            C* const exA = bufA + team * kPitch;
+            C* const exS = stage_ptr(stg) + team * kPitch;
+            DstGlobal<A> dstg{P.out + b * P.out_dist};
+            run_group<A, PT::D, 0, SrcShared<A>, DstGlobal<A>>(t, active, SrcShared<A>{srow}, dstg, nullptr, exA, tw, P.pc, P.inverse);
+            env.sync();                                   // every team has consumed its landed row
+            run_groups_stage_exch<A, PT::D, 1>(env, t, active, dstg, exA, exS, tw, P.pc, P.inverse, recycle);
         } else if constexpr (MODE == kC2C || MODE == kR2C || MODE == kC2R) {
             // kR2C: the real row is read as ncfft packed complex (kiss_fftr.c:77); the last group leaves T[] in
             // natural order in the next exchange buffer for the split pass
