@@ -76,3 +76,34 @@ def test_reference_twotone_and_bench(tname):
     for args in (["-n", "1800", "-x", "200"], ["-n", "1024", "-x", "200", "-r"], ["-n", "32,32", "-x", "20"]):
         r = subprocess.run([bench, *args], capture_output=True, timeout=600)
         assert r.returncode == 0, (args, r.stderr.decode()[-400:])
+
+
+@pytest.mark.parametrize("tool", ["fastconv", "fastconvr"])
+def test_reference_fast_fir_tool(tname, tool, tmp_path):
+    """tools/kiss_fastfir.c (overlap-scrap fast FIR filter) built against this repo's library must produce what the same
+    program produces with the compiled reference library (oracle/_ref/refbin): bit-identical in Q15/Q31."""
+    exe = _need(tool, tname)
+    ref = os.path.join(os.path.dirname(os.path.dirname(exe)), "refbin", "%s-%s" % (tool, tname))
+    if not os.path.exists(ref):
+        pytest.skip("%s not built" % ref)
+    cplx = tool == "fastconv"
+    o = Oracle(tname)
+    n, nh = 50000, 65
+    x = random_input(tname, (n,), 11, complex_=cplx)
+    h = random_input(tname, (nh,), 12, complex_=cplx)
+    if tname in ("float", "double"):
+        h = (h * 0.05).astype(o.dtype)
+    else:
+        h = (h // 8).astype(o.dtype)              # keep the Q15/Q31 filter gain below one
+    fin, fh = tmp_path / "in.bin", tmp_path / "h.bin"
+    x.tofile(fin)
+    h.tofile(fh)
+    outs = []
+    for prog in (exe, ref):
+        fo = tmp_path / ("out_%d.bin" % len(outs))
+        r = subprocess.run([prog, "-i", str(fin), "-o", str(fo), "-h", str(fh)], capture_output=True, timeout=600)
+        assert r.returncode == 0, r.stderr.decode()[-500:]
+        outs.append(np.fromfile(fo, o.dtype))
+    got, want = outs
+    assert got.size == want.size == (n - nh + 1) * (2 if cplx else 1)
+    check(tname, got, want)
