@@ -173,6 +173,18 @@ KF_HD void run_groups(Env& env, int t, bool active, const Src& src, const Dst& d
 // memory.  Items 0 and m/2 pair with themselves and are taken together by the thread whose u is 0.
 // Same operands and roundings as the reference's loop over k = 1..nc/2, so fixed point stays bit-exact.
 // ---------------------------------------------------------------------------------------------------------
+// pair index of thread t inside its warp's block of 32 pairs (PlanDesc::pairperm)
+template <PlanDesc D>
+KF_HD int pair_lane(int t)
+{
+    if constexpr (D.pairperm == 1) {
+        static_assert(D.team % 32 == 0, "pairperm permutes the lanes of whole warps");
+        return (t & ~31) | ((t & 15) << 1) | ((t >> 4) & 1);
+    } else {
+        return t;
+    }
+}
+
 template <class A>
 KF_HD void r2c_emit_pair(int ks, int nc, const cx<typename A::R>& Tk, const cx<typename A::R>& Tnk, const typename A::C* stw,
                          typename A::C* out)
@@ -196,7 +208,7 @@ KF_HD void run_r2c_last_paired(int t, bool active, const typename A::C* rd, cons
     constexpr int kIt = (half + D.team - 1) / D.team;                   // u = 0 .. half-1
     const typename A::R sg = A::sign_of(inverse);
     static_for<kIt>([&](auto ITER) {
-        const int u = t + decltype(ITER)::value * D.team;
+        const int u = pair_lane<D>(t) + decltype(ITER)::value * D.team;
         const bool on = active && u < half;
         const int wa = on ? u : 0, wb = (on && u != 0) ? m - u : half;   // items (u, m-u); (0, m/2) for u == 0
         X a[R], b[R];
@@ -257,7 +269,7 @@ KF_HD void run_c2r_first_paired(int t, bool active, const F& f, typename A::C* w
     constexpr int kIt = (half + D.team - 1) / D.team;
     const typename A::R sg = A::sign_of(inverse);
     static_for<kIt>([&](auto ITER) {
-        const int u = t + decltype(ITER)::value * D.team;
+        const int u = pair_lane<D>(t) + decltype(ITER)::value * D.team;
         const bool on = active && u < half;
         const int wa = on ? u : 0, wb = (on && u != 0) ? W - u : half;
         X a[R], b[R];

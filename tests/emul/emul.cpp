@@ -151,6 +151,22 @@ struct Entry {
 #define KF_ROW(tag, modes) KF_FUSED_##modes(tag),
 static const Entry kTable[] = { KF_PLAN_LIST(KF_ROW) };
 
+// ---- experimental plans: variants that are NOT in the product's plan list (candidates for the next tuning round), so
+// that their index math can be validated here before any GPU time is spent on them
+#include "experimental_plans.h"
+static const Entry kExperimental[] = { KF_EXPERIMENTAL_LIST(KF_ROW) { 0, { nullptr, nullptr, nullptr, nullptr } } };
+extern "C" int emul_num_experimental(void) { return (int)(sizeof(kExperimental) / sizeof(kExperimental[0])) - 1; }
+extern "C" int emul_experimental_nfft(int i) { return kExperimental[i].N; }
+extern "C" int emul_experimental_has_mode(int i, int mode) { return kExperimental[i].fn[mode] != nullptr; }
+extern "C" int emul_fused_experimental(int idx, int mode, int inverse, const void* in, void* out, long long howmany, long long in_dist,
+                                       long long out_dist, long long in_stride, const void* tw, const void* stw, long long nblocks)
+{
+    const Entry& e = kExperimental[idx];
+    if (!e.fn[mode]) return -1;
+    KParams<AT> P = mk_params(e.N, inverse, in, out, howmany, in_dist, out_dist, in_stride, tw, stw);
+    return e.fn[mode](P, nblocks);
+}
+
 extern "C" int emul_num_plans(void) { return (int)(sizeof(kTable) / sizeof(kTable[0])); }
 extern "C" int emul_plan_nfft(int i) { return kTable[i].N; }
 // first table entry that serves (N, mode) wins, exactly like find_fused in kf_launch.cu

@@ -17,7 +17,7 @@ def _stale(lib):
         return True
     t = os.path.getmtime(lib)
     csrc = os.path.join(HERE, "..", "kissfft_b200", "csrc")
-    deps = [os.path.join(EMUL, "emul.cpp")] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".h")]
+    deps = [os.path.join(EMUL, "emul.cpp"), os.path.join(EMUL, "experimental_plans.h")] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -47,6 +47,7 @@ class Emulator:
         self.lib = ctypes.CDLL(build(tname))
         vp, ci, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
         self.lib.emul_fused.argtypes = [ci, ci, ci, vp, vp, ll, ll, ll, ll, vp, vp, ll]
+        self.lib.emul_fused_experimental.argtypes = [ci, ci, ci, vp, vp, ll, ll, ll, ll, vp, vp, ll]
         self.lib.emul_generic.argtypes = [ci, ci, ci, vp, ci, vp, vp, ll, ll, ll, ll, vp, vp, ci, ci, ll]
         self.lib.emul_stage.argtypes = [ci, ci, ci, ci, ci, vp, vp, ll, ll, ll, ll, ci, ci, vp, ci, ll]
         self.lib.emul_realpass.argtypes = [ci, ci, vp, vp, ll, ll, ll, vp, ci, ll]
@@ -57,10 +58,20 @@ class Emulator:
         return [(self.lib.emul_plan_nfft(i), [m for m in range(4) if self.lib.emul_plan_has_mode(i, m)])
                 for i in range(self.lib.emul_num_plans())]
 
-    def fused(self, nfft, mode, inverse, inp, out, howmany, in_dist, out_dist, in_stride, tw, stw=None, nblocks=2, factors=None):
+    def experimental(self):
+        """[(index, nfft, modes)] of the test-only plan variants (tests/emul/experimental_plans.h)"""
+        return [(i, self.lib.emul_experimental_nfft(i), [m for m in range(4) if self.lib.emul_experimental_has_mode(i, m)])
+                for i in range(self.lib.emul_num_experimental())]
+
+    def fused(self, nfft, mode, inverse, inp, out, howmany, in_dist, out_dist, in_stride, tw, stw=None, nblocks=2, factors=None,
+              experimental=None):
         """mirrors kf_launch.cu: the fused kernel takes the rows its alignment rules allow, the run-time kernel the rest"""
-        done = self.lib.emul_fused(nfft, mode, int(inverse), _p(inp), _p(out), howmany, in_dist, out_dist, in_stride,
-                                   _p(tw), _p(stw), nblocks)
+        if experimental is not None:
+            done = self.lib.emul_fused_experimental(experimental, mode, int(inverse), _p(inp), _p(out), howmany, in_dist, out_dist,
+                                                    in_stride, _p(tw), _p(stw), nblocks)
+        else:
+            done = self.lib.emul_fused(nfft, mode, int(inverse), _p(inp), _p(out), howmany, in_dist, out_dist, in_stride,
+                                       _p(tw), _p(stw), nblocks)
         assert done >= 0, "no fused plan for nfft=%d mode=%d" % (nfft, mode)
         if done < howmany:
             assert factors is not None, "ragged tail needs the run-time kernel"

@@ -81,6 +81,31 @@ def test_fused_real(env):
         check(tname, y, o.fftri(spec), nfft)
 
 
+def test_experimental_real_plans(env):
+    """plan variants that are not in the product list yet (tests/emul/experimental_plans.h): paired groups with the
+    even/odd lane mapping, with and without the input stage as second exchange buffer"""
+    tname, o, em = env
+    ran = 0
+    for idx, nc, modes in em.experimental():
+        nfft, howmany = 2 * nc, 7
+        if R2C in modes:
+            x = random_input(tname, (howmany, nfft), 900 + idx, complex_=False)
+            X = np.zeros((howmany, nc + 1, 2), x.dtype)
+            em.fused(nc, R2C, 0, x, X, howmany, nc, nc + 1, 1, o.twiddles(nc, 0), o.super_twiddles(nc, 0), factors=o.factor(nc),
+                     experimental=idx)
+            check(tname, X, o.fftr(x), nfft)
+            ran += 1
+        if C2R in modes:
+            spec = o.fftr(random_input(tname, (howmany, nfft), 901 + idx, complex_=False)) if tname in TOL \
+                else random_input(tname, (howmany, nc + 1), 902 + idx)
+            y = np.zeros((howmany, nfft), spec.dtype)
+            em.fused(nc, C2R, 1, spec, y, howmany, nc + 1, nc, 1, o.twiddles(nc, 1), o.super_twiddles(nc, 1), factors=o.factor(nc),
+                     experimental=idx)
+            check(tname, y, o.fftri(spec), nfft)
+            ran += 1
+    assert ran >= 2
+
+
 @pytest.mark.parametrize("nfft", [1, 2, 3, 5, 7, 12, 30, 74, 120, 143, 360])
 def test_generic_c2c(env, nfft):
     tname, o, em = env

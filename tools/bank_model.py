@@ -1,0 +1,148 @@
+#!/usr/bin/env python
+"""Shared-memory wavefront model of a fused plan's exchange traffic (development aid, CPU only).
+
+Re-states PlanDesc's index math (kissfft_b200/csrc/kf_plan.h) and counts, per transform, the shared-memory wavefronts of
+every warp-wide LDS/STS of the exchange buffers for 8-byte elements: a warp access is served as two half-warps, each
+costing max(multiplicity of distinct 8-byte slots per bank pair) wavefronts.  Compared with ncu
+(l1tex__data_pipe_lsu_wavefronts_mem_shared_op_{ld,st}) it reproduces the measured conflict counts, so padding schemes
+can be screened without a GPU.
+
+    python tools/bank_model.py            # the round-1 R2C / C2R 4096-point plans
+"""
+import sys
+from functools import reduce
+
+
+class Plan:
+    def __init__(self, N, p, glen, team, logpad, skew=None):
+        self.N, self.p, self.glen, self.team, self.logpad = N, list(p), list(glen), team, logpad
+        self.L, self.G = len(p), len(glen)
+        self.skew = skew
+
+    def F(self, s):
+        return reduce(lambda a, b: a * b, self.p[:s], 1)
+
+    def m(self, s):
+        return self.N // (self.F(s) * self.p[s])
+
+    def s_hi(self, g):
+        return self.L - 1 - sum(self.glen[:g])
+
+    def s_lo(self, g):
+        return self.s_hi(g) - self.glen[g] + 1
+
+    def R(self, g):
+        return reduce(lambda a, b: a * b, self.p[self.s_lo(g):self.s_hi(g) + 1], 1)
+
+    def Flo(self, g):
+        return self.F(self.s_lo(g))
+
+    def items(self, g):
+        return self.N // self.R(g)
+
+    def W(self, g, s):
+        return reduce(lambda a, b: a * b, self.p[self.s_lo(g):s], 1)
+
+    def digit(self, g, s, e):
+        return (e // self.W(g, s)) % self.p[s]
+
+    def kout(self, g, e):
+        return sum(self.digit(g, j, e) * self.m(j) for j in range(self.s_lo(g), self.s_hi(g) + 1))
+
+    def phys(self, a):
+        if self.skew is not None:
+            return self.skew(a)
+        return a if self.logpad >= 31 else a + (a >> self.logpad)
+
+    # addresses (element units) of work item w of group g
+    def rd(self, g, w):
+        Flo, R = self.Flo(g), self.R(g)
+        off, kp = w % Flo, w // Flo
+        return [self.phys(kp * Flo * R + off + e * Flo) for e in range(R)]
+
+    def wr(self, g, w):
+        Flo, R = self.Flo(g), self.R(g)
+        off, kp = w % Flo, w // Flo
+        return [self.phys((kp + self.kout(g, e)) * Flo + off) for e in range(R)]
+
+
+def wavefronts(addrs):
+    """addrs: 32 element indices (None = inactive lane) of one warp-wide 8-byte access"""
+    total = 0
+    for half in (addrs[:16], addrs[16:]):
+        banks = {}
+        for a in half:
+            if a is not None:
+                banks.setdefault(a % 16, set()).add(a)
+        total += max((len(v) for v in banks.values()), default=0)
+    return total
+
+
+def count(plan, g, kind, item_of_thread):
+    """wavefronts per transform of group g's exchange loads ('rd') or stores ('wr'); item_of_thread(t, it) -> item or None"""
+    R, team = plan.R(g), plan.team
+    its = 0
+    total = 0
+    while True:
+        any_on = False
+        for w0 in range(0, team, 32):
+            lanes = [item_of_thread(t, its) for t in range(w0, w0 + 32)]
+            if all(l is None for l in lanes):
+                continue
+            any_on = True
+            per_lane = [(plan.rd(g, l) if kind == "rd" else plan.wr(g, l)) if l is not None else None for l in lanes]
+            for e in range(R):
+                total += wavefronts([pl[e] if pl is not None else None for pl in per_lane])
+        if not any_on:
+            break
+        its += 1
+    return total
+
+
+def plain(plan, g):
+    n = plan.items(g)
+    return lambda t, it: (t + it * plan.team) if (t + it * plan.team) < n else None
+
+
+def paired(plan, g, second):
+    """items (u, m-u); (0, m/2) for u == 0.  second=False -> item a of the pair, True -> item b"""
+    m = plan.items(g)
+    half = m // 2
+
+    def f(t, it):
+        u = t + it * plan.team
+        if u >= half:
+            return None
+        if not second:
+            return u
+        return half if u == 0 else m - u
+    return f
+
+
+def report(name, plan, mode):
+    G = plan.G
+    ideal = plan.N * 8 // 128
+    print("== %s  N=%d radices=%s groups=%s team=%d logpad=%d" % (name, plan.N, plan.p, plan.glen, plan.team, plan.logpad))
+    tot_ld = tot_st = 0
+    for g in range(G):
+        if g > 0:      # exchange loads
+            if mode == "r2c" and g == G - 1:
+                n = count(plan, g, "rd", paired(plan, g, False)) + count(plan, g, "rd", paired(plan, g, True))
+            else:
+                n = count(plan, g, "rd", plain(plan, g))
+            print("   group %d loads  : %4d wavefronts (ideal %d)" % (g, n, ideal))
+            tot_ld += n
+        if g < G - 1:  # exchange stores
+            if mode == "c2r" and g == 0:
+                n = count(plan, g, "wr", paired(plan, g, False)) + count(plan, g, "wr", paired(plan, g, True))
+            else:
+                n = count(plan, g, "wr", plain(plan, g))
+            print("   group %d stores : %4d wavefronts (ideal %d)" % (g, n, ideal))
+            tot_st += n
+    print("   exchange loads %d, stores %d per transform (input-stage reads not included)" % (tot_ld, tot_st))
+    return tot_ld, tot_st
+
+
+if __name__ == "__main__":
+    report("R2C 4096 (round-1 plan)", Plan(2048, [4, 2, 4, 4, 4, 4], [2, 2, 2], 128, 4), "r2c")
+    report("C2R 4096 (round-1 plan)", Plan(2048, [4, 4, 4, 4, 4, 2], [2, 2, 2], 128, 4), "c2r")
