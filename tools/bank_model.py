@@ -66,14 +66,19 @@ class Plan:
         return [self.phys((kp + self.kout(g, e)) * Flo + off) for e in range(R)]
 
 
+ESIZE = 8     # bytes per complex element: 8 float, 16 double, 4 Q15, 8 Q31
+
+
 def wavefronts(addrs):
-    """addrs: 32 element indices (None = inactive lane) of one warp-wide 8-byte access"""
+    """addrs: 32 element indices (None = inactive lane) of one warp-wide access of ESIZE-byte elements.  The access is
+    served in phases of 128 / ESIZE lanes; a phase costs as many wavefronts as distinct elements share one bank group."""
+    lanes = 128 // ESIZE
     total = 0
-    for half in (addrs[:16], addrs[16:]):
+    for i in range(0, 32, lanes):
         banks = {}
-        for a in half:
+        for a in addrs[i:i + lanes]:
             if a is not None:
-                banks.setdefault(a % 16, set()).add(a)
+                banks.setdefault(a % lanes, set()).add(a)
         total += max((len(v) for v in banks.values()), default=0)
     return total
 
@@ -121,7 +126,7 @@ def paired(plan, g, second):
 
 def report(name, plan, mode):
     G = plan.G
-    ideal = plan.N * 8 // 128
+    ideal = -(-plan.N * ESIZE // 128)
     print("== %s  N=%d radices=%s groups=%s team=%d logpad=%d" % (name, plan.N, plan.p, plan.glen, plan.team, plan.logpad))
     tot_ld = tot_st = 0
     for g in range(G):
@@ -143,6 +148,20 @@ def report(name, plan, mode):
     return tot_ld, tot_st
 
 
+def set_esize(n):
+    global ESIZE
+    ESIZE = n
+
+
 if __name__ == "__main__":
     report("R2C 4096 (round-1 plan)", Plan(2048, [4, 2, 4, 4, 4, 4], [2, 2, 2], 128, 4), "r2c")
     report("C2R 4096 (round-1 plan)", Plan(2048, [4, 4, 4, 4, 4, 2], [2, 2, 2], 128, 4), "c2r")
+    report("C2C f32 1024", Plan(1024, [2, 4, 4, 4, 4, 2], [3, 3], 32, 5), "c2c")
+    report("C2C f32 2048", Plan(2048, [4, 2, 4, 4, 4, 4], [2, 2, 2], 128, 4), "c2c")
+    report("C2C f32 1000", Plan(1000, [5, 5, 5, 4, 2], [3, 2], 40, 5), "c2c")
+    report("C2C f32 1155", Plan(1155, [3, 11, 5, 7], [2, 2], 35, 5), "c2c")
+    set_esize(16)
+    report("C2C f64 1000", Plan(1000, [4, 2, 5, 5, 5], [1, 1, 1, 2], 200, 3), "c2c")
+    report("C2C f64 1155", Plan(1155, [3, 5, 7, 11], [1, 1, 2], 105, 5), "c2c")
+    set_esize(4)
+    report("C2C Q15 2048", Plan(2048, [4, 4, 4, 4, 4, 2], [2, 2, 2], 128, 4), "c2c")
