@@ -104,6 +104,44 @@ def count(plan, g, kind, item_of_thread):
     return total
 
 
+def pitch(plan):
+    n = plan.phys(plan.N - 1) + 1
+    return n + 1 if n % 2 == 0 else n
+
+
+def count_cta(plan, g, kind, tpc):
+    """like count(), but over a whole CTA of tpc teams (tid = team * plan.team + t): warps may straddle two transforms when
+    the team size is not a multiple of 32.  Returns wavefronts per transform (a float)."""
+    R, T, n = plan.R(g), plan.team, plan.items(g)
+    P = pitch(plan)
+    nthreads = T * tpc
+    iters = -(-n // T)
+    total = 0
+    for it in range(iters):
+        for w0 in range(0, nthreads, 32):
+            lanes = []
+            for tid in range(w0, min(w0 + 32, nthreads)):
+                team, t = divmod(tid, T)
+                w = t + it * T
+                lanes.append((team, w) if w < n else None)
+            lanes += [None] * (32 - len(lanes))
+            if all(l is None for l in lanes):
+                continue
+            per = [None if l is None else [l[0] * P + a for a in (plan.rd(g, l[1]) if kind == "rd" else plan.wr(g, l[1]))] for l in lanes]
+            for e in range(R):
+                total += wavefronts([pl[e] if pl is not None else None for pl in per])
+    return total / tpc
+
+
+def report_cta(name, plan, tpc):
+    ideal = plan.N * ESIZE / 128
+    ld = sum(count_cta(plan, g, "rd", tpc) for g in range(1, plan.G))
+    st = sum(count_cta(plan, g, "wr", tpc) for g in range(plan.G - 1))
+    print("%-34s radices=%s groups=%s team=%d tpc=%d logpad=%d: loads %.0f stores %.0f (ideal %.0f each per exchange, %d exchanges)" % (
+        name, plan.p, plan.glen, plan.team, tpc, plan.logpad, ld, st, ideal, plan.G - 1))
+    return ld + st
+
+
 def plain(plan, g):
     n = plan.items(g)
     return lambda t, it: (t + it * plan.team) if (t + it * plan.team) < n else None
@@ -165,3 +203,10 @@ if __name__ == "__main__":
     report("C2C f64 1155", Plan(1155, [3, 5, 7, 11], [1, 1, 2], 105, 5), "c2c")
     set_esize(4)
     report("C2C Q15 2048", Plan(2048, [4, 4, 4, 4, 4, 2], [2, 2, 2], 128, 4), "c2c")
+    print("-- whole-CTA counts (team sizes that are not a multiple of 32)")
+    set_esize(8)
+    report_cta("C2C f32 1000", Plan(1000, [5, 5, 5, 4, 2], [3, 2], 40, 5), 3)
+    report_cta("C2C f32 1155", Plan(1155, [3, 11, 5, 7], [2, 2], 35, 5), 3)
+    set_esize(16)
+    report_cta("C2C f64 1000", Plan(1000, [4, 2, 5, 5, 5], [1, 1, 1, 2], 200, 3), 1)
+    report_cta("C2C f64 1155", Plan(1155, [3, 5, 7, 11], [1, 1, 2], 105, 5), 1)
