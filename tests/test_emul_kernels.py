@@ -88,6 +88,13 @@ def test_experimental_real_plans(env):
     ran = 0
     for idx, nc, modes in em.experimental():
         nfft, howmany = 2 * nc, 7
+        if C2C in modes:
+            for inverse in (0, 1):
+                x = random_input(tname, (howmany, nc), 903 + idx)
+                out = np.zeros_like(x)
+                em.fused(nc, C2C, inverse, x, out, howmany, nc, nc, 1, o.twiddles(nc, inverse), factors=o.factor(nc), experimental=idx)
+                check(tname, out, o.fft(x, inverse), nc)
+                ran += 1
         if R2C in modes:
             x = random_input(tname, (howmany, nfft), 900 + idx, complex_=False)
             X = np.zeros((howmany, nc + 1, 2), x.dtype)
