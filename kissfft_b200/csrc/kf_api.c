@@ -523,12 +523,61 @@ static int kf_exec_multipass(int mode, const kf_devplan *dp, const void *d_in, v
     return rc;
 }
 
+#ifndef FIXED_POINT
+/* Four-step path for long contiguous rows (float / double): N = N1*N2 with a fused column plan for both factors.
+ *   x[n1*N2 + n2]  --columns of length N1, times W_N^(n2*k1)-->  A[n2*N1 + k1]  --columns of length N2-->  X[k2*N1 + k1]
+ * Two launches and four passes over the data instead of the 2*L of the stage-per-launch path.  A different
+ * factorisation than kf_work's, so the result matches the reference to rounding only (hence not for fixed point).
+ * Opt-in for now (KISSFFT_FOURSTEP=1): validated in the kernel emulator, not yet timed on the GPU. */
+static int kf_fourstep_split(int nfft, int *n1, int *n2)
+{
+    int best = 0;
+    for (int a = 2; (long long)a * a <= (long long)nfft; ++a) {
+        if (nfft % a) continue;
+        const int b = nfft / a;
+        if (kfcu_has_fourstep(a) && kfcu_has_fourstep(b)) best = a;     /* the largest a <= sqrt(nfft): most balanced split */
+    }
+    if (!best) return 0;
+    *n1 = best;
+    *n2 = nfft / best;
+    return 1;
+}
+
+static int kf_exec_fourstep(const kf_devplan *dp, int n1, int n2, const void *d_in, void *d_out, long long howmany, void *stream)
+{
+    const int N = dp->plan.nfft, inverse = dp->plan.inverse;
+    kiss_fft_cfg c1 = kiss_fft_alloc(n1, inverse, NULL, NULL), c2 = kiss_fft_alloc(n2, inverse, NULL, NULL);
+    const kf_devplan *p1 = NULL, *p2 = NULL;
+    int rc = (c1 && c2) ? 0 : KISS_FFT_CUDA_ENOMEM;
+    if (!rc) rc = kf_get_devplan(c1, NULL, &p1);
+    if (!rc) rc = kf_get_devplan(c2, NULL, &p2);
+    free(c1);
+    free(c2);
+    if (rc) return rc;
+    pthread_mutex_lock(&g_mp_lock);
+    void *work = NULL;
+    rc = kf_scratch(8, sizeof(kiss_fft_cpx) * (size_t)N * (size_t)howmany, &work);
+    if (!rc) rc = kfcu_exec_fourstep((kfcu_plan *)&p1->plan, 0, d_in, work, howmany, n2, dp->plan.d_tw, stream);
+    if (!rc) rc = kfcu_exec_fourstep((kfcu_plan *)&p2->plan, 1, work, d_out, howmany, n1, NULL, stream);
+    if (!rc) rc = (int)cudaStreamSynchronize((cudaStream_t)stream);      /* the work buffer is shared */
+    pthread_mutex_unlock(&g_mp_lock);
+    return rc;
+}
+#endif
+
 static int kf_exec(int mode, const kf_devplan *dp, const void *d_in, void *d_out, long long howmany, long long in_dist,
                    long long out_dist, long long in_stride, void *stream)
 {
     int rc = kfcu_exec(mode, (kfcu_plan *)&dp->plan, d_in, d_out, howmany, in_dist, out_dist, in_stride, stream);
-    if (rc == KFCU_ETOOBIG) rc = kf_exec_multipass(mode, dp, d_in, d_out, howmany, in_dist, out_dist, in_stride, stream);
-    return rc;
+    if (rc != KFCU_ETOOBIG) return rc;
+#ifndef FIXED_POINT
+    const char *opt = getenv("KISSFFT_FOURSTEP");
+    int n1 = 0, n2 = 0;
+    if (opt && opt[0] == '1' && mode == KFCU_C2C && in_stride == 1 && in_dist == dp->plan.nfft && out_dist == dp->plan.nfft &&
+        kf_fourstep_split(dp->plan.nfft, &n1, &n2))
+        return kf_exec_fourstep(dp, n1, n2, d_in, d_out, howmany, stream);
+#endif
+    return kf_exec_multipass(mode, dp, d_in, d_out, howmany, in_dist, out_dist, in_stride, stream);
 }
 
 /* ---- device-pointer batched entry points ---------------------------------------------------------------- */

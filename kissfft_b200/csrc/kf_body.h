@@ -11,6 +11,8 @@
 //   kC2C      kiss_fft / kiss_fft_stride with unit or small input stride             (kiss_fft.c:375-404)
 //   kC2CCol   kiss_fftnd axis pass: `tpc` adjacent columns are loaded together so that HBM reads are
 //             tpc*sizeof(cpx)-byte segments, each column is written as a contiguous row (kiss_fftnd.c:172-178)
+//   kC2CColTw / kC2CColCol   the two steps of the four-step transform of a long row N = N1*N2 (float / double): columns
+//             in, rows out multiplied by W_N^(column * k); columns in, columns out (natural order)
 //   kR2C      kiss_fftr: packed complex transform + split-twiddle post pass fused     (kiss_fftr.c:63-117)
 //   kC2R      kiss_fftri: split pre pass fused + inverse complex transform            (kiss_fftr.c:119-155)
 #pragma once
@@ -20,7 +22,8 @@
 
 namespace kf {
 
-enum Mode { kC2C = 0, kC2CCol = 1, kR2C = 2, kC2R = 3 };
+enum Mode { kC2C = 0, kC2CCol = 1, kR2C = 2, kC2R = 3, kC2CColTw = 4, kC2CColCol = 5 };
+constexpr bool is_col_mode(int m) { return m == kC2CCol || m == kC2CColTw || m == kC2CColCol; }
 
 template <class A>
 struct KParams {
@@ -133,6 +136,26 @@ struct DstGlobal {
     typename A::C* base;
     template <int IT_, int E_>
     KF_HD void put(int k, const cx<typename A::R>& v) const { base[k] = A::store(v); }
+};
+// four-step, first step: row `col` of the intermediate array, multiplied by the long transform's twiddle W_N^(col*k)
+template <class A>
+struct DstGlobalTw {
+    typename A::C* base;
+    const typename A::C* twbig;
+    long long col;
+    template <int IT_, int E_>
+    KF_HD void put(int k, const cx<typename A::R>& v) const
+    {
+        base[k] = A::store(A::cmul(v, A::load(TwTab<A>::ro_load_c(twbig + col * k))));
+    }
+};
+// four-step, second step: element k of a column goes `stride` elements down (adjacent lanes hold adjacent columns)
+template <class A>
+struct DstGlobalStrided {
+    typename A::C* base;
+    long long stride;
+    template <int IT_, int E_>
+    KF_HD void put(int k, const cx<typename A::R>& v) const { base[k * stride] = A::store(v); }
 };
 template <class A>
 struct DstShared {
@@ -310,9 +333,9 @@ KF_HD void run_c2r_first_paired(int t, bool active, const F& f, typename A::C* w
 template <class A, class PT, int MODE>
 struct FusedLayout {
     static constexpr PlanDesc D = PT::D;
-    static constexpr bool kRing = D.nstage > 0 && MODE != kC2CCol;
+    static constexpr bool kRing = D.nstage > 0 && !is_col_mode(MODE);
     static constexpr int kRowIn = (MODE == kC2R) ? D.N + 1 : D.N;   // complex elements per input row
-    static_assert(D.nbuf == 2 || (D.nbuf == 1 && D.G == 2 && (MODE == kC2C || MODE == kC2CCol)) ||
+    static_assert(D.nbuf == 2 || (D.nbuf == 1 && D.G == 2 && (MODE == kC2C || is_col_mode(MODE))) ||
                       (D.nbuf == 1 && D.G == 3 && D.nstage == 1 && D.paired && (MODE == kR2C || MODE == kC2R)) ||
                       (D.nbuf == 1 && D.G >= 3 && D.nstage == 1 && MODE == kC2C),
                   "single exchange buffer: two-group C2C/column plans, or (one-stage input ring) C2C plans with three or more groups / three-group paired real plans");
@@ -635,6 +658,32 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             run_group<A, D, 0, SrcGlobal<A, false>, DstGlobal<A>>(ct, cb < P.howmany, src, dst, nullptr, cb1, tw, P.pc, P.inverse);
             env.sync();
             run_groups<A, D, 1>(env, t, active, src, dst, b1, b0, tw, P.pc, P.inverse);
+            par ^= (D.G - 1) & 1;
+        }
+        else if constexpr (MODE == kC2CColTw || MODE == kC2CColCol) {
+            // ---- four-step transform of a long row (float / double), see kf_api.c:kf_exec_fourstep ----
+            static_assert(D.G >= 2 && !A::kFixed, "four-step modes: float / double plans with a shared-memory exchange");
+            const int cteam = tid % D.tpc, ct = tid / D.tpc;
+            const long long cb = tile * D.tpc + cteam;
+            const bool con = cb < P.howmany;
+            constexpr int gl = PT::D.G - 1;
+            SrcGlobal<A, false> src{P.in + P.in_off(cb), P.in_stride};
+            DstGlobal<A> unused{nullptr};
+            C* cb1 = (par ? bufA : bufB) + cteam * kPitch;
+            C* cb0 = (par ? bufB : bufA) + cteam * kPitch;
+            run_group<A, D, 0, SrcGlobal<A, false>, DstGlobal<A>>(ct, con, src, unused, nullptr, cb1, tw, P.pc, P.inverse);
+            env.sync();
+            run_groups<A, D, 1, SrcGlobal<A, false>, DstGlobal<A>, Env, gl>(env, t, active, src, unused, b1, b0, tw, P.pc, P.inverse);
+            if constexpr (MODE == kC2CColTw) {
+                // standard mapping: the team writes its transform as a contiguous row, times W_N^(column * k)
+                const long long col = P.ncols > 0 ? b % P.ncols : b;
+                DstGlobalTw<A> dst{P.out_ptr(b), P.stw, col};
+                run_group<A, D, gl, SrcGlobal<A, false>, DstGlobalTw<A>>(t, active, src, dst, (gl & 1) ? b1 : b0, nullptr, tw, P.pc, P.inverse);
+            } else {
+                // transposed mapping again: adjacent lanes store adjacent columns, element k lands k * in_stride below
+                DstGlobalStrided<A> dst{P.out + P.out_off(cb), P.in_stride};
+                run_group<A, D, gl, SrcGlobal<A, false>, DstGlobalStrided<A>>(ct, con, src, dst, (gl & 1) ? cb1 : cb0, nullptr, tw, P.pc, P.inverse);
+            }
             par ^= (D.G - 1) & 1;
         }
         // single exchange buffer: the next tile's first group overwrites what the last group just read

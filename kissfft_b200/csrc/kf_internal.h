@@ -41,6 +41,16 @@ int kfcu_exec(int mode, kfcu_plan *plan, const void *d_in, void *d_out, long lon
 int kfcu_exec_planes(kfcu_plan *plan, const void *d_in, void *d_out, long long nplanes, long long ncols, long long col_stride,
                      long long in_pdist, long long out_pdist, void *stream);
 
+/* Four-step transform of nrows rows of length N = nfft*ncols (float / double), one pass per call:
+ *   step 0: plan of length N1 = nfft, ncols = N2: column n2 of a row viewed as [N1][N2] -> out[row*N + n2*N1 + k1] * W_N^(n2*k1)
+ *           (d_twbig: the N twiddles of the long transform);
+ *   step 1: plan of length N2 = nfft, ncols = N1: column k1 of the intermediate array viewed as [N2][N1] ->
+ *           out[row*N + k2*N1 + k1], natural order.
+ * kfcu_has_fourstep(nfft): both passes are available for this length. */
+int kfcu_exec_fourstep(kfcu_plan *plan, int step, const void *d_in, void *d_out, long long nrows, long long ncols,
+                       const void *d_twbig, void *stream);
+int kfcu_has_fourstep(int nfft);
+
 /* kfcu_exec_planes with the ncols = npeers*cols_per_peer columns of every plane scattered to npeers destination
  * buffers: column block s is written through peers[s] (+ p*out_pdist + c_local*nfft) */
 int kfcu_exec_planes_peers(kfcu_plan *plan, const void *d_in, void *const *peers, int npeers, long long nplanes,

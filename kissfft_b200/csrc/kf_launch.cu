@@ -94,19 +94,20 @@ static int launch_fused(kfcu_plan* pl, KParams<AT>& P, cudaStream_t st)
 {
     constexpr PlanDesc D = PT::D;
     // stage-twiddle tables of this plan: built once per (device plan) from the host twiddles, then cached
-    if (D.gtw_total() > 0 && !pl->d_gtw[MODE]) {
+    constexpr int kSlot = (MODE == kC2CColTw || MODE == kC2CColCol) ? (int)kC2CCol : MODE;   // same plan tag as the column mode
+    if (D.gtw_total() > 0 && !pl->d_gtw[kSlot]) {
         std::lock_guard<std::mutex> lk(g_gtw_mutex);
-        if (!pl->d_gtw[MODE]) {
+        if (!pl->d_gtw[kSlot]) {
             std::vector<CT> tab = build_gtw<AT, PT>((const CT*)pl->h_tw);
             void* d = nullptr;
             cudaError_t e = cudaMalloc(&d, tab.size() * sizeof(CT));
             if (e != cudaSuccess) return (int)e;
             e = cudaMemcpy(d, tab.data(), tab.size() * sizeof(CT), cudaMemcpyHostToDevice);
             if (e != cudaSuccess) { cudaFree(d); return (int)e; }
-            pl->d_gtw[MODE] = d;
+            pl->d_gtw[kSlot] = d;
         }
     }
-    P.gtw = (const CT*)pl->d_gtw[MODE];
+    P.gtw = (const CT*)pl->d_gtw[kSlot];
     fill_g0tw<AT, PT>(P, (const CT*)pl->h_tw);
     // rows the fused kernel may take (alignment rules of the bulk-async ring); the remainder, normally none,
     // goes to the run-time kernel
@@ -144,17 +145,23 @@ static int launch_fused(kfcu_plan* pl, KParams<AT>& P, cudaStream_t st)
 
 struct FusedEntry {
     int N;
-    fused_launch_fn fn[4];   // indexed by Mode; null = not instantiated
+    fused_launch_fn fn[6];   // indexed by Mode; null = not instantiated
 };
 
-#define KF_FUSED_ALL(PT) { PT::D.N, { launch_fused<PT, kC2C>, launch_fused<PT, kC2CCol>, launch_fused<PT, kR2C>, launch_fused<PT, kC2R> } }
-#define KF_FUSED_C2C(PT) { PT::D.N, { launch_fused<PT, kC2C>, nullptr, nullptr, nullptr } }
-#define KF_FUSED_C2C_REAL(PT) { PT::D.N, { launch_fused<PT, kC2C>, nullptr, launch_fused<PT, kR2C>, launch_fused<PT, kC2R> } }
-#define KF_FUSED_C2C_COL(PT) { PT::D.N, { launch_fused<PT, kC2C>, launch_fused<PT, kC2CCol>, nullptr, nullptr } }
-#define KF_FUSED_COL(PT) { PT::D.N, { nullptr, launch_fused<PT, kC2CCol>, nullptr, nullptr } }
-#define KF_FUSED_R2C(PT) { PT::D.N, { nullptr, nullptr, launch_fused<PT, kR2C>, nullptr } }
-#define KF_FUSED_C2R(PT) { PT::D.N, { nullptr, nullptr, nullptr, launch_fused<PT, kC2R> } }
-#define KF_FUSED_REAL(PT) { PT::D.N, { nullptr, nullptr, launch_fused<PT, kR2C>, launch_fused<PT, kC2R> } }
+// the two four-step modes ride on every plan that serves the column mode (float / double only)
+#if defined(FIXED_POINT)
+#define KF_4STEP(PT) nullptr, nullptr
+#else
+#define KF_4STEP(PT) launch_fused<PT, kC2CColTw>, launch_fused<PT, kC2CColCol>
+#endif
+#define KF_FUSED_ALL(PT) { PT::D.N, { launch_fused<PT, kC2C>, launch_fused<PT, kC2CCol>, launch_fused<PT, kR2C>, launch_fused<PT, kC2R>, KF_4STEP(PT) } }
+#define KF_FUSED_C2C(PT) { PT::D.N, { launch_fused<PT, kC2C>, nullptr, nullptr, nullptr, nullptr, nullptr } }
+#define KF_FUSED_C2C_REAL(PT) { PT::D.N, { launch_fused<PT, kC2C>, nullptr, launch_fused<PT, kR2C>, launch_fused<PT, kC2R>, nullptr, nullptr } }
+#define KF_FUSED_C2C_COL(PT) { PT::D.N, { launch_fused<PT, kC2C>, launch_fused<PT, kC2CCol>, nullptr, nullptr, KF_4STEP(PT) } }
+#define KF_FUSED_COL(PT) { PT::D.N, { nullptr, launch_fused<PT, kC2CCol>, nullptr, nullptr, KF_4STEP(PT) } }
+#define KF_FUSED_R2C(PT) { PT::D.N, { nullptr, nullptr, launch_fused<PT, kR2C>, nullptr, nullptr, nullptr } }
+#define KF_FUSED_C2R(PT) { PT::D.N, { nullptr, nullptr, nullptr, launch_fused<PT, kC2R>, nullptr, nullptr } }
+#define KF_FUSED_REAL(PT) { PT::D.N, { nullptr, nullptr, launch_fused<PT, kR2C>, launch_fused<PT, kC2R>, nullptr, nullptr } }
 
 #include "kf_plans.inc"
 
@@ -234,6 +241,35 @@ extern "C" int kfcu_exec_planes(kfcu_plan* plan, const void* d_in, void* d_out, 
     P.out_pdist = out_pdist;
     if (const FusedEntry* fe = find_fused(plan->nfft, kC2CCol)) return fe->fn[kC2CCol](plan, P, (cudaStream_t)stream);
     return launch_generic(kC2CCol, plan, P, (cudaStream_t)stream);
+}
+
+// the two passes of the four-step transform of rows of length N = N1 * N2 (float / double; kf_api.c:kf_exec_fourstep).
+//   step 0 (kC2CColTw): plan of length N1; plane = one row viewed as [N1][N2]; column n2 -> out[p*N + n2*N1 + k1] * W_N^(n2*k1)
+//   step 1 (kC2CColCol): plan of length N2; plane = the intermediate array viewed as [N2][N1]; column k1 -> out[p*N + k2*N1 + k1]
+// d_twbig: the N twiddles of the long transform (step 0 only).  Returns KFCU_EINVAL when no fused column plan serves nfft.
+extern "C" int kfcu_exec_fourstep(kfcu_plan* plan, int step, const void* d_in, void* d_out, long long nrows, long long ncols,
+                                  const void* d_twbig, void* stream)
+{
+    if (!plan || !d_in || !d_out || nrows < 0 || ncols < 1 || step < 0 || step > 1) return KFCU_EINVAL;
+    if (nrows == 0) return 0;
+    const int mode = step == 0 ? (int)kC2CColTw : (int)kC2CColCol;
+    const FusedEntry* fe = find_fused(plan->nfft, mode);
+    if (!fe) return KFCU_EINVAL;
+    const long long N = (long long)plan->nfft * ncols;
+    KParams<AT> P = make_params(plan, d_in, d_out, nrows * ncols, 1, step == 0 ? plan->nfft : 1, ncols);
+    P.ncols = ncols;
+    P.in_pdist = N;
+    P.out_pdist = N;
+    if (step == 0) {
+        if (!d_twbig) return KFCU_EINVAL;
+        P.stw = (const CT*)d_twbig;
+    }
+    return fe->fn[mode](plan, P, (cudaStream_t)stream);
+}
+
+extern "C" int kfcu_has_fourstep(int nfft)
+{
+    return find_fused(nfft, kC2CColTw) != nullptr && find_fused(nfft, kC2CColCol) != nullptr;
 }
 
 // the same pass with the columns of every plane split into npeers blocks; block s goes through peers[s]

@@ -138,23 +138,28 @@ static int run_fused(KParams<AT>& P, long long nblocks)
 typedef int (*fused_fn)(KParams<AT>&, long long);
 struct Entry {
     int N;
-    fused_fn fn[4];
+    fused_fn fn[6];
 };
-#define KF_FUSED_ALL(PT) { PT::D.N, { run_fused<PT, kC2C>, run_fused<PT, kC2CCol>, run_fused<PT, kR2C>, run_fused<PT, kC2R> } }
-#define KF_FUSED_C2C(PT) { PT::D.N, { run_fused<PT, kC2C>, nullptr, nullptr, nullptr } }
-#define KF_FUSED_C2C_REAL(PT) { PT::D.N, { run_fused<PT, kC2C>, nullptr, run_fused<PT, kR2C>, run_fused<PT, kC2R> } }
-#define KF_FUSED_C2C_COL(PT) { PT::D.N, { run_fused<PT, kC2C>, run_fused<PT, kC2CCol>, nullptr, nullptr } }
-#define KF_FUSED_COL(PT) { PT::D.N, { nullptr, run_fused<PT, kC2CCol>, nullptr, nullptr } }
-#define KF_FUSED_R2C(PT) { PT::D.N, { nullptr, nullptr, run_fused<PT, kR2C>, nullptr } }
-#define KF_FUSED_C2R(PT) { PT::D.N, { nullptr, nullptr, nullptr, run_fused<PT, kC2R> } }
-#define KF_FUSED_REAL(PT) { PT::D.N, { nullptr, nullptr, run_fused<PT, kR2C>, run_fused<PT, kC2R> } }
+#if defined(FIXED_POINT)
+#define KF_4STEP(PT) nullptr, nullptr
+#else
+#define KF_4STEP(PT) run_fused<PT, kC2CColTw>, run_fused<PT, kC2CColCol>
+#endif
+#define KF_FUSED_ALL(PT) { PT::D.N, { run_fused<PT, kC2C>, run_fused<PT, kC2CCol>, run_fused<PT, kR2C>, run_fused<PT, kC2R>, KF_4STEP(PT) } }
+#define KF_FUSED_C2C(PT) { PT::D.N, { run_fused<PT, kC2C>, nullptr, nullptr, nullptr, nullptr, nullptr } }
+#define KF_FUSED_C2C_REAL(PT) { PT::D.N, { run_fused<PT, kC2C>, nullptr, run_fused<PT, kR2C>, run_fused<PT, kC2R>, nullptr, nullptr } }
+#define KF_FUSED_C2C_COL(PT) { PT::D.N, { run_fused<PT, kC2C>, run_fused<PT, kC2CCol>, nullptr, nullptr, KF_4STEP(PT) } }
+#define KF_FUSED_COL(PT) { PT::D.N, { nullptr, run_fused<PT, kC2CCol>, nullptr, nullptr, KF_4STEP(PT) } }
+#define KF_FUSED_R2C(PT) { PT::D.N, { nullptr, nullptr, run_fused<PT, kR2C>, nullptr, nullptr, nullptr } }
+#define KF_FUSED_C2R(PT) { PT::D.N, { nullptr, nullptr, nullptr, run_fused<PT, kC2R>, nullptr, nullptr } }
+#define KF_FUSED_REAL(PT) { PT::D.N, { nullptr, nullptr, run_fused<PT, kR2C>, run_fused<PT, kC2R>, nullptr, nullptr } }
 #define KF_ROW(tag, modes) KF_FUSED_##modes(tag),
 static const Entry kTable[] = { KF_PLAN_LIST(KF_ROW) };
 
 // ---- experimental plans: variants that are NOT in the product's plan list (candidates for the next tuning round), so
 // that their index math can be validated here before any GPU time is spent on them
 #include "experimental_plans.h"
-static const Entry kExperimental[] = { KF_EXPERIMENTAL_LIST(KF_ROW) { 0, { nullptr, nullptr, nullptr, nullptr } } };
+static const Entry kExperimental[] = { KF_EXPERIMENTAL_LIST(KF_ROW) { 0, { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr } } };
 extern "C" int emul_num_experimental(void) { return (int)(sizeof(kExperimental) / sizeof(kExperimental[0])) - 1; }
 extern "C" int emul_experimental_nfft(int i) { return kExperimental[i].N; }
 extern "C" int emul_experimental_has_mode(int i, int mode) { return kExperimental[i].fn[mode] != nullptr; }
@@ -186,6 +191,23 @@ extern "C" int emul_fused(int nfft, int mode, int inverse, const void* in, void*
     for (const Entry& e : kTable)
         if (e.N == nfft && e.fn[mode]) {
             KParams<AT> P = mk_params(nfft, inverse, in, out, howmany, in_dist, out_dist, in_stride, tw, stw);
+            return e.fn[mode](P, nblocks);
+        }
+    return -1;
+}
+
+// one pass of the four-step transform, parameters exactly as kf_launch.cu:kfcu_exec_fourstep builds them
+extern "C" int emul_fourstep(int nfft, int step, int inverse, const void* in, void* out, long long nrows, long long ncols,
+                             const void* tw, const void* twbig, long long nblocks)
+{
+    const int mode = step == 0 ? (int)kC2CColTw : (int)kC2CColCol;
+    for (const Entry& e : kTable)
+        if (e.N == nfft && e.fn[mode]) {
+            const long long N = (long long)nfft * ncols;
+            KParams<AT> P = mk_params(nfft, inverse, in, out, nrows * ncols, 1, step == 0 ? nfft : 1, ncols, tw, step == 0 ? twbig : nullptr);
+            P.ncols = ncols;
+            P.in_pdist = N;
+            P.out_pdist = N;
             return e.fn[mode](P, nblocks);
         }
     return -1;

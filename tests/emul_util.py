@@ -47,6 +47,7 @@ class Emulator:
         self.lib = ctypes.CDLL(build(tname))
         vp, ci, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
         self.lib.emul_fused.argtypes = [ci, ci, ci, vp, vp, ll, ll, ll, ll, vp, vp, ll]
+        self.lib.emul_fourstep.argtypes = [ci, ci, ci, vp, vp, ll, ll, vp, vp, ll]
         self.lib.emul_fused_experimental.argtypes = [ci, ci, ci, vp, vp, ll, ll, ll, ll, vp, vp, ll]
         self.lib.emul_generic.argtypes = [ci, ci, ci, vp, ci, vp, vp, ll, ll, ll, ll, vp, vp, ci, ci, ll]
         self.lib.emul_stage.argtypes = [ci, ci, ci, ci, ci, vp, vp, ll, ll, ll, ll, ci, ci, vp, ci, ll]
@@ -83,6 +84,15 @@ class Emulator:
                                        in_dist, out_dist, in_stride, _p(tw), _p(stw), 2, 32, 1)
             assert rc == 0
         return done
+
+    def fourstep(self, n1, n2, inverse, inp, out, nrows, tw1, tw2, twbig, nblocks=3):
+        """rows of length n1*n2 by the two four-step passes (mirrors kf_api.c:kf_exec_fourstep); False when the plans are missing"""
+        work = np.zeros_like(inp)
+        a = self.lib.emul_fourstep(n1, 0, int(inverse), _p(inp), _p(work), nrows, n2, _p(tw1), _p(twbig), nblocks)
+        if a < 0:
+            return False
+        b = self.lib.emul_fourstep(n2, 1, int(inverse), _p(work), _p(out), nrows, n1, _p(tw2), None, nblocks)
+        return b >= 0
 
     def generic(self, nfft, mode, inverse, factors, inp, out, howmany, in_dist, out_dist, in_stride, tw, stw=None,
                 tpc=2, nthreads=32, nblocks=2):

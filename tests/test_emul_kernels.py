@@ -81,6 +81,22 @@ def test_fused_real(env):
         check(tname, y, o.fftri(spec), nfft)
 
 
+@pytest.mark.parametrize("n1,n2", [(128, 128), (256, 128)])
+def test_fourstep_long_rows(env, n1, n2):
+    """N = n1*n2 as two fused column passes (float / double): columns of length n1 times W_N^(n2 k1), then columns of
+    length n2 written in natural order"""
+    tname, o, em = env
+    if tname not in TOL:
+        pytest.skip("the four-step path is float / double only (a different factorisation is not bit-exact)")
+    N, rows = n1 * n2, 2
+    for inverse in (0, 1):
+        x = random_input(tname, (rows, N), 77 + inverse)
+        out = np.zeros_like(x)
+        ok = em.fourstep(n1, n2, inverse, x, out, rows, o.twiddles(n1, inverse), o.twiddles(n2, inverse), o.twiddles(N, inverse))
+        assert ok, "no fused column plan for %d or %d" % (n1, n2)
+        check(tname, out, o.fft(x, inverse), N)
+
+
 def test_experimental_real_plans(env):
     """plan variants that are not in the product list yet (tests/emul/experimental_plans.h): paired groups with the
     even/odd lane mapping, with and without the input stage as second exchange buffer"""

@@ -4,6 +4,7 @@
 Bars (BASELINE.json north_star): Q15/Q31 bit-exact; float relative RMS <= 1e-6*log2(N); double <= 1e-14*log2(N).
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -527,3 +528,28 @@ def test_fused_fast_convolution(tname, nfft, nimp):
     full = np.convolve(xc, hc)[nimp - 1: nimp - 1 + done]
     assert rel_rms(got[:done], np.stack([full.real, full.imag], -1)) <= 20 * TOL[tname] * np.log2(n)
     lib.fastconv_free(cfg)
+
+
+@pytest.mark.skipif(os.environ.get("KISSFFT_TEST_EXPERIMENTAL") != "1",
+                    reason="opt-in four-step path: emulator-validated, to be enabled once it has run on a GPU (KISSFFT_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("tname", ["float", "double"])
+@pytest.mark.parametrize("nfft", [16384, 65536, 1 << 20])
+def test_fourstep_long_rows_opt_in(tname, nfft, monkeypatch):
+    """KISSFFT_FOURSTEP=1: long contiguous rows as two fused column passes instead of one launch per radix stage"""
+    import torch
+    import kissfft_b200
+    from oracle.loader import Oracle, random_input, rel_rms
+    monkeypatch.setenv("KISSFFT_FOURSTEP", "1")
+    lib, o = kissfft_b200.get(tname), Oracle(tname)
+    rows = 3
+    x = random_input(tname, (rows, nfft), 4242)
+    for inverse in (False, True):
+        cfg = lib.alloc(nfft, inverse)
+        d_in = torch.from_numpy(x).cuda()
+        d_out = torch.empty_like(d_in)
+        before = lib.launch_count()
+        lib.fft_batch_dev(cfg, d_in, d_out, rows, nfft, nfft, 1, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert lib.launch_count() - before == 2
+        tol = (1e-6 if tname == "float" else 1e-14) * np.log2(nfft)
+        assert rel_rms(d_out.cpu().numpy(), o.fft(x, inverse)) <= tol
