@@ -723,12 +723,44 @@ static int kf_fftnd_dev_locked(kiss_fftnd_cfg st, const kiss_fft_cpx *d_in, kiss
     return 0;
 }
 
+/* In-layout variant (opt-in, KISSFFT_FFTND_INLAYOUT=1): every axis is transformed where it lies -- strided columns in,
+ * the same strided columns out -- instead of kiss_fftnd.c's transposing sweeps, and the last axis is a plain row pass.
+ * Axes still run in the reference's order 0,1,... on the same operands, so the results (fixed point included) are the
+ * same bits; no work buffer is needed.  Emulator-validated, not yet timed on the GPU. */
+static int kf_fftnd_inlayout_ok(kiss_fftnd_cfg st)
+{
+    const char *opt = getenv("KISSFFT_FFTND_INLAYOUT");
+    if (!opt || opt[0] != '1' || st->ndims < 2) return 0;
+    for (int k = 0; k + 1 < st->ndims; ++k)
+        if (!kfcu_has_colcol(st->dims[k])) return 0;
+    return 1;
+}
+
+static int kf_fftnd_dev_inlayout(kiss_fftnd_cfg st, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, void *stream)
+{
+    long long nplanes = 1, below = st->dimprod;
+    for (int k = 0; k < st->ndims; ++k) {
+        const int n = st->dims[k];
+        below /= n;                                   /* elements per index step of axis k */
+        const kiss_fft_cpx *src = (k == 0) ? d_in : d_out;
+        const kf_devplan *dp;
+        KF_CHECK(kf_get_devplan(st->states[k], NULL, &dp));
+        if (below == 1)
+            KF_CHECK(kf_exec(KFCU_C2C, dp, src, d_out, nplanes, n, n, 1, stream));
+        else
+            KF_CHECK(kfcu_exec_fourstep((kfcu_plan *)&dp->plan, 1, src, d_out, nplanes, below, NULL, stream));
+        nplanes *= n;
+    }
+    return 0;
+}
+
 int kiss_fftnd_dev(kiss_fftnd_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, kiss_fft_cpx *d_work, void *stream)
 {
     if (!cfg || cfg->magic != KF_MAGIC_ND || !d_in || !d_out) {
         KF_ERROR("kiss_fftnd_dev: bad argument");
         return KISS_FFT_CUDA_EINVAL;
     }
+    if (kf_fftnd_inlayout_ok(cfg)) return kf_fftnd_dev_inlayout(cfg, d_in, d_out, stream);
     if (d_work) return kf_fftnd_dev_locked(cfg, d_in, d_out, d_work, stream);
     /* internal scratch: serialise users of the shared slot and wait for completion before releasing it */
     pthread_mutex_lock(&g_stage_lock);

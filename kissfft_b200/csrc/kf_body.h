@@ -12,7 +12,8 @@
 //   kC2CCol   kiss_fftnd axis pass: `tpc` adjacent columns are loaded together so that HBM reads are
 //             tpc*sizeof(cpx)-byte segments, each column is written as a contiguous row (kiss_fftnd.c:172-178)
 //   kC2CColTw / kC2CColCol   the two steps of the four-step transform of a long row N = N1*N2 (float / double): columns
-//             in, rows out multiplied by W_N^(column * k); columns in, columns out (natural order)
+//             in, rows out multiplied by W_N^(column * k); columns in, columns out (natural order).  kC2CColCol alone is
+//             also an axis pass of an N-D array that leaves the layout unchanged (every datatype)
 //   kR2C      kiss_fftr: packed complex transform + split-twiddle post pass fused     (kiss_fftr.c:63-117)
 //   kC2R      kiss_fftri: split pre pass fused + inverse complex transform            (kiss_fftr.c:119-155)
 #pragma once
@@ -662,7 +663,7 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
         }
         else if constexpr (MODE == kC2CColTw || MODE == kC2CColCol) {
             // ---- four-step transform of a long row (float / double), see kf_api.c:kf_exec_fourstep ----
-            static_assert(D.G >= 2 && !A::kFixed, "four-step modes: float / double plans with a shared-memory exchange");
+            static_assert(D.G >= 2 && (MODE == kC2CColCol || !A::kFixed), "column modes need a shared-memory exchange; the twiddled pass is float / double only");
             const int cteam = tid % D.tpc, ct = tid / D.tpc;
             const long long cb = tile * D.tpc + cteam;
             const bool con = cb < P.howmany;

@@ -50,6 +50,7 @@ int kfcu_exec_planes(kfcu_plan *plan, const void *d_in, void *d_out, long long n
 int kfcu_exec_fourstep(kfcu_plan *plan, int step, const void *d_in, void *d_out, long long nrows, long long ncols,
                        const void *d_twbig, void *stream);
 int kfcu_has_fourstep(int nfft);
+int kfcu_has_colcol(int nfft);   /* step 1 alone (every datatype): an axis pass that keeps the array layout */
 
 /* kfcu_exec_planes with the ncols = npeers*cols_per_peer columns of every plane scattered to npeers destination
  * buffers: column block s is written through peers[s] (+ p*out_pdist + c_local*nfft) */

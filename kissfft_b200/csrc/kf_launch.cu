@@ -150,7 +150,7 @@ struct FusedEntry {
 
 // the two four-step modes ride on every plan that serves the column mode (float / double only)
 #if defined(FIXED_POINT)
-#define KF_4STEP(PT) nullptr, nullptr
+#define KF_4STEP(PT) nullptr, launch_fused<PT, kC2CColCol>
 #else
 #define KF_4STEP(PT) launch_fused<PT, kC2CColTw>, launch_fused<PT, kC2CColCol>
 #endif
@@ -266,6 +266,8 @@ extern "C" int kfcu_exec_fourstep(kfcu_plan* plan, int step, const void* d_in, v
     }
     return fe->fn[mode](plan, P, (cudaStream_t)stream);
 }
+
+extern "C" int kfcu_has_colcol(int nfft) { return find_fused(nfft, kC2CColCol) != nullptr; }
 
 extern "C" int kfcu_has_fourstep(int nfft)
 {

@@ -141,7 +141,7 @@ struct Entry {
     fused_fn fn[6];
 };
 #if defined(FIXED_POINT)
-#define KF_4STEP(PT) nullptr, nullptr
+#define KF_4STEP(PT) nullptr, run_fused<PT, kC2CColCol>
 #else
 #define KF_4STEP(PT) run_fused<PT, kC2CColTw>, run_fused<PT, kC2CColCol>
 #endif

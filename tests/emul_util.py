@@ -94,6 +94,10 @@ class Emulator:
         b = self.lib.emul_fourstep(n2, 1, int(inverse), _p(work), _p(out), nrows, n1, _p(tw2), None, nblocks)
         return b >= 0
 
+    def colcol(self, nfft, inverse, inp, out, nplanes, ncols, tw, nblocks=3):
+        """axis pass that keeps the layout: plane p, column c: inp[p][j][c] (j < nfft) -> out[p][k][c]; False without a plan"""
+        return self.lib.emul_fourstep(nfft, 1, int(inverse), _p(inp), _p(out), nplanes, ncols, _p(tw), None, nblocks) >= 0
+
     def generic(self, nfft, mode, inverse, factors, inp, out, howmany, in_dist, out_dist, in_stride, tw, stw=None,
                 tpc=2, nthreads=32, nblocks=2):
         fac = np.array([x for pm in factors for x in pm], np.int32)

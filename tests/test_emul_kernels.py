@@ -97,6 +97,21 @@ def test_fourstep_long_rows(env, n1, n2):
         check(tname, out, o.fft(x, inverse), N)
 
 
+def test_fftnd_in_layout(env):
+    """kiss_fftnd with every axis transformed where it lies (kf_api.c:kf_fftnd_dev_inlayout): axes 0 and 1 by the
+    column-in / column-out pass, the last axis as rows; same bits as the reference's transposing sweeps in fixed point"""
+    tname, o, em = env
+    dims = (64, 128, 4)
+    x = random_input(tname, dims, 31)
+    a = np.zeros_like(x)
+    assert em.colcol(64, 0, x, a, 1, 128 * 4, o.twiddles(64, 0))                 # axis 0: one plane of 512 columns
+    b = np.zeros_like(x)
+    assert em.colcol(128, 0, a, b, 64, 4, o.twiddles(128, 0))                    # axis 1: 64 planes of 4 columns (ragged tile)
+    c = np.zeros_like(x)
+    em.generic(4, C2C, 0, o.factor(4), b.reshape(-1, 4, 2), c.reshape(-1, 4, 2), 64 * 128, 4, 4, 1, o.twiddles(4, 0))   # axis 2: rows
+    check(tname, c, o.fftnd(x), 64 * 128 * 4)
+
+
 def test_experimental_real_plans(env):
     """plan variants that are not in the product list yet (tests/emul/experimental_plans.h): paired groups with the
     even/odd lane mapping, with and without the input stage as second exchange buffer"""

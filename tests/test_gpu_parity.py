@@ -553,3 +553,32 @@ def test_fourstep_long_rows_opt_in(tname, nfft, monkeypatch):
         assert lib.launch_count() - before == 2
         tol = (1e-6 if tname == "float" else 1e-14) * np.log2(nfft)
         assert rel_rms(d_out.cpu().numpy(), o.fft(x, inverse)) <= tol
+
+
+@pytest.mark.skipif(os.environ.get("KISSFFT_TEST_EXPERIMENTAL") != "1",
+                    reason="opt-in in-layout kiss_fftnd: emulator-validated, to be enabled once it has run on a GPU (KISSFFT_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("tname", ["float", "double", "int16_t", "int32_t"])
+@pytest.mark.parametrize("dims", [(64, 128, 256), (128, 64), (256, 256, 30)])
+def test_fftnd_in_layout_opt_in(tname, dims, monkeypatch):
+    """KISSFFT_FFTND_INLAYOUT=1: every axis transformed where it lies; same bits as the transposing sweeps in fixed point"""
+    import torch
+    import kissfft_b200
+    from oracle.loader import Oracle, random_input, rel_rms
+    monkeypatch.setenv("KISSFFT_FFTND_INLAYOUT", "1")
+    lib, o = kissfft_b200.get(tname), Oracle(tname)
+    x = random_input(tname, dims, 99)
+    cfg = lib.allocnd(list(dims), False)
+    d_in = torch.from_numpy(x).cuda()
+    d_out = torch.empty_like(d_in)
+    lib.fftnd_dev(cfg, d_in, d_out, None, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    want = o.fftnd(x)
+    if tname in ("float", "double"):
+        n = float(np.prod(dims))
+        assert rel_rms(d_out.cpu().numpy(), want) <= (1e-6 if tname == "float" else 1e-14) * np.log2(n)
+    else:
+        assert np.array_equal(d_out.cpu().numpy(), want)
+    # in place
+    lib.fftnd_dev(cfg, d_in, d_in, None, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(d_in, d_out)
