@@ -49,6 +49,8 @@ struct PlanDesc {
     int paired;             // real transforms on work-item pairs.  kiss_fftr plan: the last group runs items k' and m-k' in the
                             // same thread, so every bin pair (k, nc-k) of the split post pass is complete in its registers;
                             // kiss_fftri plan: the first group runs items u and W-u, reading every spectrum pair once
+    int maxblocks;          // 0: as many CTAs per SM as fit.  n > 0: at most n, with the shared-memory carve-out sized for n
+                            // CTAs so that the rest of the SM's 256 KB stays L1 (the twiddle tables live there); host side only
     int pairperm;           // paired groups: which pairs the lanes of a warp take.  0: lane l takes pair l of the warp's block of 32;
                             // 1: lanes 0-15 take the even pairs, lanes 16-31 the odd ones (keeps the mirrored item's
                             // shared-memory accesses conflict-free when its group has 8 points, tools/bank_model.py)
