@@ -22,6 +22,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include "../../include/kfc.h"
 #include "../../include/kiss_fft_cuda.h"
@@ -324,14 +325,31 @@ typedef struct kf_devplan {
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 static kf_devplan *g_plans = NULL;
 
-/* scratch pool (per process, used under g_stage_lock by the host-pointer entry points) */
-static pthread_mutex_t g_stage_lock = PTHREAD_MUTEX_INITIALIZER;
-static pthread_mutex_t g_mp_lock = PTHREAD_MUTEX_INITIALIZER; /* work buffers of the multi-pass path (slots 8-10) */
+/* ---- staging contexts --------------------------------------------------------------------------------------
+ * Everything a host-pointer call needs on the device side lives in a staging context: a stream, grow-only device
+ * scratch slots and grow-only pinned bounce buffers.  A call takes an idle context of the current device from the pool
+ * (creating one when all are busy) and gives it back when its result is in the caller's buffer, so concurrent calls on
+ * different threads run concurrently -- the reference's kiss_fft is thread-parallel on a shared cfg
+ * (reference README.md:217) -- and the pool lock is held only for the hand-over.  kiss_fft_cleanup() frees the idle
+ * contexts; it must not run concurrently with transforms (it also frees the device tables they use).
+ *
+ * Lock order (never nested otherwise): g_mp_lock -> g_pool_lock -> g_lock. */
+typedef struct kf_ctx {
+    int device, busy;
+    cudaStream_t stream;
+    void *d_buf[3];                 /* device scratch: input, output, work */
+    size_t d_bytes[3];
+    void *h_pin[2];                 /* pinned bounce buffers: input, output */
+    size_t h_bytes[2];
+    struct kf_ctx *next;
+} kf_ctx;
+
+static pthread_mutex_t g_pool_lock = PTHREAD_MUTEX_INITIALIZER;
+static kf_ctx *g_pool = NULL;
+static pthread_mutex_t g_mp_lock = PTHREAD_MUTEX_INITIALIZER; /* work buffers of the long-row paths (kf_mp_scratch) */
 typedef struct { void *ptr; size_t bytes; int device; } kf_buf;
-#define KF_NSLOTS 11
-static kf_buf g_dev_bufs[KF_NSLOTS];
-static cudaStream_t g_streams[4];
-static int g_streams_dev = -1;
+#define KF_MP_SLOTS 3
+static kf_buf g_mp_bufs[KF_MP_SLOTS];
 
 static int kf_get_devplan(const struct kiss_fft_state *cfg, const kiss_fft_cpx *stw, const kf_devplan **out)
 {
@@ -387,12 +405,23 @@ static int kf_get_devplan(const struct kiss_fft_state *cfg, const kiss_fft_cpx *
     return 0;
 }
 
+static void kf_ctx_destroy(kf_ctx *c)
+{
+    cudaSetDevice(c->device);
+    for (int i = 0; i < 3; ++i)
+        if (c->d_buf[i]) cudaFree(c->d_buf[i]);
+    for (int i = 0; i < 2; ++i)
+        if (c->h_pin[i]) cudaFreeHost(c->h_pin[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    free(c);
+}
+
 void kiss_fft_cleanup(void)
 {
     int cur = 0;
     cudaGetDevice(&cur);
     pthread_mutex_lock(&g_mp_lock);
-    pthread_mutex_lock(&g_stage_lock);
+    pthread_mutex_lock(&g_pool_lock);
     pthread_mutex_lock(&g_lock);
     for (kf_devplan *e = g_plans; e;) {
         kf_devplan *n = e->next;
@@ -406,31 +435,37 @@ void kiss_fft_cleanup(void)
         e = n;
     }
     g_plans = NULL;
-    for (int i = 0; i < KF_NSLOTS; ++i) {
-        if (g_dev_bufs[i].ptr) {
-            cudaSetDevice(g_dev_bufs[i].device);
-            cudaFree(g_dev_bufs[i].ptr);
+    for (int i = 0; i < KF_MP_SLOTS; ++i) {
+        if (g_mp_bufs[i].ptr) {
+            cudaSetDevice(g_mp_bufs[i].device);
+            cudaFree(g_mp_bufs[i].ptr);
         }
-        g_dev_bufs[i].ptr = NULL;
-        g_dev_bufs[i].bytes = 0;
+        g_mp_bufs[i].ptr = NULL;
+        g_mp_bufs[i].bytes = 0;
     }
-    if (g_streams_dev >= 0) {
-        cudaSetDevice(g_streams_dev);
-        for (int i = 0; i < 4; ++i) cudaStreamDestroy(g_streams[i]);
-        g_streams_dev = -1;
+    /* idle staging contexts go; a busy one belongs to a call that is still running (documented misuse) and is left */
+    kf_ctx **pp = &g_pool;
+    while (*pp) {
+        kf_ctx *c = *pp;
+        if (c->busy) {
+            pp = &c->next;
+        } else {
+            *pp = c->next;
+            kf_ctx_destroy(c);
+        }
     }
     cudaSetDevice(cur);
     pthread_mutex_unlock(&g_lock);
-    pthread_mutex_unlock(&g_stage_lock);
+    pthread_mutex_unlock(&g_pool_lock);
     pthread_mutex_unlock(&g_mp_lock);
 }
 
-/* scratch slot `i`, at least `bytes` large, on the current device (caller holds g_stage_lock) */
-static int kf_scratch(int i, size_t bytes, void **out)
+/* work-buffer slot `i` of the long-row paths, at least `bytes` large, on the current device (caller holds g_mp_lock) */
+static int kf_mp_scratch(int i, size_t bytes, void **out)
 {
     int dev = 0;
     KF_CHECK(cudaGetDevice(&dev));
-    kf_buf *b = &g_dev_bufs[i];
+    kf_buf *b = &g_mp_bufs[i];
     if (b->ptr && (b->bytes < bytes || b->device != dev)) {
         cudaSetDevice(b->device);
         cudaFree(b->ptr);
@@ -447,21 +482,85 @@ static int kf_scratch(int i, size_t bytes, void **out)
     return 0;
 }
 
-static int kf_get_streams(void)
+static int kf_ctx_acquire(kf_ctx **out)
 {
     int dev = 0;
     KF_CHECK(cudaGetDevice(&dev));
-    if (g_streams_dev != dev) {
-        if (g_streams_dev >= 0) {
-            cudaSetDevice(g_streams_dev);
-            for (int i = 0; i < 4; ++i) cudaStreamDestroy(g_streams[i]);
-            cudaSetDevice(dev);
-            g_streams_dev = -1;
+    pthread_mutex_lock(&g_pool_lock);
+    kf_ctx *c;
+    for (c = g_pool; c; c = c->next)
+        if (!c->busy && c->device == dev) break;
+    if (c) c->busy = 1;
+    pthread_mutex_unlock(&g_pool_lock);
+    if (!c) {
+        c = (kf_ctx *)calloc(1, sizeof(*c));
+        if (!c) return KISS_FFT_CUDA_ENOMEM;
+        c->device = dev;
+        c->busy = 1;
+        int rc = (int)cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (rc) {
+            free(c);
+            return kf_cuda_fail(__FILE__, __LINE__, "cudaStreamCreate", rc);
         }
-        for (int i = 0; i < 4; ++i) KF_CHECK(cudaStreamCreateWithFlags(&g_streams[i], cudaStreamNonBlocking));
-        g_streams_dev = dev;
+        pthread_mutex_lock(&g_pool_lock);
+        c->next = g_pool;
+        g_pool = c;
+        pthread_mutex_unlock(&g_pool_lock);
     }
+    *out = c;
     return 0;
+}
+
+static void kf_ctx_release(kf_ctx *c)
+{
+    if (!c) return;
+    pthread_mutex_lock(&g_pool_lock);
+    c->busy = 0;
+    pthread_mutex_unlock(&g_pool_lock);
+}
+
+/* device scratch slot / pinned bounce buffer of a context, grown on demand (the context is owned by the caller) */
+static int kf_ctx_dev(kf_ctx *c, int slot, size_t bytes, void **out)
+{
+    if (c->d_bytes[slot] < bytes || !c->d_buf[slot]) {
+        if (c->d_buf[slot]) {
+            KF_CHECK(cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_buf[slot]);
+            c->d_buf[slot] = NULL;
+            c->d_bytes[slot] = 0;
+        }
+        KF_CHECK(cudaMalloc(&c->d_buf[slot], bytes ? bytes : 1));
+        c->d_bytes[slot] = bytes;
+    }
+    *out = c->d_buf[slot];
+    return 0;
+}
+
+static int kf_ctx_pin(kf_ctx *c, int slot, size_t bytes, void **out)
+{
+    if (c->h_bytes[slot] < bytes || !c->h_pin[slot]) {
+        if (c->h_pin[slot]) {
+            KF_CHECK(cudaStreamSynchronize(c->stream));
+            cudaFreeHost(c->h_pin[slot]);
+            c->h_pin[slot] = NULL;
+            c->h_bytes[slot] = 0;
+        }
+        KF_CHECK(cudaHostAlloc(&c->h_pin[slot], bytes ? bytes : 1, cudaHostAllocDefault));
+        c->h_bytes[slot] = bytes;
+    }
+    *out = c->h_pin[slot];
+    return 0;
+}
+
+/* 0: pageable host memory (the driver would stage it synchronously), 1: pinned / registered host memory */
+static int kf_is_pinned_host(const void *p)
+{
+    struct cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return a.type == cudaMemoryTypeHost;
 }
 
 static int kf_is_device_ptr(const void *p)
@@ -475,8 +574,8 @@ static int kf_is_device_ptr(const void *p)
 }
 
 /* ---- execution: shared-memory kernels, or the multi-pass path for lengths that do not fit them --------------- */
-/* One radix stage per launch, ping-ponging between two dense work buffers (slots 8, 9); the real modes add a work
- * buffer for the packed-complex array (slot 10) and a stand-alone split pass.  The work buffers are shared, so the
+/* One radix stage per launch, ping-ponging between two dense work buffers (slots 0, 1); the real modes add a work
+ * buffer for the packed-complex array (slot 2) and a stand-alone split pass.  The work buffers are shared, so the
  * call holds g_mp_lock and waits for the stream before releasing it. */
 static int kf_exec_multipass(int mode, const kf_devplan *dp, const void *d_in, void *d_out, long long howmany, long long in_dist,
                              long long out_dist, long long in_stride, void *stream)
@@ -486,9 +585,9 @@ static int kf_exec_multipass(int mode, const kf_devplan *dp, const void *d_in, v
     const size_t dense = sizeof(kiss_fft_cpx) * (size_t)N * (size_t)howmany;
     pthread_mutex_lock(&g_mp_lock);
     void *w0 = NULL, *w1 = NULL, *wt = NULL;
-    int rc = kf_scratch(8, dense, &w0);
-    if (!rc) rc = kf_scratch(9, dense, &w1);
-    if (!rc && (mode == KFCU_R2C || mode == KFCU_C2R)) rc = kf_scratch(10, dense, &wt);
+    int rc = kf_mp_scratch(0, dense, &w0);
+    if (!rc) rc = kf_mp_scratch(1, dense, &w1);
+    if (!rc && (mode == KFCU_R2C || mode == KFCU_C2R)) rc = kf_mp_scratch(2, dense, &wt);
     const void *src = d_in;
     void *dst_final = d_out;
     long long sdist = in_dist, sstride = in_stride, ddist = out_dist;
@@ -528,7 +627,8 @@ static int kf_exec_multipass(int mode, const kf_devplan *dp, const void *d_in, v
  *   x[n1*N2 + n2]  --columns of length N1, times W_N^(n2*k1)-->  A[n2*N1 + k1]  --columns of length N2-->  X[k2*N1 + k1]
  * Two launches and four passes over the data instead of the 2*L of the stage-per-launch path.  A different
  * factorisation than kf_work's, so the result matches the reference to rounding only (hence not for fixed point).
- * Opt-in for now (KISSFFT_FOURSTEP=1): validated in the kernel emulator, not yet timed on the GPU. */
+ * Default for long float/double rows since round 2 (2.5-3x the stage-per-launch path on B200,
+ * profiles/r02/long_rows_*_{fourstep,multipass}.jsonl); KISSFFT_FOURSTEP=0 selects the stage-per-launch path. */
 static int kf_fourstep_split(int nfft, int *n1, int *n2)
 {
     int best = 0;
@@ -543,7 +643,8 @@ static int kf_fourstep_split(int nfft, int *n1, int *n2)
     return 1;
 }
 
-static int kf_exec_fourstep(const kf_devplan *dp, int n1, int n2, const void *d_in, void *d_out, long long howmany, void *stream)
+static int kf_exec_fourstep(int mode, const kf_devplan *dp, int n1, int n2, const void *d_in, void *d_out, long long howmany,
+                            long long in_dist, long long out_dist, void *stream)
 {
     const int N = dp->plan.nfft, inverse = dp->plan.inverse;
     kiss_fft_cfg c1 = kiss_fft_alloc(n1, inverse, NULL, NULL), c2 = kiss_fft_alloc(n2, inverse, NULL, NULL);
@@ -554,12 +655,24 @@ static int kf_exec_fourstep(const kf_devplan *dp, int n1, int n2, const void *d_
     free(c1);
     free(c2);
     if (rc) return rc;
+    const size_t dense = sizeof(kiss_fft_cpx) * (size_t)N * (size_t)howmany;
     pthread_mutex_lock(&g_mp_lock);
-    void *work = NULL;
-    rc = kf_scratch(8, sizeof(kiss_fft_cpx) * (size_t)N * (size_t)howmany, &work);
-    if (!rc) rc = kfcu_exec_fourstep((kfcu_plan *)&p1->plan, 0, d_in, work, howmany, n2, dp->plan.d_tw, stream);
-    if (!rc) rc = kfcu_exec_fourstep((kfcu_plan *)&p2->plan, 1, work, d_out, howmany, n1, NULL, stream);
-    if (!rc) rc = (int)cudaStreamSynchronize((cudaStream_t)stream);      /* the work buffer is shared */
+    void *work = NULL, *wt = NULL;
+    rc = kf_mp_scratch(0, dense, &work);
+    /* real transforms of a long row: the packed complex transform runs four-step on a dense array T[] (slot 2) and the
+     * split pass (kiss_fftr.c:88-116 / :131-153) is a stand-alone kernel before / after it */
+    if (!rc && mode != KFCU_C2C) rc = kf_mp_scratch(2, dense, &wt);
+    const void *src = d_in;
+    void *dst = d_out;
+    if (!rc && mode == KFCU_C2R) {
+        rc = kfcu_realpass(&dp->plan, 0, d_in, wt, howmany, in_dist, N, stream);
+        src = wt;
+    }
+    if (mode == KFCU_R2C) dst = wt;
+    if (!rc) rc = kfcu_exec_fourstep((kfcu_plan *)&p1->plan, 0, src, work, howmany, n2, dp->plan.d_tw, stream);
+    if (!rc) rc = kfcu_exec_fourstep((kfcu_plan *)&p2->plan, 1, work, dst, howmany, n1, NULL, stream);
+    if (!rc && mode == KFCU_R2C) rc = kfcu_realpass(&dp->plan, 1, wt, d_out, howmany, N, out_dist, stream);
+    if (!rc) rc = (int)cudaStreamSynchronize((cudaStream_t)stream);      /* the work buffers are shared */
     pthread_mutex_unlock(&g_mp_lock);
     return rc;
 }
@@ -573,9 +686,14 @@ static int kf_exec(int mode, const kf_devplan *dp, const void *d_in, void *d_out
 #ifndef FIXED_POINT
     const char *opt = getenv("KISSFFT_FOURSTEP");
     int n1 = 0, n2 = 0;
-    if (opt && opt[0] == '1' && mode == KFCU_C2C && in_stride == 1 && in_dist == dp->plan.nfft && out_dist == dp->plan.nfft &&
-        kf_fourstep_split(dp->plan.nfft, &n1, &n2))
-        return kf_exec_fourstep(dp, n1, n2, d_in, d_out, howmany, stream);
+    const int N = dp->plan.nfft;
+    /* complex rows must be dense (the passes view each row as an N1 x N2 array); real rows may be any distance apart
+     * because their split pass reads / writes them and the complex transform runs on the dense T[] */
+    const int dense_ok = mode == KFCU_C2C ? (in_stride == 1 && in_dist == N && out_dist == N)
+                                          : (mode == KFCU_R2C ? in_dist == N : out_dist == N);
+    if (!(opt && opt[0] == '0') && (mode == KFCU_C2C || mode == KFCU_R2C || mode == KFCU_C2R) && dense_ok &&
+        kf_fourstep_split(N, &n1, &n2))
+        return kf_exec_fourstep(mode, dp, n1, n2, d_in, d_out, howmany, in_dist, out_dist, stream);
 #endif
     return kf_exec_multipass(mode, dp, d_in, d_out, howmany, in_dist, out_dist, in_stride, stream);
 }
@@ -723,23 +841,37 @@ static int kf_fftnd_dev_locked(kiss_fftnd_cfg st, const kiss_fft_cpx *d_in, kiss
     return 0;
 }
 
-/* In-layout variant (opt-in, KISSFFT_FFTND_INLAYOUT=1): every axis is transformed where it lies -- strided columns in,
- * the same strided columns out -- instead of kiss_fftnd.c's transposing sweeps, and the last axis is a plain row pass.
- * Axes still run in the reference's order 0,1,... on the same operands, so the results (fixed point included) are the
- * same bits; no work buffer is needed.  Emulator-validated, not yet timed on the GPU. */
-static int kf_fftnd_inlayout_ok(kiss_fftnd_cfg st)
+/* In-layout variant (default whenever every leading axis has a fused column plan; KISSFFT_FFTND_INLAYOUT=0 selects the
+ * transposing sweeps): every axis is transformed where it lies -- strided columns in, the same strided columns out --
+ * instead of kiss_fftnd.c's transposing sweeps, and the last axis is a plain row pass.  Axes still run in the
+ * reference's order 0,1,... on the same operands, so the results (fixed point included) are the same bits; no work
+ * buffer is needed (the reference's tmpbuf is 8 GiB at 1024^3, kiss_fftnd.c:38). */
+static int kf_inlayout_enabled(void)
 {
     const char *opt = getenv("KISSFFT_FFTND_INLAYOUT");
-    if (!opt || opt[0] != '1' || st->ndims < 2) return 0;
-    for (int k = 0; k + 1 < st->ndims; ++k)
-        if (!kfcu_has_colcol(st->dims[k])) return 0;
+    return !(opt && opt[0] == '0');
+}
+
+/* can the leading `naxes` axes of `st` be transformed where they lie, with `inner` contiguous elements below the last
+ * of them (inner == 1: the last axis is a plain row pass)? */
+static int kf_axes_inlayout_ok(kiss_fftnd_cfg st, int naxes, long long inner)
+{
+    if (!kf_inlayout_enabled()) return 0;
+    for (int k = 0; k < naxes; ++k) {
+        const int is_rows = (k == naxes - 1 && inner == 1);
+        if (!is_rows && !kfcu_has_colcol(st->dims[k])) return 0;
+    }
     return 1;
 }
 
-static int kf_fftnd_dev_inlayout(kiss_fftnd_cfg st, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, void *stream)
+/* axes 0..naxes-1 of the array [dims[0]]..[dims[naxes-1]][inner], in the reference's order, each where it lies: the
+ * first pass reads d_in and writes d_out, the others run in place on d_out */
+static int kf_axes_inlayout(kiss_fftnd_cfg st, int naxes, long long inner, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out,
+                            void *stream)
 {
-    long long nplanes = 1, below = st->dimprod;
-    for (int k = 0; k < st->ndims; ++k) {
+    long long nplanes = 1, below = inner;
+    for (int k = 0; k < naxes; ++k) below *= st->dims[k];
+    for (int k = 0; k < naxes; ++k) {
         const int n = st->dims[k];
         below /= n;                                   /* elements per index step of axis k */
         const kiss_fft_cpx *src = (k == 0) ? d_in : d_out;
@@ -760,16 +892,17 @@ int kiss_fftnd_dev(kiss_fftnd_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *d
         KF_ERROR("kiss_fftnd_dev: bad argument");
         return KISS_FFT_CUDA_EINVAL;
     }
-    if (kf_fftnd_inlayout_ok(cfg)) return kf_fftnd_dev_inlayout(cfg, d_in, d_out, stream);
+    if (cfg->ndims >= 2 && kf_axes_inlayout_ok(cfg, cfg->ndims, 1)) return kf_axes_inlayout(cfg, cfg->ndims, 1, d_in, d_out, stream);
     if (d_work) return kf_fftnd_dev_locked(cfg, d_in, d_out, d_work, stream);
-    /* internal scratch: serialise users of the shared slot and wait for completion before releasing it */
-    pthread_mutex_lock(&g_stage_lock);
+    /* internal scratch from a staging context: this variant waits for completion before giving the context back */
+    kf_ctx *cx = NULL;
+    KF_CHECK(kf_ctx_acquire(&cx));
     void *w = NULL;
-    int rc = kf_scratch(2, sizeof(kiss_fft_cpx) * (size_t)cfg->dimprod, &w);
+    int rc = kf_ctx_dev(cx, 2, sizeof(kiss_fft_cpx) * (size_t)cfg->dimprod, &w);
     if (!rc) rc = kf_fftnd_dev_locked(cfg, d_in, d_out, (kiss_fft_cpx *)w, stream);
-    if (!rc) rc = (int)cudaStreamSynchronize((cudaStream_t)stream);
-    pthread_mutex_unlock(&g_stage_lock);
-    return rc;
+    int e = (int)cudaStreamSynchronize((cudaStream_t)stream);
+    kf_ctx_release(cx);
+    return rc ? rc : e;
 }
 
 /* kiss_fftndr.c:86-110 and :112-132 on device buffers.
@@ -806,17 +939,25 @@ int kiss_fftndr_dev(kiss_fftndr_cfg cfg, const kiss_fft_scalar *d_time, kiss_fft
     const size_t nrbins = (size_t)cfg->dimReal / 2 + 1;
     const size_t total = (size_t)cfg->dimOther * nrbins;
     if (cfg->ndims == 1) return kiss_fftr_batch_dev(cfg->cfg_r, d_time, d_freq, 1, (size_t)cfg->dimReal, nrbins, stream);
-    pthread_mutex_lock(&g_stage_lock);
+    if (kf_axes_inlayout_ok(cfg->cfg_nd, cfg->cfg_nd->ndims, (long long)nrbins)) {
+        /* no gather / scatter at all (kiss_fftndr.c:101-108 folded away): the half spectra land in the caller's array
+         * [dimOther][B] and every leading axis is transformed where it lies -- stream-ordered, no scratch, no sync */
+        KF_CHECK(kiss_fftr_batch_dev(cfg->cfg_r, d_time, d_freq, (size_t)cfg->dimOther, (size_t)cfg->dimReal, nrbins, stream));
+        return kf_axes_inlayout(cfg->cfg_nd, cfg->cfg_nd->ndims, (long long)nrbins, d_freq, d_freq, stream);
+    }
+    kf_ctx *cx = NULL;
+    KF_CHECK(kf_ctx_acquire(&cx));
     void *w0 = NULL, *w1 = NULL;
-    int rc = kf_scratch(3, sizeof(kiss_fft_cpx) * total, &w0);
-    if (!rc) rc = kf_scratch(4, sizeof(kiss_fft_cpx) * total, &w1);
+    int rc = kf_ctx_dev(cx, 0, sizeof(kiss_fft_cpx) * total, &w0);
+    if (!rc) rc = kf_ctx_dev(cx, 1, sizeof(kiss_fft_cpx) * total, &w1);
     kiss_fft_cpx *a = (kiss_fft_cpx *)w0, *b = (kiss_fft_cpx *)w1;
     if (!rc) rc = kiss_fftr_batch_dev(cfg->cfg_r, d_time, a, (size_t)cfg->dimOther, (size_t)cfg->dimReal, nrbins, stream);
     if (!rc) rc = kf_leading_axes_dev(cfg->cfg_nd, total, &a, &b, stream);
     /* a: [B][dimOther] -> d_freq: [dimOther][B] */
     if (!rc) rc = kfcu_transpose(a, d_freq, (long long)nrbins, (long long)cfg->dimOther, stream);
-    if (!rc) rc = (int)cudaStreamSynchronize((cudaStream_t)stream);
-    pthread_mutex_unlock(&g_stage_lock);
+    int e = (int)cudaStreamSynchronize((cudaStream_t)stream);       /* the scratch goes back to the pool */
+    kf_ctx_release(cx);
+    if (!rc) rc = e;
     if (rc) return kf_cuda_fail(__FILE__, __LINE__, "kiss_fftndr_dev", rc);
     return 0;
 }
@@ -834,27 +975,36 @@ int kiss_fftndri_dev(kiss_fftndr_cfg cfg, const kiss_fft_cpx *d_freq, kiss_fft_s
     const size_t nrbins = (size_t)cfg->dimReal / 2 + 1;
     const size_t total = (size_t)cfg->dimOther * nrbins;
     if (cfg->ndims == 1) return kiss_fftri_batch_dev(cfg->cfg_r, d_freq, d_time, 1, nrbins, (size_t)cfg->dimReal, stream);
-    pthread_mutex_lock(&g_stage_lock);
+    kf_ctx *cx = NULL;
+    KF_CHECK(kf_ctx_acquire(&cx));
     void *w0 = NULL, *w1 = NULL;
-    int rc = kf_scratch(3, sizeof(kiss_fft_cpx) * total, &w0);
-    if (!rc) rc = kf_scratch(4, sizeof(kiss_fft_cpx) * total, &w1);
-    kiss_fft_cpx *a = (kiss_fft_cpx *)w0, *b = (kiss_fft_cpx *)w1;
-    /* first leading-axis pass reads the caller's buffer directly ([d0].. [B] has d0 leading already) */
+    int rc = kf_ctx_dev(cx, 0, sizeof(kiss_fft_cpx) * total, &w0);
+    kiss_fft_cpx *a = (kiss_fft_cpx *)w0, *b = NULL;
     kiss_fftnd_cfg nd = cfg->cfg_nd;
-    if (!rc) {
-        const size_t cols = total / (size_t)nd->dims[0];
-        rc = kiss_fft_axis_pass_dev(nd->states[0], d_freq, a, cols, cols, stream);
+    if (!rc && kf_axes_inlayout_ok(nd, nd->ndims, (long long)nrbins)) {
+        /* leading axes where they lie: the caller's spectrum is read once (it is const), the rest runs in place in `a` */
+        rc = kf_axes_inlayout(nd, nd->ndims, (long long)nrbins, d_freq, a, stream);
+        if (!rc) rc = kiss_fftri_batch_dev(cfg->cfg_r, a, d_time, (size_t)cfg->dimOther, nrbins, (size_t)cfg->dimReal, stream);
+    } else {
+        if (!rc) rc = kf_ctx_dev(cx, 1, sizeof(kiss_fft_cpx) * total, &w1);
+        b = (kiss_fft_cpx *)w1;
+        /* first leading-axis pass reads the caller's buffer directly ([d0].. [B] has d0 leading already) */
+        if (!rc) {
+            const size_t cols = total / (size_t)nd->dims[0];
+            rc = kiss_fft_axis_pass_dev(nd->states[0], d_freq, a, cols, cols, stream);
+        }
+        for (int k = 1; !rc && k < nd->ndims; ++k) {
+            const size_t cols = total / (size_t)nd->dims[k];
+            rc = kiss_fft_axis_pass_dev(nd->states[k], a, b, cols, cols, stream);
+            kiss_fft_cpx *t = a; a = b; b = t;
+        }
+        /* a: [B][dimOther] -> b: [dimOther][B], then the real inverse of every row (kiss_fftndr.c:127-131) */
+        if (!rc) rc = kfcu_transpose(a, b, (long long)nrbins, (long long)cfg->dimOther, stream);
+        if (!rc) rc = kiss_fftri_batch_dev(cfg->cfg_r, b, d_time, (size_t)cfg->dimOther, nrbins, (size_t)cfg->dimReal, stream);
     }
-    for (int k = 1; !rc && k < nd->ndims; ++k) {
-        const size_t cols = total / (size_t)nd->dims[k];
-        rc = kiss_fft_axis_pass_dev(nd->states[k], a, b, cols, cols, stream);
-        kiss_fft_cpx *t = a; a = b; b = t;
-    }
-    /* a: [B][dimOther] -> b: [dimOther][B], then the real inverse of every row (kiss_fftndr.c:127-131) */
-    if (!rc) rc = kfcu_transpose(a, b, (long long)nrbins, (long long)cfg->dimOther, stream);
-    if (!rc) rc = kiss_fftri_batch_dev(cfg->cfg_r, b, d_time, (size_t)cfg->dimOther, nrbins, (size_t)cfg->dimReal, stream);
-    if (!rc) rc = (int)cudaStreamSynchronize((cudaStream_t)stream);
-    pthread_mutex_unlock(&g_stage_lock);
+    int e = (int)cudaStreamSynchronize((cudaStream_t)stream);
+    kf_ctx_release(cx);
+    if (!rc) rc = e;
     if (rc) return kf_cuda_fail(__FILE__, __LINE__, "kiss_fftndri_dev", rc);
     return 0;
 }
@@ -880,51 +1030,124 @@ static int kf_chunk_c2r(void *cfg, const void *d_in, void *d_out, size_t n, void
                                 (size_t)c->nfft, stream);
 }
 
-#ifndef KF_CHUNK_MIB
-#define KF_CHUNK_MIB 32
-#endif
+/* One host-pointer batched call = `nlanes` lanes working through the chunks of the batch round-robin.  A lane owns a
+ * staging context (stream, device chunk buffers, pinned bounce buffers) and runs, per chunk,
+ *     [memcpy caller -> pinned]  H2D  kernel  D2H  [memcpy pinned -> caller]
+ * in order on its own host thread; the lanes overlap each other, so the copy engines (both directions), the SMs and
+ * the host cores doing the bounce copies are all busy at once.  The bracketed steps exist only for PAGEABLE caller
+ * memory -- what every drop-in caller of the reference passes (test/benchkiss.c:76-79, tools/fftutil.c:24-27): a
+ * cudaMemcpyAsync on it would be staged synchronously by the driver, one direction at a time.  Pinned caller buffers
+ * are handed to the copy engines directly.  KISSFFT_HOST_LANES / KISSFFT_CHUNK_MIB override the defaults. */
+/* defaults from the sweep in profiles/r02/e2e_probe_lanes_chunks.jsonl (16-core host, PCIe Gen5): pinned caller buffers are
+ * PCIe-bound from 2 lanes x 16 MiB on; pageable ones are bound by the host's bounce copies and want many lanes of
+ * small chunks */
+#define KF_CHUNK_MIB_PINNED 32
+#define KF_CHUNK_MIB_PAGEABLE 4
+#define KF_MAX_LANES 16
+
+typedef struct {
+    kf_chunk_fn fn;
+    void *cfg;
+    const char *in;
+    char *out;
+    size_t howmany, rows, in_row_bytes, out_row_bytes;
+    int lane, nlanes, device, in_pinned, out_pinned;
+    kf_ctx *cx;
+    int rc;
+} kf_lane;
+
+static void *kf_lane_main(void *arg)
+{
+    kf_lane *L = (kf_lane *)arg;
+    int rc = (int)cudaSetDevice(L->device);
+    kf_ctx *cx = L->cx;
+    const size_t nchunks = (L->howmany + L->rows - 1) / L->rows;
+    void *din = NULL, *dout = NULL, *pin = NULL, *pout = NULL;
+    if (!rc) rc = kf_ctx_dev(cx, 0, L->rows * L->in_row_bytes, &din);
+    if (!rc) rc = kf_ctx_dev(cx, 1, L->rows * L->out_row_bytes, &dout);
+    if (!rc && !L->in_pinned) rc = kf_ctx_pin(cx, 0, L->rows * L->in_row_bytes, &pin);
+    if (!rc && !L->out_pinned) rc = kf_ctx_pin(cx, 1, L->rows * L->out_row_bytes, &pout);
+    for (size_t c = (size_t)L->lane; !rc && c < nchunks; c += (size_t)L->nlanes) {
+        const size_t first = c * L->rows;
+        const size_t n = (L->howmany - first < L->rows) ? L->howmany - first : L->rows;
+        const void *src = L->in + first * L->in_row_bytes;
+        void *dst = L->out + first * L->out_row_bytes;
+        if (!L->in_pinned) {
+            memcpy(pin, src, n * L->in_row_bytes);
+            src = pin;
+        }
+        rc = (int)cudaMemcpyAsync(din, src, n * L->in_row_bytes, cudaMemcpyHostToDevice, cx->stream);
+        if (!rc) rc = L->fn(L->cfg, din, dout, n, cx->stream);
+        if (!rc) rc = (int)cudaMemcpyAsync(L->out_pinned ? dst : pout, dout, n * L->out_row_bytes, cudaMemcpyDeviceToHost, cx->stream);
+        const int e = (int)cudaStreamSynchronize(cx->stream);
+        if (!rc) rc = e;
+        if (!rc && !L->out_pinned) memcpy(dst, pout, n * L->out_row_bytes);
+    }
+    L->rc = rc;
+    return NULL;
+}
+
+static int kf_host_lanes(size_t nchunks, int pinned)
+{
+    int lanes = 4;
+    if (!pinned) {
+        /* bounce copies run on the host cores: three quarters of them, shared with the other ranks of this node */
+        long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+        const char *lw = getenv("LOCAL_WORLD_SIZE");
+        const int ranks = (lw && atoi(lw) > 0) ? atoi(lw) : 1;
+        lanes = (int)(ncpu * 3 / 4 / ranks);
+        if (lanes < 2) lanes = 2;
+        if (lanes > 12) lanes = 12;
+    }
+    const char *env = getenv("KISSFFT_HOST_LANES");
+    if (env && atoi(env) > 0) lanes = atoi(env);
+    if (lanes > KF_MAX_LANES) lanes = KF_MAX_LANES;
+    if ((size_t)lanes > nchunks) lanes = (int)nchunks;
+    return lanes < 1 ? 1 : lanes;
+}
+
 static int kf_host_pipeline(kf_chunk_fn fn, void *cfg, const void *in, void *out, size_t howmany, size_t in_row_bytes,
                             size_t out_row_bytes)
 {
-    enum { NS = 3 };
     if (howmany == 0) return 0;
-    pthread_mutex_lock(&g_stage_lock);
-    int rc = kf_get_streams();
-    /* chunk so that one chunk moves ~KF_CHUNK_MIB each way: large enough for PCIe efficiency, small enough that the
-     * un-overlapped first H2D and last D2H of a call stay short (KISSFFT_CHUNK_MIB overrides, for experiments) */
-    size_t chunk_mib = KF_CHUNK_MIB;
+    const int in_pinned = kf_is_pinned_host(in), out_pinned = kf_is_pinned_host(out);
+    size_t chunk_mib = (in_pinned && out_pinned) ? KF_CHUNK_MIB_PINNED : KF_CHUNK_MIB_PAGEABLE;
     const char *env = getenv("KISSFFT_CHUNK_MIB");
     if (env && atoi(env) > 0 && atoi(env) <= 1024) chunk_mib = (size_t)atoi(env);
     size_t rows = (chunk_mib << 20) / (in_row_bytes > out_row_bytes ? in_row_bytes : out_row_bytes);
     if (rows < 1) rows = 1;
     if (rows >= 64) rows &= ~(size_t)63; /* whole tiles for every fused plan (tpc <= 16) and 16-byte aligned chunk sizes */
     if (rows > howmany) rows = howmany;
-    void *din[NS], *dout[NS];
-    for (int s = 0; s < NS && !rc; ++s) {
-        /* one allocation per slot: input chunk followed by output chunk (256-B aligned) */
-        const size_t inb = (rows * in_row_bytes + 255u) & ~(size_t)255u;
-        void *base = NULL;
-        rc = kf_scratch(5 + s, inb + rows * out_row_bytes, &base);
-        din[s] = base;
-        dout[s] = (char *)base + inb;
+    const size_t nchunks = (howmany + rows - 1) / rows;
+    const int nlanes = kf_host_lanes(nchunks, in_pinned && out_pinned);
+    int dev = 0;
+    KF_CHECK(cudaGetDevice(&dev));
+    kf_lane lanes[KF_MAX_LANES];
+    pthread_t thr[KF_MAX_LANES];
+    int started[KF_MAX_LANES];
+    int rc = 0;
+    for (int l = 0; l < nlanes; ++l) {
+        kf_lane *L = &lanes[l];
+        memset(L, 0, sizeof(*L));
+        started[l] = 0;
+        L->fn = fn; L->cfg = cfg; L->in = (const char *)in; L->out = (char *)out;
+        L->howmany = howmany; L->rows = rows; L->in_row_bytes = in_row_bytes; L->out_row_bytes = out_row_bytes;
+        L->lane = l; L->nlanes = nlanes; L->device = dev; L->in_pinned = in_pinned; L->out_pinned = out_pinned;
+        if (!rc) rc = kf_ctx_acquire(&L->cx);
     }
-    size_t done = 0;
-    int c = 0;
-    while (!rc && done < howmany) {
-        const size_t n = (howmany - done < rows) ? howmany - done : rows;
-        const int s = c % NS;
-        cudaStream_t st = g_streams[s];
-        rc = (int)cudaMemcpyAsync(din[s], (const char *)in + done * in_row_bytes, n * in_row_bytes, cudaMemcpyHostToDevice, st);
-        if (!rc) rc = fn(cfg, din[s], dout[s], n, st);
-        if (!rc) rc = (int)cudaMemcpyAsync((char *)out + done * out_row_bytes, dout[s], n * out_row_bytes, cudaMemcpyDeviceToHost, st);
-        done += n;
-        ++c;
+    if (!rc) {
+        for (int l = 1; l < nlanes; ++l) {
+            if (pthread_create(&thr[l], NULL, kf_lane_main, &lanes[l]) == 0) started[l] = 1;
+        }
+        kf_lane_main(&lanes[0]);                   /* the calling thread is lane 0 */
+        for (int l = 1; l < nlanes; ++l) {
+            if (started[l]) pthread_join(thr[l], NULL);
+            else kf_lane_main(&lanes[l]);          /* thread creation failed: run the lane here */
+        }
+        for (int l = 0; l < nlanes; ++l)
+            if (!rc) rc = lanes[l].rc;
     }
-    for (int s = 0; s < NS; ++s) {
-        int e = (g_streams_dev >= 0) ? (int)cudaStreamSynchronize(g_streams[s]) : 0;
-        if (!rc) rc = e;
-    }
-    pthread_mutex_unlock(&g_stage_lock);
+    for (int l = 0; l < nlanes; ++l) kf_ctx_release(lanes[l].cx);
     if (rc) return kf_cuda_fail(__FILE__, __LINE__, "host batch pipeline", rc);
     return 0;
 }
@@ -962,28 +1185,47 @@ int kiss_fftri_batch(kiss_fftr_cfg cfg, const kiss_fft_cpx *freqdata, kiss_fft_s
 /* ---- the reference's transform calls -------------------------------------------------------------------- */
 
 /* run `body` on device copies of host buffers: in (in_bytes) -> out (out_bytes) */
-typedef int (*kf_dev_body)(void *cfg, const void *d_in, void *d_out, void *d_work, long long arg);
+typedef int (*kf_dev_body)(void *cfg, const void *d_in, void *d_out, void *d_work, long long arg, void *stream);
+
+/* bytes up to which a host buffer is bounced through the context's pinned buffer (one memcpy + an asynchronous DMA)
+ * instead of being handed to cudaMemcpy as pageable memory */
+#define KF_BOUNCE_MAX ((size_t)4 << 20)
 
 static int kf_stage_through_device(kf_dev_body body, void *cfg, const void *in, size_t in_bytes, void *out, size_t out_bytes,
                                    size_t work_bytes, long long arg)
 {
-    pthread_mutex_lock(&g_stage_lock);
-    void *din = NULL, *dout = NULL, *dwork = NULL;
-    int rc = kf_scratch(0, in_bytes, &din);
-    if (!rc) rc = kf_scratch(1, out_bytes, &dout);
-    if (!rc && work_bytes) rc = kf_scratch(2, work_bytes, &dwork);
-    if (!rc) rc = (int)cudaMemcpy(din, in, in_bytes, cudaMemcpyHostToDevice);
-    if (!rc) rc = body(cfg, din, dout, dwork, arg);
-    if (!rc) rc = (int)cudaMemcpy(out, dout, out_bytes, cudaMemcpyDeviceToHost); /* synchronises with the kernel */
-    pthread_mutex_unlock(&g_stage_lock);
+    kf_ctx *cx = NULL;
+    KF_CHECK(kf_ctx_acquire(&cx));
+    void *din = NULL, *dout = NULL, *dwork = NULL, *pin = NULL, *pout = NULL;
+    cudaStream_t st = cx->stream;
+    int rc = kf_ctx_dev(cx, 0, in_bytes, &din);
+    if (!rc) rc = kf_ctx_dev(cx, 1, out_bytes, &dout);
+    if (!rc && work_bytes) rc = kf_ctx_dev(cx, 2, work_bytes, &dwork);
+    const int bounce_in = in_bytes <= KF_BOUNCE_MAX, bounce_out = out_bytes <= KF_BOUNCE_MAX;
+    if (!rc && bounce_in) rc = kf_ctx_pin(cx, 0, in_bytes, &pin);
+    if (!rc && bounce_out) rc = kf_ctx_pin(cx, 1, out_bytes, &pout);
+    if (!rc) {
+        if (bounce_in) {
+            memcpy(pin, in, in_bytes);
+            rc = (int)cudaMemcpyAsync(din, pin, in_bytes, cudaMemcpyHostToDevice, st);
+        } else {
+            rc = (int)cudaMemcpyAsync(din, in, in_bytes, cudaMemcpyHostToDevice, st);
+        }
+    }
+    if (!rc) rc = body(cfg, din, dout, dwork, arg, st);
+    if (!rc) rc = (int)cudaMemcpyAsync(bounce_out ? pout : out, dout, out_bytes, cudaMemcpyDeviceToHost, st);
+    const int e = (int)cudaStreamSynchronize(st);      /* also after a failed body: the scratch goes back to the pool */
+    if (!rc) rc = e;
+    if (!rc && bounce_out) memcpy(out, pout, out_bytes);
+    kf_ctx_release(cx);
     return rc;
 }
 
-static int kf_body_stride(void *cfg, const void *d_in, void *d_out, void *d_work, long long stride)
+static int kf_body_stride(void *cfg, const void *d_in, void *d_out, void *d_work, long long stride, void *stream)
 {
     (void)d_work;
     kiss_fft_cfg c = (kiss_fft_cfg)cfg;
-    return kiss_fft_batch_dev(c, (const kiss_fft_cpx *)d_in, (kiss_fft_cpx *)d_out, 1, 0, 0, (int)stride, NULL);
+    return kiss_fft_batch_dev(c, (const kiss_fft_cpx *)d_in, (kiss_fft_cpx *)d_out, 1, 0, 0, (int)stride, stream);
 }
 
 void kiss_fft_stride(kiss_fft_cfg st, const kiss_fft_cpx *fin, kiss_fft_cpx *fout, int in_stride)
@@ -1011,17 +1253,17 @@ void kiss_fft_stride(kiss_fft_cfg st, const kiss_fft_cpx *fin, kiss_fft_cpx *fou
 
 void kiss_fft(kiss_fft_cfg cfg, const kiss_fft_cpx *fin, kiss_fft_cpx *fout) { kiss_fft_stride(cfg, fin, fout, 1); }
 
-static int kf_body_r2c(void *cfg, const void *d_in, void *d_out, void *d_work, long long arg)
+static int kf_body_r2c(void *cfg, const void *d_in, void *d_out, void *d_work, long long arg, void *stream)
 {
     (void)d_work; (void)arg;
     kiss_fftr_cfg c = (kiss_fftr_cfg)cfg;
-    return kiss_fftr_batch_dev(c, (const kiss_fft_scalar *)d_in, (kiss_fft_cpx *)d_out, 1, 0, 0, NULL);
+    return kiss_fftr_batch_dev(c, (const kiss_fft_scalar *)d_in, (kiss_fft_cpx *)d_out, 1, 0, 0, stream);
 }
-static int kf_body_c2r(void *cfg, const void *d_in, void *d_out, void *d_work, long long arg)
+static int kf_body_c2r(void *cfg, const void *d_in, void *d_out, void *d_work, long long arg, void *stream)
 {
     (void)d_work; (void)arg;
     kiss_fftr_cfg c = (kiss_fftr_cfg)cfg;
-    return kiss_fftri_batch_dev(c, (const kiss_fft_cpx *)d_in, (kiss_fft_scalar *)d_out, 1, 0, 0, NULL);
+    return kiss_fftri_batch_dev(c, (const kiss_fft_cpx *)d_in, (kiss_fft_scalar *)d_out, 1, 0, 0, stream);
 }
 
 void kiss_fftr(kiss_fftr_cfg st, const kiss_fft_scalar *timedata, kiss_fft_cpx *freqdata)
@@ -1064,10 +1306,22 @@ void kiss_fftri(kiss_fftr_cfg st, const kiss_fft_cpx *freqdata, kiss_fft_scalar 
     if (rc) kf_cuda_fail(__FILE__, __LINE__, "kiss_fftri", rc);
 }
 
-static int kf_body_nd(void *cfg, const void *d_in, void *d_out, void *d_work, long long arg)
+static int kf_body_nd(void *cfg, const void *d_in, void *d_out, void *d_work, long long arg, void *stream)
 {
     (void)arg;
-    return kf_fftnd_dev_locked((kiss_fftnd_cfg)cfg, (const kiss_fft_cpx *)d_in, (kiss_fft_cpx *)d_out, (kiss_fft_cpx *)d_work, NULL);
+    kiss_fftnd_cfg st = (kiss_fftnd_cfg)cfg;
+    if (!d_work) return kf_axes_inlayout(st, st->ndims, 1, (const kiss_fft_cpx *)d_in, (kiss_fft_cpx *)d_out, stream);
+    return kf_fftnd_dev_locked(st, (const kiss_fft_cpx *)d_in, (kiss_fft_cpx *)d_out, (kiss_fft_cpx *)d_work, stream);
+}
+static int kf_body_ndr(void *cfg, const void *d_in, void *d_out, void *d_work, long long arg, void *stream)
+{
+    (void)d_work; (void)arg;
+    return kiss_fftndr_dev((kiss_fftndr_cfg)cfg, (const kiss_fft_scalar *)d_in, (kiss_fft_cpx *)d_out, stream);
+}
+static int kf_body_ndri(void *cfg, const void *d_in, void *d_out, void *d_work, long long arg, void *stream)
+{
+    (void)d_work; (void)arg;
+    return kiss_fftndri_dev((kiss_fftndr_cfg)cfg, (const kiss_fft_cpx *)d_in, (kiss_fft_scalar *)d_out, stream);
 }
 
 void kiss_fftnd(kiss_fftnd_cfg st, const kiss_fft_cpx *fin, kiss_fft_cpx *fout)
@@ -1081,7 +1335,8 @@ void kiss_fftnd(kiss_fftnd_cfg st, const kiss_fft_cpx *fin, kiss_fft_cpx *fout)
         return;
     }
     const size_t bytes = sizeof(kiss_fft_cpx) * (size_t)st->dimprod;
-    int rc = kf_stage_through_device(kf_body_nd, st, fin, bytes, fout, bytes, bytes, 0);
+    const int inlay = st->ndims >= 2 && kf_axes_inlayout_ok(st, st->ndims, 1);      /* then no work buffer is needed */
+    int rc = kf_stage_through_device(kf_body_nd, st, fin, bytes, fout, bytes, inlay ? 0 : bytes, 0);
     if (rc) kf_cuda_fail(__FILE__, __LINE__, "kiss_fftnd", rc);
 }
 
@@ -1098,14 +1353,7 @@ void kiss_fftndr(kiss_fftndr_cfg st, const kiss_fft_scalar *timedata, kiss_fft_c
     const size_t nrbins = (size_t)st->dimReal / 2 + 1;
     const size_t in_bytes = sizeof(kiss_fft_scalar) * (size_t)st->dimOther * (size_t)st->dimReal;
     const size_t out_bytes = sizeof(kiss_fft_cpx) * (size_t)st->dimOther * nrbins;
-    void *din = NULL, *dout = NULL;
-    int rc = (int)cudaMalloc(&din, in_bytes);
-    if (!rc) rc = (int)cudaMalloc(&dout, out_bytes);
-    if (!rc) rc = (int)cudaMemcpy(din, timedata, in_bytes, cudaMemcpyHostToDevice);
-    if (!rc) rc = kiss_fftndr_dev(st, (const kiss_fft_scalar *)din, (kiss_fft_cpx *)dout, NULL);
-    if (!rc) rc = (int)cudaMemcpy(freqdata, dout, out_bytes, cudaMemcpyDeviceToHost);
-    cudaFree(din);
-    cudaFree(dout);
+    int rc = kf_stage_through_device(kf_body_ndr, st, timedata, in_bytes, freqdata, out_bytes, 0, 0);
     if (rc) kf_cuda_fail(__FILE__, __LINE__, "kiss_fftndr", rc);
 }
 
@@ -1122,14 +1370,7 @@ void kiss_fftndri(kiss_fftndr_cfg st, const kiss_fft_cpx *freqdata, kiss_fft_sca
     const size_t nrbins = (size_t)st->dimReal / 2 + 1;
     const size_t out_bytes = sizeof(kiss_fft_scalar) * (size_t)st->dimOther * (size_t)st->dimReal;
     const size_t in_bytes = sizeof(kiss_fft_cpx) * (size_t)st->dimOther * nrbins;
-    void *din = NULL, *dout = NULL;
-    int rc = (int)cudaMalloc(&din, in_bytes);
-    if (!rc) rc = (int)cudaMalloc(&dout, out_bytes);
-    if (!rc) rc = (int)cudaMemcpy(din, freqdata, in_bytes, cudaMemcpyHostToDevice);
-    if (!rc) rc = kiss_fftndri_dev(st, (const kiss_fft_cpx *)din, (kiss_fft_scalar *)dout, NULL);
-    if (!rc) rc = (int)cudaMemcpy(timedata, dout, out_bytes, cudaMemcpyDeviceToHost);
-    cudaFree(din);
-    cudaFree(dout);
+    int rc = kf_stage_through_device(kf_body_ndri, st, freqdata, in_bytes, timedata, out_bytes, 0, 0);
     if (rc) kf_cuda_fail(__FILE__, __LINE__, "kiss_fftndri", rc);
 }
 

@@ -132,9 +132,12 @@ def test_real_batch(ctx, nfft):
 ND_DIMS = [(8,), (4, 3), (2, 3, 4), (30, 20, 12), (64, 64), (16, 16, 16), (256, 64), (5, 6, 7, 4), (64, 128, 32)]
 
 
+@pytest.mark.parametrize("inlayout", ["1", "0"])
 @pytest.mark.parametrize("dims", ND_DIMS)
-def test_fftnd(ctx, dims):
+def test_fftnd(ctx, dims, inlayout, monkeypatch):
+    """both kiss_fftnd strategies: axes transformed where they lie (default) and the reference's transposing sweeps"""
     tname, lib, o = ctx
+    monkeypatch.setenv("KISSFFT_FFTND_INLAYOUT", inlayout)
     n = int(np.prod(dims))
     for inverse in (False, True):
         x = random_input(tname, dims, 31 + n)
@@ -236,10 +239,13 @@ def test_reference_api_with_host_pointers(ctx):
     lib.free(cfgi)
 
 
+@pytest.mark.parametrize("fourstep", ["1", "0"])
 @pytest.mark.parametrize("nfft", [16384, 30000, 32768, 65536])
-def test_large_lengths_multipass(ctx, nfft):
-    """lengths beyond the shared-memory kernels run one radix stage per launch over global memory"""
+def test_large_lengths(ctx, nfft, fourstep, monkeypatch):
+    """lengths beyond the shared-memory kernels: four-step (two fused column passes; float/double with a fused plan for
+    both factors) or one radix stage per launch over global memory (fixed point, other lengths, KISSFFT_FOURSTEP=0)"""
     tname, lib, o = ctx
+    monkeypatch.setenv("KISSFFT_FOURSTEP", fourstep)
     howmany = 3
     x = random_input(tname, (howmany, nfft), 90 + nfft)
     for inverse in (False, True):
@@ -461,6 +467,77 @@ def test_config5_3d_single_gpu_256():
     lib.free(cfg)
 
 
+def sampled_dft_check(x, X, nbins, seed, tol):
+    """SURVEY.md 8(d) parity sampling for arrays too large for the CPU oracle: Parseval over the whole array and `nbins`
+    random output bins against direct DFT sums accumulated in float64 (on the GPU, chunked over the leading axis).
+    x, X: torch complex-as-(...,2) float32 tensors of shape dims + (2,), X = DFT(x) in natural order."""
+    dims = tuple(x.shape[:-1])
+    d0, rest = dims[0], int(np.prod(dims[1:]))
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    ks = [torch.randint(0, d, (nbins,), generator=g) for d in dims]
+    cd = torch.complex128
+    # separable phase factors exp(-2 pi i k_a n_a / d_a), one column per sampled bin
+    W = [torch.exp(-2j * np.pi * (torch.arange(d, dtype=torch.float64)[:, None] * k[None, :].double()) / d).to(cd).cuda()
+         for d, k in zip(dims, ks)]
+    acc = torch.zeros(nbins, dtype=cd, device="cuda")
+    ein = torch.zeros((), dtype=torch.float64, device="cuda")
+    eout = torch.zeros((), dtype=torch.float64, device="cuda")
+    step = max(1, (1 << 25) // rest)
+    for p0 in range(0, d0, step):
+        p1 = min(d0, p0 + step)
+        xc = torch.view_as_complex(x[p0:p1].contiguous()).to(cd)             # [p][d1]...[dlast]
+        ein += (xc.real ** 2 + xc.imag ** 2).sum()
+        Xc = X[p0:p1].double()
+        eout += (Xc ** 2).sum()
+        del Xc
+        t = xc.reshape(-1, dims[-1]) @ W[-1]                                  # contract the last axis -> [.., nbins]
+        del xc
+        for a in range(len(dims) - 2, 0, -1):                                 # then the middle axes, innermost first
+            t = (t.reshape(-1, dims[a], nbins) * W[a][None]).sum(1)
+        acc += (t.reshape(p1 - p0, nbins) * W[0][p0:p1]).sum(0)
+    n = float(np.prod(dims))
+    assert abs(float(eout) / (n * float(ein)) - 1.0) <= tol, "Parseval: %r vs %r" % (float(eout), n * float(ein))
+    idx = tuple(k.cuda() for k in ks)
+    got = torch.view_as_complex(X[idx].contiguous()).to(cd)
+    err = float((got - acc).abs().pow(2).sum().sqrt() / acc.abs().pow(2).sum().sqrt())
+    assert err <= tol, "sampled bins rel-rms %.3g > %.3g" % (err, tol)
+    return err
+
+
+def test_config5_3d_single_gpu_1024():
+    """BASELINE configs[4] on one GPU: kiss_fftnd 1024^3 complex float (8 GiB in, 8 GiB out, no work buffer).  The CPU
+    oracle would need ~5 min and 24 GiB here, so SURVEY.md 8(d)'s sampling applies: Parseval over the whole array +
+    64 random bins vs float64 direct DFT sums, tolerance 1e-6*log2(N)."""
+    import kissfft_b200
+    free, _ = torch.cuda.mem_get_info()
+    if free < 19 * (1 << 30):
+        pytest.skip("needs 19 GiB of free device memory")
+    lib = kissfft_b200.get("float")
+    dims = (1024, 1024, 1024)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    x = torch.rand(dims + (2,), generator=g, device="cuda", dtype=torch.float32) * 2 - 1
+    X = torch.empty_like(x)
+    cfg = lib.allocnd(dims)
+    lib.fftnd_dev(cfg, x, X, None, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    sampled_dft_check(x, X, 64, 77, 1e-6 * 30)
+    # inverse of the forward result returns N * x (kiss_fftnd does not scale): whole-array round trip, in place
+    cfgi = lib.allocnd(dims, True)
+    lib.fftnd_dev(cfgi, X, X, None, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    num = torch.zeros((), dtype=torch.float64, device="cuda")
+    den = torch.zeros((), dtype=torch.float64, device="cuda")
+    for p0 in range(0, 1024, 64):
+        d = X[p0:p0 + 64].double() / float(1 << 30) - x[p0:p0 + 64].double()
+        num += (d ** 2).sum()
+        den += (x[p0:p0 + 64].double() ** 2).sum()
+    assert float((num / den).sqrt()) <= 2e-6 * 30
+    lib.free(cfg)
+    lib.free(cfgi)
+
+
 def test_slab_single_rank_and_planes_pass():
     """slab decomposition with G == 1 (steps A, B, C without the exchange) and the plane-batched column pass"""
     import kissfft_b200
@@ -530,16 +607,14 @@ def test_fused_fast_convolution(tname, nfft, nimp):
     lib.fastconv_free(cfg)
 
 
-@pytest.mark.skipif(os.environ.get("KISSFFT_TEST_EXPERIMENTAL") != "1",
-                    reason="opt-in four-step path: emulator-validated, to be enabled once it has run on a GPU (KISSFFT_TEST_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("tname", ["float", "double"])
 @pytest.mark.parametrize("nfft", [16384, 65536, 1 << 20])
-def test_fourstep_long_rows_opt_in(tname, nfft, monkeypatch):
-    """KISSFFT_FOURSTEP=1: long contiguous rows as two fused column passes instead of one launch per radix stage"""
+def test_fourstep_long_rows(tname, nfft, monkeypatch):
+    """default for float/double (KISSFFT_FOURSTEP=0 opts out): long contiguous rows as two fused column passes instead of one launch per radix stage"""
     import torch
     import kissfft_b200
     from oracle.loader import Oracle, random_input, rel_rms
-    monkeypatch.setenv("KISSFFT_FOURSTEP", "1")
+    monkeypatch.delenv("KISSFFT_FOURSTEP", raising=False)
     lib, o = kissfft_b200.get(tname), Oracle(tname)
     rows = 3
     x = random_input(tname, (rows, nfft), 4242)
@@ -555,16 +630,14 @@ def test_fourstep_long_rows_opt_in(tname, nfft, monkeypatch):
         assert rel_rms(d_out.cpu().numpy(), o.fft(x, inverse)) <= tol
 
 
-@pytest.mark.skipif(os.environ.get("KISSFFT_TEST_EXPERIMENTAL") != "1",
-                    reason="opt-in in-layout kiss_fftnd: emulator-validated, to be enabled once it has run on a GPU (KISSFFT_TEST_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("tname", ["float", "double", "int16_t", "int32_t"])
 @pytest.mark.parametrize("dims", [(64, 128, 256), (128, 64), (256, 256, 30)])
-def test_fftnd_in_layout_opt_in(tname, dims, monkeypatch):
-    """KISSFFT_FFTND_INLAYOUT=1: every axis transformed where it lies; same bits as the transposing sweeps in fixed point"""
+def test_fftnd_in_layout(tname, dims, monkeypatch):
+    """default (KISSFFT_FFTND_INLAYOUT=0 opts out): every axis transformed where it lies; same bits as the transposing sweeps in fixed point"""
     import torch
     import kissfft_b200
     from oracle.loader import Oracle, random_input, rel_rms
-    monkeypatch.setenv("KISSFFT_FFTND_INLAYOUT", "1")
+    monkeypatch.delenv("KISSFFT_FFTND_INLAYOUT", raising=False)
     lib, o = kissfft_b200.get(tname), Oracle(tname)
     x = random_input(tname, dims, 99)
     cfg = lib.allocnd(list(dims), False)
