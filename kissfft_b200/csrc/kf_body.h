@@ -197,24 +197,30 @@ KF_HD void run_groups(Env& env, int t, bool active, const Src& src, const Dst& d
 // memory.  Items 0 and m/2 pair with themselves and are taken together by the thread whose u is 0.
 // Same operands and roundings as the reference's loop over k = 1..nc/2, so fixed point stays bit-exact.
 // ---------------------------------------------------------------------------------------------------------
-// pair index of thread t inside its warp's block of 32 pairs (PlanDesc::pairperm)
-template <PlanDesc D>
-KF_HD int pair_lane(int t)
+// Bin pairs a thread of a paired group handles, in the order both paired passes enumerate them: pair jj (< R) of the
+// thread whose first item is u, with m work items in the group (half = m/2, nc = R*m bins):
+//   u != 0:  jj even -> k = u + (jj/2)*m        jj odd -> k = (m-u) + (jj/2)*m
+//   u == 0:  jj == 0 -> k = nc/2 (self-paired)  jj even -> k = (jj/2)*m      jj odd -> k = half + (jj/2)*m
+KF_HD int pair_ks(int u, int jj, int m, int nc)
 {
-    if constexpr (D.pairperm == 1) {
-        static_assert(D.team % 32 == 0, "pairperm permutes the lanes of whole warps");
-        return (t & ~31) | ((t & 15) << 1) | ((t >> 4) & 1);
-    } else {
-        return t;
-    }
+    const int e = jj >> 1, odd = jj & 1;
+    if (u != 0) return (odd ? m - u : u) + e * m;
+    return jj == 0 ? nc / 2 : (odd ? m / 2 : 0) + e * m;
+}
+
+// split twiddle of pair jj: from the thread's registers when hoisted (HS), else from the table
+template <class A, bool HS>
+KF_HD cx<typename A::R> split_tw(const typename A::C* stw, const cx<typename A::R>* hst, int idx, int ks)
+{
+    if constexpr (HS) return hst[idx];
+    else return A::load(TwTab<A>::ro_load_c(stw + (ks - 1)));
 }
 
 template <class A>
-KF_HD void r2c_emit_pair(int ks, int nc, const cx<typename A::R>& Tk, const cx<typename A::R>& Tnk, const typename A::C* stw,
+KF_HD void r2c_emit_pair(int ks, int nc, const cx<typename A::R>& Tk, const cx<typename A::R>& Tnk, const cx<typename A::R>& st,
                          typename A::C* out)
 {
     typedef cx<typename A::R> X;
-    const X st = A::load(TwTab<A>::ro_load_c(stw + (ks - 1)));
     X ok, onk;
     fftr_post_pair<A>(ks, nc, Tk, Tnk, st, ok, onk);
     if (ks != nc - ks) out[ks] = A::store(ok);     // ks == nc/2: the reference's second assignment wins
@@ -225,16 +231,20 @@ KF_HD void r2c_emit_pair(int ks, int nc, const cx<typename A::R>& Tk, const cx<t
 // in-place input stage; it contains a CTA barrier only when every thread reaches it exactly once, kIt == 1).
 template <class A, PlanDesc D, class Mid>
 KF_HD void run_r2c_last_paired(int t, bool active, const typename A::C* rd, const TwTab<A>& tw, const PlanConsts<A>& pc,
-                               const typename A::C* stw, typename A::C* out, int inverse, const Mid& mid)
+                               const typename A::C* stw, const cx<typename A::R>* hst, typename A::C* out, int inverse, const Mid& mid)
 {
     typedef cx<typename A::R> X;
     constexpr int gl = D.G - 1, R = D.R(gl), m = D.items(gl), nc = D.N, half = m / 2;
     constexpr int kIt = (half + D.team - 1) / D.team;                   // u = 0 .. half-1
+    constexpr bool HS = (D.hoist & 1) != 0;
     const typename A::R sg = A::sign_of(inverse);
     static_for<kIt>([&](auto ITER) {
-        const int u = pair_lane<D>(t) + decltype(ITER)::value * D.team;
+        constexpr int it = decltype(ITER)::value;
+        const int u = t + it * D.team;
         const bool on = active && u < half;
         const int wa = on ? u : 0, wb = (on && u != 0) ? m - u : half;   // items (u, m-u); (0, m/2) for u == 0
+        constexpr int kHa = (D.hoist & 4) ? D.hoist_base(gl, 2 * it) : -1, kHb = (D.hoist & 4) ? D.hoist_base(gl, 2 * it + 1) : -1;
+        auto st = [&](int jj, int ks) { return split_tw<A, HS>(stw, hst, it * R + jj, ks); };
         X a[R], b[R];
         if (on) {
             item_load<A, D, gl>(wa, rd, a);
@@ -242,8 +252,8 @@ KF_HD void run_r2c_last_paired(int t, bool active, const typename A::C* rd, cons
         }
         mid();
         if (on) {
-            item_stages<A, D, gl>(wa, a, tw, pc, sg);
-            item_stages<A, D, gl>(wb, b, tw, pc, sg);
+            item_stages<A, D, gl, kHa>(wa, a, tw, pc, sg);
+            item_stages<A, D, gl, kHb>(wb, b, tw, pc, sg);
             if (u == 0) {
                 // a = T[j*m], b = T[m/2 + j*m]: both items pair with themselves
                 X ok, onk;
@@ -253,16 +263,16 @@ KF_HD void run_r2c_last_paired(int t, bool active, const typename A::C* rd, cons
                 out[nc] = A::store(onk);
                 static_for<R / 2>([&](auto JJ) {
                     constexpr int j = decltype(JJ)::value;
-                    if constexpr (j >= 1) r2c_emit_pair<A>(j * m, nc, a[D.reg_of_j(gl, j)], a[D.reg_of_j(gl, R - j)], stw, out);
-                    r2c_emit_pair<A>(half + j * m, nc, b[D.reg_of_j(gl, j)], b[D.reg_of_j(gl, R - 1 - j)], stw, out);
+                    if constexpr (j >= 1) r2c_emit_pair<A>(j * m, nc, a[D.reg_of_j(gl, j)], a[D.reg_of_j(gl, R - j)], st(2 * j, j * m), out);
+                    r2c_emit_pair<A>(half + j * m, nc, b[D.reg_of_j(gl, j)], b[D.reg_of_j(gl, R - 1 - j)], st(2 * j + 1, half + j * m), out);
                 });
-                r2c_emit_pair<A>(nc / 2, nc, a[eh], a[eh], stw, out);           // k == nc/2 pairs with itself
+                r2c_emit_pair<A>(nc / 2, nc, a[eh], a[eh], st(0, nc / 2), out);   // k == nc/2 pairs with itself
             } else {
                 static_for<R / 2>([&](auto JJ) {
                     constexpr int j = decltype(JJ)::value;
                     constexpr int ej = D.reg_of_j(gl, j), en = D.reg_of_j(gl, R - 1 - j);
-                    r2c_emit_pair<A>(u + j * m, nc, a[ej], b[en], stw, out);
-                    r2c_emit_pair<A>((m - u) + j * m, nc, b[ej], a[en], stw, out);
+                    r2c_emit_pair<A>(u + j * m, nc, a[ej], b[en], st(2 * j, u + j * m), out);
+                    r2c_emit_pair<A>((m - u) + j * m, nc, b[ej], a[en], st(2 * j + 1, (m - u) + j * m), out);
                 });
             }
         }
@@ -276,26 +286,28 @@ KF_HD void run_r2c_last_paired(int t, bool active, const typename A::C* rd, cons
 // produces both T values of the pair as the reference does (SrcC2RFused evaluates each pair twice).
 // ---------------------------------------------------------------------------------------------------------
 template <class A, class F>
-KF_HD void c2r_make_pair(int ks, int nc, const F& f, const typename A::C* stw, cx<typename A::R>& Tk, cx<typename A::R>& Tnk)
+KF_HD void c2r_make_pair(int ks, int nc, const F& f, const cx<typename A::R>& st, cx<typename A::R>& Tk, cx<typename A::R>& Tnk)
 {
     typedef cx<typename A::R> X;
     const X Fa = f(ks), Fb = f(nc - ks);
-    const X st = A::load(TwTab<A>::ro_load_c(stw + (ks - 1)));
     fftri_pre_pair<A>(ks, Fa, Fb, st, Tk, Tnk);
 }
 
 template <class A, PlanDesc D, class F, class Mid>
 KF_HD void run_c2r_first_paired(int t, bool active, const F& f, typename A::C* wr, const TwTab<A>& tw, const PlanConsts<A>& pc,
-                                const typename A::C* stw, int inverse, const Mid& mid)
+                                const typename A::C* stw, const cx<typename A::R>* hst, int inverse, const Mid& mid)
 {
     typedef cx<typename A::R> X;
     constexpr int R = D.R(0), W = D.items(0), nc = D.N, half = W / 2;
     constexpr int kIt = (half + D.team - 1) / D.team;
+    constexpr bool HS = (D.hoist & 1) != 0;
     const typename A::R sg = A::sign_of(inverse);
     static_for<kIt>([&](auto ITER) {
-        const int u = pair_lane<D>(t) + decltype(ITER)::value * D.team;
+        constexpr int it = decltype(ITER)::value;
+        const int u = t + it * D.team;
         const bool on = active && u < half;
         const int wa = on ? u : 0, wb = (on && u != 0) ? W - u : half;
+        auto st = [&](int jj, int ks) { return split_tw<A, HS>(stw, hst, it * R + jj, ks); };
         X a[R], b[R];
         if (on) {
             if (u == 0) {
@@ -303,15 +315,15 @@ KF_HD void run_c2r_first_paired(int t, bool active, const F& f, typename A::C* w
                 fftri_pre_pair<A>(0, f(0), f(nc), f(0), a[0], dummy);            // T[0] from F[0], F[nc]
                 static_for<R / 2>([&](auto EE) {
                     constexpr int e = decltype(EE)::value;
-                    if constexpr (e >= 1) c2r_make_pair<A>(e * W, nc, f, stw, a[e], a[R - e]);
-                    c2r_make_pair<A>(half + e * W, nc, f, stw, b[e], b[R - 1 - e]);
+                    if constexpr (e >= 1) c2r_make_pair<A>(e * W, nc, f, st(2 * e, e * W), a[e], a[R - e]);
+                    c2r_make_pair<A>(half + e * W, nc, f, st(2 * e + 1, half + e * W), b[e], b[R - 1 - e]);
                 });
-                c2r_make_pair<A>(nc / 2, nc, f, stw, dummy, a[R / 2]);             // k == nc/2: the second assignment wins
+                c2r_make_pair<A>(nc / 2, nc, f, st(0, nc / 2), dummy, a[R / 2]);   // k == nc/2: the second assignment wins
             } else {
                 static_for<R / 2>([&](auto EE) {
                     constexpr int e = decltype(EE)::value;
-                    c2r_make_pair<A>(u + e * W, nc, f, stw, a[e], b[R - 1 - e]);
-                    c2r_make_pair<A>((W - u) + e * W, nc, f, stw, b[e], a[R - 1 - e]);
+                    c2r_make_pair<A>(u + e * W, nc, f, st(2 * e, u + e * W), a[e], b[R - 1 - e]);
+                    c2r_make_pair<A>((W - u) + e * W, nc, f, st(2 * e + 1, (W - u) + e * W), b[e], a[R - 1 - e]);
                 });
             }
         }
@@ -322,6 +334,53 @@ KF_HD void run_c2r_first_paired(int t, bool active, const F& f, typename A::C* w
             item_store<A, D, 0>(wa, wr, a);
             item_store<A, D, 0>(wb, wr, b);
         }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Loop-invariant tables into registers (PlanDesc::hoist).  A persistent CTA's thread t runs the same work items of
+// every group for every tile, so the twiddles those items need never change: they are fetched once, before the tile
+// loop, instead of once per transform (ncu r01: 690-780 MB of L1 table traffic per launch, more than the payload).
+// PAIRG = the group this mode runs on work-item pairs (kiss_fftr: the last one), or -1.
+// ---------------------------------------------------------------------------------------------------------
+template <class A, PlanDesc D, int PAIRG, int g = 1>
+KF_HD void hoist_fill(int t, const TwTab<A>& tw, cx<typename A::R>* hreg)
+{
+    if constexpr (g < D.G) {
+        if constexpr (g == PAIRG) {
+            if constexpr ((D.hoist & 4) != 0) {
+                constexpr int m = D.items(g), half = m / 2, kIt = (half + D.team - 1) / D.team;
+                static_for<kIt>([&](auto ITER) {
+                    constexpr int it = decltype(ITER)::value;
+                    const int u = t + it * D.team;
+                    const bool in = u < half;
+                    hoist_item<A, D, g, D.hoist_base(g, 2 * it)>(tw, in ? u : 0, hreg);
+                    hoist_item<A, D, g, D.hoist_base(g, 2 * it + 1)>(tw, (in && u != 0) ? m - u : half, hreg);
+                });
+            }
+        } else if constexpr ((D.hoist & 2) != 0) {
+            static_for<D.iters(g)>([&](auto ITER) {
+                constexpr int it = decltype(ITER)::value;
+                const int w = t + it * D.team;
+                hoist_item<A, D, g, D.hoist_base(g, it)>(tw, w < D.items(g) ? w : D.items(g) - 1, hreg);
+            });
+        }
+        hoist_fill<A, D, PAIRG, g + 1>(t, tw, hreg);
+    }
+}
+
+// split twiddles of the bin pairs thread t handles in the paired group with m items of R points (pair_ks order)
+template <class A, PlanDesc D, int R, int m>
+KF_HD void hoist_fill_split(int t, const typename A::C* stw, cx<typename A::R>* hst)
+{
+    constexpr int half = m / 2, kIt = (half + D.team - 1) / D.team;
+    static_for<kIt>([&](auto ITER) {
+        constexpr int it = decltype(ITER)::value;
+        const int u0 = t + it * D.team, u = u0 < half ? u0 : 0;
+        static_for<R>([&](auto JJ) {
+            constexpr int jj = decltype(JJ)::value;
+            hst[it * R + jj] = A::load(TwTab<A>::ro_load_c(stw + (pair_ks(u, jj, m, D.N) - 1)));
+        });
     });
 }
 
@@ -416,7 +475,20 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
 
     const int tid = env.tid();
     const int team = tid / D.team, t = tid % D.team;              // standard mapping: a team owns a transform
-    const TwTab<A> tw{P.tw, P.gtw, P.g0tw, P.ctw};
+    // loop-invariant tables of this thread's work items (registers; PlanDesc::hoist)
+    constexpr int kPairG = LY::kPairedLast ? D.G - 1 : -1;
+    constexpr int kPairR = LY::kPairedLast ? D.R(D.G - 1) : (LY::kPairedFirst ? D.R(0) : 2);
+    constexpr int kPairM = D.N / kPairR;
+    constexpr bool kHoistSplit = (D.hoist & 1) && (LY::kPairedLast || LY::kPairedFirst);
+    static_assert(!(D.hoist != 0 && LY::kShflPost), "hoisted tables assume the standard thread numbering");
+    X hreg[D.hoist_total() > 0 && (D.hoist & 6) ? D.hoist_total() : 1];
+    X hst[kHoistSplit ? ((kPairM / 2 + D.team - 1) / D.team) * kPairR : 1];
+    {
+        const TwTab<A> tw0{P.tw, P.gtw, P.g0tw, P.ctw, nullptr};
+        if constexpr ((D.hoist & 6) != 0) hoist_fill<A, PT::D, kPairG>(t, tw0, hreg);
+        if constexpr (kHoistSplit) hoist_fill_split<A, PT::D, kPairR, kPairM>(t, P.stw, hst);
+    }
+    const TwTab<A> tw{P.tw, P.gtw, P.g0tw, P.ctw, hreg};
     const long long ntiles = (P.howmany + D.tpc - 1) / D.tpc;
     int par = 0;   // parity of the exchange buffer sequence, carried across tiles (see run_groups)
 
@@ -482,7 +554,7 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             env.sync();                                   // every team has consumed its landed row
             run_group<A, PT::D, 1, S, DstGlobal<A>>(t, active, S{srow}, unused, exA, exS, tw, P.pc, P.inverse);
             env.sync();
-            run_r2c_last_paired<A, PT::D>(t, active, exS, tw, P.pc, P.stw, P.out + b * P.out_dist, P.inverse, [&]() {
+            run_r2c_last_paired<A, PT::D>(t, active, exS, tw, P.pc, P.stw, hst, P.out + b * P.out_dist, P.inverse, [&]() {
                 env.sync();                               // the stage is consumed again: refill it
                 recycle();
             });
@@ -499,7 +571,7 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             };
             if constexpr (kRing) run_all(SrcShared<A>{srow});
             else run_all(SrcGlobal<A, true>{P.in + b * P.in_dist, 1});
-            run_r2c_last_paired<A, PT::D>(t, active, (gl & 1) ? b1 : b0, tw, P.pc, P.stw, P.out + b * P.out_dist, P.inverse, []() {});
+            run_r2c_last_paired<A, PT::D>(t, active, (gl & 1) ? b1 : b0, tw, P.pc, P.stw, hst, P.out + b * P.out_dist, P.inverse, []() {});
             par ^= (D.G - 1) & 1;
         } else if constexpr (MODE == kC2R && LY::kStageExch) {
             // ---- kiss_fftri, three groups: paired first group from the stage -> A -> stage -> last group ----
@@ -507,7 +579,7 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             C* const exS = stage_ptr(stg) + team * kPitch;
             DstGlobal<A> dstg{P.out + b * P.out_dist};
             auto f = [&](int i) { return A::load(srow[i]); };
-            run_c2r_first_paired<A, PT::D>(t, active, f, exA, tw, P.pc, P.stw, P.inverse, []() {});
+            run_c2r_first_paired<A, PT::D>(t, active, f, exA, tw, P.pc, P.stw, hst, P.inverse, []() {});
             env.sync();                                   // every team has consumed its landed row
             run_group<A, PT::D, 1, NoSrc, DstGlobal<A>>(t, active, NoSrc{}, dstg, exA, exS, tw, P.pc, P.inverse);
             env.sync();
@@ -519,11 +591,11 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             DstGlobal<A> dstg{P.out + b * P.out_dist};
             if constexpr (kRing) {
                 auto f = [&](int i) { return A::load(srow[i]); };
-                run_c2r_first_paired<A, PT::D>(t, active, f, b1, tw, P.pc, P.stw, P.inverse, []() {});
+                run_c2r_first_paired<A, PT::D>(t, active, f, b1, tw, P.pc, P.stw, hst, P.inverse, []() {});
             } else {
                 const C* row = P.in + b * P.in_dist;
                 auto f = [&](int i) { return A::load(ld_stream(row + i)); };
-                run_c2r_first_paired<A, PT::D>(t, active, f, b1, tw, P.pc, P.stw, P.inverse, []() {});
+                run_c2r_first_paired<A, PT::D>(t, active, f, b1, tw, P.pc, P.stw, hst, P.inverse, []() {});
             }
             env.sync();
             recycle();
@@ -747,6 +819,7 @@ KF_HD void fastconv_body(const FCParams<A>& P, Env& env)
     typedef cx<typename A::R> X;
     static_assert(!A::kFixed, "fast convolution is float/double only (reference: kiss_fastfir.c:152)");
     static_assert(D.R(0) == D.R(D.G - 1) && D.iters(0) == D.iters(D.G - 1), "fast convolution needs a palindromic plan");
+    static_assert(D.hoist == 0, "the fast-convolution kernel does not hoist tables");
     constexpr int GL = D.G - 1, R = D.R(GL), IT = D.iters(GL), M = D.items(GL);
     constexpr int kPitch = D.pitch();
     C* const smem = reinterpret_cast<C*>(env.smem());

@@ -45,6 +45,7 @@ struct TwTab {
     const C* gtw;   // per-group stage-twiddle tables [g][slot][work item] (PlanDesc::slot), exact copies of tw[] entries
     const X* g0;    // group 0's slots (kernel parameter space)
     const X* ctw;   // split-twiddle constants (kernel parameter space), PlanDesc::cslot
+    const X* hreg;  // this thread's loop-invariant stage twiddles (registers), PlanDesc::hoist_base; null when not hoisted
     KF_HD X get(int idx) const
     {
         // all storage complexes are plain {S r, i}; load as one vector
@@ -78,12 +79,32 @@ struct PlanConsts {
     cx<typename A::R> yb;     // tw[2N/5]
 };
 
-// stage twiddle of slot `slot` (compile-time) for work item w of group g
-template <class A, PlanDesc D, int g>
+// stage twiddle of slot `slot` (compile-time) for work item w of group g.  HB >= 0: the thread fetched this item's
+// twiddles into registers before its tile loop (fused_body, PlanDesc::hoist) and HB is their base index in tw.hreg.
+template <class A, PlanDesc D, int g, int HB = -1>
 KF_HD cx<typename A::R> stage_tw(const TwTab<A>& tw, int slot, int w)
 {
     if constexpr (g == 0) return tw.g0[slot];
+    else if constexpr (HB >= 0) return tw.hreg[HB + slot];
     else return A::load(TwTab<A>::ro_load_c(tw.gtw + (D.gtw_offset(g) + slot * D.items(g)) + w));
+}
+
+// fetches the stage twiddles of work item w of group g (the slots run_stage reads from the table) into hreg[HB ...]
+template <class A, PlanDesc D, int g, int HB>
+KF_HD void hoist_item(const TwTab<A>& tw, int w, cx<typename A::R>* hreg)
+{
+    static_for<D.glen[g]>([&](auto SS) {
+        constexpr int s = D.s_hi(g) - decltype(SS)::value;
+        static_for<D.R(g)>([&](auto E) {
+            constexpr int e = decltype(E)::value;
+            if constexpr (D.slot_fetched(g, s, e, A::kFixed)) {
+                static_for<D.p[s] - 1>([&](auto Q) {
+                    constexpr int slot = D.slot(g, s, e) + decltype(Q)::value;
+                    hreg[HB + slot] = stage_tw<A, D, g>(tw, slot, w);
+                });
+            }
+        });
+    });
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -115,7 +136,7 @@ KF_HD void bfly_generic_fixed(cx<typename A::R>* v, int ks, const TwTab<A>& tw)
 // twiddles are applied first (p-1 products, as the radix-2..5 butterflies do) and the remaining constant
 // p-point DFT uses the conjugate symmetry W_p^(p-j) = conj(W_p^j): outputs q1 and p-q1 share their sums.
 // Same operands, different association => equal up to rounding (parity is relative-RMS for float/double).
-template <class A, PlanDesc D, int g, int p, bool TW1>
+template <class A, PlanDesc D, int g, int p, bool TW1, int HB = -1>
 KF_HD void bfly_generic_float(cx<typename A::R>* v, int slot0, int w, const TwTab<A>& tw)
 {
     constexpr int N = D.N;
@@ -127,7 +148,7 @@ KF_HD void bfly_generic_float(cx<typename A::R>* v, int slot0, int w, const TwTa
     y[0] = v[0];
     static_for<p - 1>([&](auto Qm1) {
         constexpr int q = decltype(Qm1)::value + 1;
-        y[q] = TW1 ? v[q] : A::cmul_bf(v[q], stage_tw<A, D, g>(tw, slot0 + q - 1, w));
+        y[q] = TW1 ? v[q] : A::cmul_bf(v[q], stage_tw<A, D, g, HB>(tw, slot0 + q - 1, w));
     });
     X a[h + 1], b[h + 1];
     X sum = y[0];
@@ -159,7 +180,7 @@ KF_HD void bfly_generic_float(cx<typename A::R>* v, int slot0, int w, const TwTa
 // ---------------------------------------------------------------------------------------------------------
 // one radix stage s of group g applied to the R(g) registers of a work item whose k' is `kp`
 // ---------------------------------------------------------------------------------------------------------
-template <class A, PlanDesc D, int g, int s>
+template <class A, PlanDesc D, int g, int s, int HB = -1>
 KF_HD void run_stage(cx<typename A::R>* v, int kp, int w, const TwTab<A>& tw, const PlanConsts<A>& pc, typename A::R sg)
 {
     typedef cx<typename A::R> X;
@@ -181,9 +202,9 @@ KF_HD void run_stage(cx<typename A::R>* v, int kp, int w, const TwTab<A>& tw, co
             auto T = [&](int q) {
                 if constexpr (kSplit) {
                     constexpr int sl0 = D.slot(g, s, e - D.upper_base(g, s, up));
-                    return A::cmul(stage_tw<A, D, g>(tw, sl0 + q - 1, w), tw.ctw[D.cslot(g, s, up, 1) + q - 1]);
+                    return A::cmul(stage_tw<A, D, g, HB>(tw, sl0 + q - 1, w), tw.ctw[D.cslot(g, s, up, 1) + q - 1]);
                 } else {
-                    return stage_tw<A, D, g>(tw, sl + q - 1, w);
+                    return stage_tw<A, D, g, HB>(tw, sl + q - 1, w);
                 }
             };
             if constexpr (p == 2) {
@@ -197,18 +218,18 @@ KF_HD void run_stage(cx<typename A::R>* v, int kp, int w, const TwTab<A>& tw, co
             } else if constexpr (A::kFixed) {
                 bfly_generic_fixed<A, D.N, p, Fs, ms>(x, ks, tw);
             } else {
-                bfly_generic_float<A, D, g, p, kTw1>(x, sl, w, tw);
+                bfly_generic_float<A, D, g, p, kTw1, HB>(x, sl, w, tw);
             }
             static_for<p>([&](auto Q) { constexpr int q = decltype(Q)::value; v[e + q * Ws] = x[q]; });
         }
     });
 }
 
-template <class A, PlanDesc D, int g, int s>
+template <class A, PlanDesc D, int g, int s, int HB = -1>
 KF_HD void run_stages_from(cx<typename A::R>* v, int kp, int w, const TwTab<A>& tw, const PlanConsts<A>& pc, typename A::R sg)
 {
-    run_stage<A, D, g, s>(v, kp, w, tw, pc, sg);
-    if constexpr (s > D.s_lo(g)) run_stages_from<A, D, g, s - 1>(v, kp, w, tw, pc, sg);
+    run_stage<A, D, g, s, HB>(v, kp, w, tw, pc, sg);
+    if constexpr (s > D.s_lo(g)) run_stages_from<A, D, g, s - 1, HB>(v, kp, w, tw, pc, sg);
 }
 
 KF_HD int phys_rt(int a, int logpad) { return logpad >= 31 ? a : a + (a >> logpad); }
@@ -238,10 +259,10 @@ KF_HD void item_load(int w, const typename A::C* rd, cx<typename A::R>* v)
 }
 
 // the radix stages of group g on the registers of work item w
-template <class A, PlanDesc D, int g>
+template <class A, PlanDesc D, int g, int HB = -1>
 KF_HD void item_stages(int w, cx<typename A::R>* v, const TwTab<A>& tw, const PlanConsts<A>& pc, typename A::R sg)
 {
-    run_stages_from<A, D, g, D.s_hi(g)>(v, w / D.Flo(g), w, tw, pc, sg);
+    run_stages_from<A, D, g, D.s_hi(g), HB>(v, w / D.Flo(g), w, tw, pc, sg);
 }
 
 // the outputs of work item w of group g < G-1, written to the exchange buffer the next group reads
@@ -281,7 +302,9 @@ KF_HD void run_group(int t, bool active, const Src& src, const Dst& dst, const t
             } else {
                 item_load<A, D, g>(w, rd, v);
             }
-            item_stages<A, D, g>(w, v, tw, pc, sg);
+            // hoisted stage twiddles (ordinary groups >= 1 only; the item a thread runs in iteration `it` never changes)
+            constexpr int kHB = ((D.hoist & 2) && g >= 1) ? D.hoist_base(g, it) : -1;
+            item_stages<A, D, g, kHB>(w, v, tw, pc, sg);
             if constexpr (kLast) {
                 static_for<R>([&](auto E) {
                     constexpr int e = decltype(E)::value;

@@ -131,14 +131,6 @@ static int launch_fused(kfcu_plan* pl, KParams<AT>& P, cudaStream_t st)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, D.threads(), smem);
         if (e != cudaSuccess) return (int)e;
         if (nb < 1) return (int)cudaErrorLaunchOutOfResources;
-        if constexpr (D.maxblocks > 0) {
-            // fewer resident CTAs than would fit: shrink the shared-memory carve-out to what they need, the rest is L1
-            if (nb > D.maxblocks) {
-                nb = D.maxblocks;
-                const int pct = (int)(((size_t)nb * (smem + 1024) * 100 + 233471) / 233472);
-                cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
-            }
-        }
         blocks_per_sm[dev] = nb;
     }
     const long long ntiles = (P.howmany + D.tpc - 1) / D.tpc;

@@ -49,11 +49,9 @@ struct PlanDesc {
     int paired;             // real transforms on work-item pairs.  kiss_fftr plan: the last group runs items k' and m-k' in the
                             // same thread, so every bin pair (k, nc-k) of the split post pass is complete in its registers;
                             // kiss_fftri plan: the first group runs items u and W-u, reading every spectrum pair once
-    int maxblocks;          // 0: as many CTAs per SM as fit.  n > 0: at most n, with the shared-memory carve-out sized for n
-                            // CTAs so that the rest of the SM's 256 KB stays L1 (the twiddle tables live there); host side only
-    int pairperm;           // paired groups: which pairs the lanes of a warp take.  0: lane l takes pair l of the warp's block of 32;
-                            // 1: lanes 0-15 take the even pairs, lanes 16-31 the odd ones (keeps the mirrored item's
-                            // shared-memory accesses conflict-free when its group has 8 points, tools/bank_model.py)
+    int hoist;              // loop-invariant tables kept in registers across the tiles of a persistent CTA (a thread always runs
+                            // the same work items): bit 0 = split twiddles of the paired real pass, bit 1 = stage twiddles of
+                            // the unpaired groups >= 1, bit 2 = stage twiddles of the paired group
     int nbuf;               // exchange buffers: 2 = ping-pong (default); 1 = single buffer: two-group plans in the C2C /
                             // column modes (+ one barrier per tile; halves shared memory => wider column tiles), or
                             // three-group paired real plans, where the input stage doubles as the second buffer
@@ -149,6 +147,22 @@ struct PlanDesc {
         for (int gg = 1; gg < G; ++gg)
             for (int j = s_lo(gg); j <= s_hi(gg); ++j) n += nctw_stage(gg, j);
         return n;
+    }
+    // ---- loop-invariant twiddles kept in registers (PlanDesc::hoist) ------------------------------------------------
+    // hreg[hoist_base(g, ord) + slot]: stage twiddle `slot` of the ord-th work item a thread runs in group g >= 1
+    // (ord = iteration for ordinary groups; 2*iteration + {0, 1} for the items (u, m-u) of a paired group)
+    KF_CE int hoist_ords(int g) const { return 2 * iters(g); }
+    KF_CE int hoist_base(int g, int ord) const
+    {
+        int n = 0;
+        for (int j = 1; j < g; ++j) n += hoist_ords(j) * nslots(j);
+        return n + ord * nslots(g);
+    }
+    KF_CE int hoist_total() const { return G >= 2 ? hoist_base(G - 1, hoist_ords(G - 1)) : 0; }
+    // is slot set (g, s, e) fetched from the table at run time?  (split mode derives the upper != 0 ones)
+    KF_CE bool slot_fetched(int g, int s, int e, bool fixed) const
+    {
+        return digit(g, s, e) == 0 && (fixed || twmode != 1 || e / (W(g, s) * p[s]) == 0);
     }
     // register index of the first element whose upper digits (stages above s) form combination `up`
     KF_CE int upper_base(int g, int s, int up) const { return up * W(g, s) * p[s]; }

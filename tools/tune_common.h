@@ -17,7 +17,7 @@ typedef AT::C CT;
 struct TuneEntry {
     long long (*rows_ok)(const kf::KParams<AT>&);
     std::string label;
-    int threads, tpc, maxblocks;
+    int threads, tpc;
     size_t smem;
     const void* kernel;
     void (*launch)(const kf::KParams<AT>&, unsigned grid, size_t smem);
@@ -54,7 +54,6 @@ static TuneEntry make_entry(const char* label)
     e.launch = launch_variant<PT, MODE>;
     e.prepare = prepare_variant<PT>;
     e.rows_ok = kf::fused_rows<AT, PT, MODE>;
-    e.maxblocks = PT::D.maxblocks;
     return e;
 }
 
@@ -155,11 +154,6 @@ static int tune_main(int argc, char** argv, std::vector<TuneEntry>& vars, int nf
         int nb = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.kernel, v.threads, v.smem));
         if (nb < 1) { printf("{\"variant\": \"%s\", \"error\": \"does not fit\"}\n", v.label.c_str()); continue; }
-        if (v.maxblocks > 0 && nb > v.maxblocks) {   // cap the resident CTAs and give the spare shared memory back to L1
-            nb = v.maxblocks;
-            const int pct = (int)(((size_t)nb * (v.smem + 1024) * 100 + 233471) / 233472);
-            CK(cudaFuncSetAttribute(v.kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
-        }
         cudaFuncAttributes fa;
         CK(cudaFuncGetAttributes(&fa, v.kernel));
         const long long ntiles = (batch + v.tpc - 1) / v.tpc;

@@ -46,12 +46,12 @@ def gen(spec):
         src = HEAD % {"root": ROOT}
         for j, v in enumerate(chunk):
             idx = ci + j
-            src += "struct V%d { static constexpr PlanDesc D = make_plan(%d, %s, %s, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d); };\n" % (
-                idx, spec["nfft"], lst(v.get("radices", spec["radices"])), lst(v["groups"]), v["team"], v["tpc"], v["logpad"], v["minblocks"], v.get("nstage", 0), v.get("nbuf", 2), v.get("twmode", 0), v.get("shfl", 0), v.get("paired", 0), v.get("pairperm", 0), v.get("maxblocks", 0))
+            src += "struct V%d { static constexpr PlanDesc D = make_plan(%d, %s, %s, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d); };\n" % (
+                idx, spec["nfft"], lst(v.get("radices", spec["radices"])), lst(v["groups"]), v["team"], v["tpc"], v["logpad"], v["minblocks"], v.get("nstage", 0), v.get("nbuf", 2), v.get("twmode", 0), v.get("shfl", 0), v.get("paired", 0), v.get("hoist", 0))
         src += "void register_chunk_%d(std::vector<TuneEntry>& out) {\n" % (ci // nper)
         for j, v in enumerate(chunk):
             idx = ci + j
-            label = "r%s_g%s_t%d_c%d_p%d_b%d_s%d_n%d_w%d_x%d_q%d%s%s" % ("".join(map(str, v.get("radices", spec["radices"]))), "".join(map(str, v["groups"])), v["team"], v["tpc"], v["logpad"], v["minblocks"], v.get("nstage", 0), v.get("nbuf", 2), v.get("twmode", 0), v.get("shfl", 0), v.get("paired", 0), "_m1" if v.get("pairperm", 0) else "", "_k%d" % v["maxblocks"] if v.get("maxblocks", 0) else "")
+            label = "r%s_g%s_t%d_c%d_p%d_b%d_s%d_n%d_w%d_x%d_q%d%s" % ("".join(map(str, v.get("radices", spec["radices"]))), "".join(map(str, v["groups"])), v["team"], v["tpc"], v["logpad"], v["minblocks"], v.get("nstage", 0), v.get("nbuf", 2), v.get("twmode", 0), v.get("shfl", 0), v.get("paired", 0), "_h%d" % v["hoist"] if v.get("hoist", 0) else "")
             src += '    out.push_back(make_entry<V%d, k%s>("%s"));\n' % (idx, spec["mode"], label)
         src += "}\n"
         path = os.path.join(BUILD, "tune_%s_%d.cu" % (name, ci // nper))
