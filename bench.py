@@ -417,12 +417,12 @@ def measure_slab(name, args, dist, rank, world, t1_ms):
     """slab-sharded 3-D transform (strong scaling) on all ranks, fenced per-step timing like everything else; parity by
     SURVEY 8(d) sampling: 32 bins of the distributed output vs float64 direct DFT sums all-reduced over the slabs"""
     import torch
-    from kissfft_b200.slab import SlabFFT3D
+    from kissfft_b200.slab import MgpuFFT3D
     w = WORKLOADS[name]
     dims = w["dims"]
-    plan = SlabFFT3D(dims, tname=w["tname"], p2p=w.get("p2p", False))
+    plan = MgpuFFT3D(dims, tname=w["tname"], p2p=w.get("p2p", False))     # the library's C-ABI (kiss_fftnd_mgpu_*)
     g = plan.geo
-    sx, ssend, srecv, sout = plan.alloc()
+    sx, sout = plan.alloc()
     synth = Synth(w["tname"], 999 + rank)
     x0 = synth(tuple(sx.shape))
     sx.copy_(x0)
@@ -432,7 +432,7 @@ def measure_slab(name, args, dist, rank, world, t1_ms):
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
-    plan.forward(sx, ssend, srecv, sout, stream)
+    plan.forward(sx, sout, stream)
     barrier()
     # parity on the result of THIS call (the timed loop below re-transforms sx in place, like the r01 bench did)
     gcpu = torch.Generator(device="cpu")
@@ -458,7 +458,7 @@ def measure_slab(name, args, dist, rank, world, t1_ms):
     pars = abs(float(tot[1]) / (float(np.prod(dims)) * float(tot[0])) - 1.0)
     tol = 1e-6 * math.log2(float(np.prod(dims)))
     del x0
-    total, per = time_kernels([("slab3d", lambda: plan.forward(sx, ssend, srecv, sout, stream))], args.steps, args.warmup, barrier)
+    total, per = time_kernels([("slab3d", lambda: plan.forward(sx, sout, stream))], args.steps, args.warmup, barrier)
     t = torch.tensor([total / args.steps], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
@@ -466,6 +466,8 @@ def measure_slab(name, args, dist, rank, world, t1_ms):
     peak, _ = measured_peak()
     local_bytes = algorithmic_bytes(w) * 3 // world
     out = {"workload": w["desc"], "dtype": DTYPE_NAME[w["tname"]], "ms": ms, "scaling": "strong",
+           "api": "kiss_fftnd_mgpu_exec (C-ABI)", "exchange": "peer stores over NVLink (CUDA IPC)" if plan.info["p2p"] else "NCCL grouped send/recv",
+           "pipeline_chunks": plan.info["chunks"],
            "gflops": flops_per_step(w) / (ms * 1e-3) / 1e9,
            "parity": "32 sampled bins vs float64 DFT sums rel-rms %.2e, Parseval defect %.1e (<= %.1e)" % (err, pars, tol),
            "parity_ok": bool(err <= tol and pars <= tol),
@@ -476,7 +478,8 @@ def measure_slab(name, args, dist, rank, world, t1_ms):
     if t1_ms:
         out["t1_ms_single_gpu_same_run"] = t1_ms
         out["strong_scaling_efficiency"] = t1_ms / (world * ms)
-    del plan, sx, ssend, srecv, sout
+    plan.close()
+    del plan, sx, sout
     torch.cuda.empty_cache()
     return out
 
@@ -548,11 +551,11 @@ def run_ours(args, w, rank, world, local_rank):
             lib.fft_batch(cf, p_x, p_X, b)
         h2d = d2h = h_x.numel() * h_x.element_size()
     elif w["kind"] == "slab":
-        from kissfft_b200.slab import SlabFFT3D
-        plan = SlabFFT3D(w["dims"], tname=w["tname"], p2p=w.get("p2p", False))
-        sx, ssend, srecv, sout = plan.alloc()
+        from kissfft_b200.slab import MgpuFFT3D
+        plan = MgpuFFT3D(w["dims"], tname=w["tname"], p2p=w.get("p2p", False))
+        sx, sout = plan.alloc()
         sx.copy_(synth(tuple(sx.shape)))
-        kernels = [("slab3d", lambda: plan.forward(sx, ssend, srecv, sout, stream))]
+        kernels = [("slab3d", lambda: plan.forward(sx, sout, stream))]
     else:
         dims = w["dims"]
         d_x = synth(tuple(dims) + (2,))

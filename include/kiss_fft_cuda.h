@@ -7,9 +7,15 @@
  *
  * Conventions
  *   - `*_dev` functions take CUDA device pointers and a cudaStream_t (passed as void*, NULL = default stream);
- *     they enqueue work and return without synchronising.
- *   - functions without the suffix take HOST pointers, stage through pinned memory with copy/compute overlap,
- *     and return when the result is in the output buffer.
+ *     they enqueue work and return without synchronising -- EXCEPT where they need internal scratch memory that goes
+ *     back to a shared pool: rows longer than the shared-memory kernels hold (nfft > ~14.5 k complex float),
+ *     kiss_fftnd_dev with d_work == NULL when an axis has no layout-keeping plan, kiss_fftndri_dev, kiss_fftndr_dev in
+ *     that same fallback case, and the unfused fast convolution.  Those wait for the stream before returning.
+ *   - functions without the suffix take HOST pointers and return when the result is in the output buffer.  The batch is
+ *     cut into chunks that move through parallel lanes (H2D, kernel, D2H on one stream per lane).  Pinned (or
+ *     cudaHostRegister-ed) caller buffers are handed to the copy engines directly; ordinary pageable buffers -- what
+ *     callers of the reference pass -- are bounced through internal pinned buffers by the lanes' host threads, so both
+ *     copy directions and the kernels still overlap (a cudaMemcpyAsync on pageable memory would not).
  *   - distances (`*_dist`) are in elements of the respective side (kiss_fft_cpx for complex rows,
  *     kiss_fft_scalar for real rows); real-row distances and real device pointers must be even / 2*sizeof(scalar)
  *     aligned because a real row is read as packed complex (kiss_fftr.c:77).
@@ -72,30 +78,80 @@ int KISS_FFT_API kiss_fft_planes_pass_peers_dev(kiss_fft_cfg cfg, const kiss_fft
                                                 int npeers, size_t nplanes, size_t cols_per_peer, size_t col_stride,
                                                 size_t in_plane_dist, size_t out_plane_dist, void *stream);
 
+/* the same with the peers' column blocks spread out in the input: block s reads the input columns
+ * s*peer_col_dist + [0, cols_per_peer) of every plane (peer_col_dist >= cols_per_peer).  Lets one launch handle a CHUNK
+ * of every destination's column range, so that the exchange pipelines chunk by chunk (kiss_fftnd_mgpu_exec). */
+int KISS_FFT_API kiss_fft_planes_pass_peers2_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *const *d_peers,
+                                                 int npeers, size_t nplanes, size_t cols_per_peer, size_t peer_col_dist,
+                                                 size_t col_stride, size_t in_plane_dist, size_t out_plane_dist, void *stream);
+
 /* kiss_fftndr / kiss_fftndri on device buffers (kiss_fftndr.c:86-132) */
 int KISS_FFT_API kiss_fftndr_dev(kiss_fftndr_cfg cfg, const kiss_fft_scalar *d_time, kiss_fft_cpx *d_freq, void *stream);
 int KISS_FFT_API kiss_fftndri_dev(kiss_fftndr_cfg cfg, const kiss_fft_cpx *d_freq, kiss_fft_scalar *d_time, void *stream);
 
-/* ---- host-pointer batched (pinned staging + H2D / kernel / D2H overlap) ----------------------------------- */
+/* ---- kiss_fftnd over several GPUs: slab decomposition, ONE PROCESS PER GPU ---------------------------
+ * The reference's kiss_fftnd (kiss_fftnd.c:156-188) transforms one array in one address space.  Here a 3-D array
+ * d0 x d1 x d2 is distributed in slabs of d0/G planes: rank r holds x[r*d0/G .. (r+1)*d0/G)[d1][d2].  One exchange
+ * (all-to-all) is needed; the result comes out "transposed": rank r holds X[k0][k1][k2] for k2 in [r*d2/G, (r+1)*d2/G)
+ * stored as d_out[k2 - r*d2/G][k1][k0].  dims[0] and dims[2] must be divisible by G (G <= 16).
+ *
+ *   kiss_fftnd_mgpu_get_id   rank 0 only: fills a KISS_FFT_MGPU_ID_BYTES rendezvous id (an ncclUniqueId); the caller
+ *                            distributes it to the other ranks by whatever it has (MPI_Bcast, a pipe, a file, ...)
+ *   kiss_fftnd_mgpu_alloc    COLLECTIVE; current CUDA device = this rank's GPU.  flags: KISS_FFT_MGPU_P2P asks for the
+ *                            fused exchange -- the column-pass kernel stores its rows straight into the other ranks'
+ *                            receive buffers over NVLink (buffers mapped with CUDA IPC: all ranks on one node) -- and
+ *                            falls back to NCCL (grouped ncclSend/ncclRecv per chunk, libnccl.so.2 loaded at run time)
+ *                            when peer mapping is not possible; kiss_fftnd_mgpu_uses_p2p() tells which one is active.
+ *                            nranks == 1 needs neither NCCL nor an id.
+ *   kiss_fftnd_mgpu_exec     COLLECTIVE, stream-ordered on `stream`: d_in is overwritten (its rows are transformed in
+ *                            place, like kiss_fft with fin == fout); d_out receives the transposed-out slab.
+ *   kiss_fftnd_mgpu_free     COLLECTIVE. */
+#define KISS_FFT_MGPU_ID_BYTES 128
+#define KISS_FFT_MGPU_P2P 1u
+typedef struct kiss_fftnd_mgpu_state *kiss_fftnd_mgpu_cfg;
+int KISS_FFT_API kiss_fftnd_mgpu_get_id(void *id);
+kiss_fftnd_mgpu_cfg KISS_FFT_API kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int inverse_fft, int rank, int nranks,
+                                                       const void *id, unsigned flags);
+int KISS_FFT_API kiss_fftnd_mgpu_exec(kiss_fftnd_mgpu_cfg cfg, kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, void *stream);
+void KISS_FFT_API kiss_fftnd_mgpu_free(kiss_fftnd_mgpu_cfg cfg);
+/* complex elements of this rank's input / output slab; 1 when the peer-store exchange is active; chunks the exchange is
+ * pipelined in; bytes this rank sends to other ranks per exec (NVLink roofline numerator); last error of this thread */
+size_t KISS_FFT_API kiss_fftnd_mgpu_local_in_elems(kiss_fftnd_mgpu_cfg cfg);
+size_t KISS_FFT_API kiss_fftnd_mgpu_local_out_elems(kiss_fftnd_mgpu_cfg cfg);
+int KISS_FFT_API kiss_fftnd_mgpu_uses_p2p(kiss_fftnd_mgpu_cfg cfg);
+int KISS_FFT_API kiss_fftnd_mgpu_chunks(kiss_fftnd_mgpu_cfg cfg);
+size_t KISS_FFT_API kiss_fftnd_mgpu_a2a_bytes(kiss_fftnd_mgpu_cfg cfg);
+const char KISS_FFT_API *kiss_fftnd_mgpu_last_error(void);
+
+/* ---- host-pointer batched (parallel lanes of H2D / kernel / D2H, pinned bounce buffers for pageable memory) --- */
 int KISS_FFT_API kiss_fft_batch(kiss_fft_cfg cfg, const kiss_fft_cpx *in, kiss_fft_cpx *out, size_t howmany);
 int KISS_FFT_API kiss_fftr_batch(kiss_fftr_cfg cfg, const kiss_fft_scalar *timedata, kiss_fft_cpx *freqdata, size_t howmany);
 int KISS_FFT_API kiss_fftri_batch(kiss_fftr_cfg cfg, const kiss_fft_cpx *freqdata, kiss_fft_scalar *timedata, size_t howmany);
 
-/* ---- fused fast convolution (float / double builds only, like the reference: kiss_fastfir.c:152) ------------------
- * The overlap-scrap FIR filter of the reference's tools/kiss_fastfir.c (complex-sample build): FFT -> multiply by the
- * filter's frequency response -> IFFT for every block, fused into ONE kernel (the spectrum never leaves the SM).
- *   kiss_fastconv_alloc   kiss_fastfir_alloc (kiss_fastfir.c:59-165): *pnfft == 0 picks the reference's default size
- *   kiss_fastconv_dev     kff_nocopy / fastconv1buf (kiss_fastfir.c:167-206) on device buffers: processes every complete
- *                         nfft-sample block of the n input samples, block b reading d_in + b*ngood and writing ngood
- *                         samples at d_out + b*ngood (ngood = nfft - n_imp_resp + 1); *nprocessed = blocks*ngood. */
+/* ---- fast convolution (float / double builds only, like the reference: kiss_fastfir.c:152) ---------------------------
+ * The overlap-scrap FIR filter of the reference's tools/kiss_fastfir.c: FFT -> multiply by the filter's frequency response
+ * -> IFFT for every block.
+ *   kiss_fastconv_alloc   kiss_fastfir_alloc (kiss_fastfir.c:59-165), complex samples: *pnfft == 0 picks the reference's
+ *                         default size; any nfft the transforms accept
+ *   kiss_fastconvr_alloc  the same for the reference's REAL_FASTFIR build (real samples and impulse response,
+ *                         kiss_fftr / kiss_fftri, nfft/2+1 bins; nfft even)
+ *   kiss_fastconv_dev /   kff_nocopy / fastconv1buf (kiss_fastfir.c:167-206) on device buffers: processes every complete
+ *   kiss_fastconvr_dev    nfft-sample block of the n input samples, block b reading d_in + b*ngood and writing ngood
+ *                         samples at d_out + b*ngood (ngood = nfft - n_imp_resp + 1); *nprocessed = blocks*ngood.
+ * Complex samples with nfft in {256, 512, 1024, 2048, 4096} run as ONE fused kernel (the spectrum never leaves the SM),
+ * stream-ordered.  Every other case -- other lengths, real samples -- is composed from separate launches (block gather,
+ * batched transform, pointwise product, batched inverse, clipped copy) over internal scratch and waits for the stream. */
 #ifndef FIXED_POINT
 typedef struct kiss_fastconv_state *kiss_fastconv_cfg;
 kiss_fastconv_cfg KISS_FFT_API kiss_fastconv_alloc(const kiss_fft_cpx *imp_resp, size_t n_imp_resp, size_t *pnfft);
+kiss_fastconv_cfg KISS_FFT_API kiss_fastconvr_alloc(const kiss_fft_scalar *imp_resp, size_t n_imp_resp, size_t *pnfft);
 void KISS_FFT_API kiss_fastconv_free(kiss_fastconv_cfg cfg);
 size_t KISS_FFT_API kiss_fastconv_block_advance(kiss_fastconv_cfg cfg);
 size_t KISS_FFT_API kiss_fastconv_nfft(kiss_fastconv_cfg cfg);
 int KISS_FFT_API kiss_fastconv_dev(kiss_fastconv_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, size_t n,
                                    size_t *nprocessed, void *stream);
+int KISS_FFT_API kiss_fastconvr_dev(kiss_fastconv_cfg cfg, const kiss_fft_scalar *d_in, kiss_fft_scalar *d_out, size_t n,
+                                    size_t *nprocessed, void *stream);
 #endif
 
 /* ---- introspection ---------------------------------------------------------------------------------------- */
@@ -103,7 +159,8 @@ const char KISS_FFT_API *kiss_fft_cuda_last_error(void);
 /* kernels launched by this library since it was loaded */
 long long KISS_FFT_API kiss_fft_cuda_launch_count(void);
 /* 1 when nfft has a compile-time fused plan (single HBM round trip) in this build, 0 when it runs on the
- * run-time shared-memory kernel, -1 when it is not supported */
+ * run-time shared-memory kernel, 2 when it is longer than those hold and takes the long-row paths (four-step or one
+ * radix stage per launch), -1 for nfft <= 0 */
 int KISS_FFT_API kiss_fft_cuda_plan_kind(int nfft);
 /* testing aid: route every length through the run-time shared-memory kernel (1) or restore the default (0) */
 void KISS_FFT_API kiss_fft_cuda_force_generic(int on);

@@ -23,6 +23,10 @@ API_SYMBOLS = (
     "kiss_fftndr_alloc", "kiss_fftndr", "kiss_fftndri",
     "kfc_fft", "kfc_ifft", "kfc_cleanup",
     "kiss_fft_batch_dev", "kiss_fftr_batch_dev", "kiss_fftri_batch_dev", "kiss_fftnd_dev", "kiss_fft_axis_pass_dev", "kiss_fft_planes_pass_dev", "kiss_fft_planes_pass_peers_dev",
+    "kiss_fft_planes_pass_peers2_dev",
+    "kiss_fftnd_mgpu_get_id", "kiss_fftnd_mgpu_alloc", "kiss_fftnd_mgpu_exec", "kiss_fftnd_mgpu_free", "kiss_fftnd_mgpu_local_in_elems",
+    "kiss_fftnd_mgpu_local_out_elems", "kiss_fftnd_mgpu_uses_p2p", "kiss_fftnd_mgpu_chunks", "kiss_fftnd_mgpu_a2a_bytes",
+    "kiss_fftnd_mgpu_last_error",
     "kiss_fftndr_dev", "kiss_fftndri_dev", "kiss_fft_batch", "kiss_fftr_batch", "kiss_fftri_batch",
     "kiss_fft_cuda_last_error", "kiss_fft_cuda_launch_count", "kiss_fft_cuda_plan_kind", "kiss_fft_cuda_scalar_bytes",
     "kiss_fft_cuda_is_fixed_point", "kiss_fft_cuda_force_generic", "kiss_fft_cuda_set_grid_limit",
@@ -30,8 +34,8 @@ API_SYMBOLS = (
 
 
 # float / double builds only (the reference's fast FIR "won't work for fixed point", kiss_fastfir.c:152)
-FASTCONV_SYMBOLS = ("kiss_fastconv_alloc", "kiss_fastconv_free", "kiss_fastconv_block_advance", "kiss_fastconv_nfft",
-                    "kiss_fastconv_dev")
+FASTCONV_SYMBOLS = ("kiss_fastconv_alloc", "kiss_fastconvr_alloc", "kiss_fastconv_free", "kiss_fastconv_block_advance",
+                    "kiss_fastconv_nfft", "kiss_fastconv_dev", "kiss_fastconvr_dev")
 
 
 def lib_path(tname):
@@ -93,6 +97,19 @@ class KissFFT:
         L.kiss_fft_axis_pass_dev.argtypes = [vp, vp, vp, sz, sz, vp]
         L.kiss_fft_planes_pass_dev.argtypes = [vp, vp, vp, sz, sz, sz, sz, sz, vp]
         L.kiss_fft_planes_pass_peers_dev.argtypes = [vp, vp, ctypes.POINTER(vp), ci, sz, sz, sz, sz, sz, vp]
+        L.kiss_fft_planes_pass_peers2_dev.argtypes = [vp, vp, ctypes.POINTER(vp), ci, sz, sz, sz, sz, sz, sz, vp]
+        L.kiss_fftnd_mgpu_get_id.argtypes = [vp]
+        L.kiss_fftnd_mgpu_alloc.restype = vp
+        L.kiss_fftnd_mgpu_alloc.argtypes = [ctypes.POINTER(ci), ci, ci, ci, ci, vp, ctypes.c_uint]
+        L.kiss_fftnd_mgpu_exec.argtypes = [vp, vp, vp, vp]
+        L.kiss_fftnd_mgpu_free.argtypes = [vp]
+        L.kiss_fftnd_mgpu_free.restype = None
+        for name in ("kiss_fftnd_mgpu_local_in_elems", "kiss_fftnd_mgpu_local_out_elems", "kiss_fftnd_mgpu_a2a_bytes"):
+            getattr(L, name).argtypes = [vp]
+            getattr(L, name).restype = sz
+        for name in ("kiss_fftnd_mgpu_uses_p2p", "kiss_fftnd_mgpu_chunks"):
+            getattr(L, name).argtypes = [vp]
+        L.kiss_fftnd_mgpu_last_error.restype = ctypes.c_char_p
         L.kiss_fftndr_dev.argtypes = [vp, vp, vp, vp]
         L.kiss_fftndri_dev.argtypes = [vp, vp, vp, vp]
         L.kiss_fft_batch.argtypes = [vp, vp, vp, sz]
@@ -115,6 +132,9 @@ class KissFFT:
             L.kiss_fastconv_nfft.argtypes = [vp]
             L.kiss_fastconv_nfft.restype = sz
             L.kiss_fastconv_dev.argtypes = [vp, vp, vp, sz, ctypes.POINTER(sz), vp]
+            L.kiss_fastconvr_alloc.restype = vp
+            L.kiss_fastconvr_alloc.argtypes = [vp, sz, ctypes.POINTER(sz)]
+            L.kiss_fastconvr_dev.argtypes = [vp, vp, vp, sz, ctypes.POINTER(sz), vp]
         self._libc = ctypes.CDLL(None)
         self._libc.free.argtypes = [vp]
         if L.kiss_fft_cuda_scalar_bytes() != np.dtype(self.dtype).itemsize:
@@ -190,6 +210,39 @@ class KissFFT:
                                                             col_stride, in_plane_dist, out_plane_dist,
                                                             ctypes.c_void_p(stream)), "kiss_fft_planes_pass_peers_dev")
 
+    # ---- kiss_fftnd over several GPUs (one process per GPU), include/kiss_fft_cuda.h ----
+    MGPU_P2P = 1
+
+    def mgpu_get_id(self):
+        """rank 0: the 128-byte rendezvous id to hand to every rank's mgpu_alloc"""
+        buf = ctypes.create_string_buffer(128)
+        rc = self.lib.kiss_fftnd_mgpu_get_id(buf)
+        if rc != 0:
+            raise KissFFTError("kiss_fftnd_mgpu_get_id failed (%d): %s" % (rc, (self.lib.kiss_fftnd_mgpu_last_error() or b"").decode()))
+        return buf.raw
+
+    def mgpu_alloc(self, dims, rank, nranks, ident=None, inverse=False, flags=0):
+        arr = (ctypes.c_int * len(dims))(*[int(d) for d in dims])
+        idbuf = ctypes.create_string_buffer(ident, 128) if ident is not None else None
+        cfg = self.lib.kiss_fftnd_mgpu_alloc(arr, len(dims), int(bool(inverse)), int(rank), int(nranks), idbuf, int(flags))
+        if not cfg:
+            raise KissFFTError("kiss_fftnd_mgpu_alloc failed: %s" % (self.lib.kiss_fftnd_mgpu_last_error() or b"").decode())
+        return cfg
+
+    def mgpu_exec(self, cfg, d_in, d_out, stream=0):
+        rc = self.lib.kiss_fftnd_mgpu_exec(cfg, _ptr(d_in), _ptr(d_out), ctypes.c_void_p(stream))
+        if rc != 0:
+            raise KissFFTError("kiss_fftnd_mgpu_exec failed (%d): %s" % (rc, (self.lib.kiss_fftnd_mgpu_last_error() or b"").decode()))
+
+    def mgpu_free(self, cfg):
+        self.lib.kiss_fftnd_mgpu_free(cfg)
+
+    def mgpu_info(self, cfg):
+        L = self.lib
+        return {"in_elems": int(L.kiss_fftnd_mgpu_local_in_elems(cfg)), "out_elems": int(L.kiss_fftnd_mgpu_local_out_elems(cfg)),
+                "p2p": bool(L.kiss_fftnd_mgpu_uses_p2p(cfg)), "chunks": int(L.kiss_fftnd_mgpu_chunks(cfg)),
+                "a2a_bytes": int(L.kiss_fftnd_mgpu_a2a_bytes(cfg))}
+
     def fftndr_dev(self, cfg, d_time, d_freq, stream=0):
         self._check(self.lib.kiss_fftndr_dev(cfg, _ptr(d_time), _ptr(d_freq), ctypes.c_void_p(stream)), "kiss_fftndr_dev")
 
@@ -242,6 +295,21 @@ class KissFFT:
         done = ctypes.c_size_t(0)
         self._check(self.lib.kiss_fastconv_dev(cfg, _ptr(d_in), _ptr(d_out), n, ctypes.byref(done), ctypes.c_void_p(stream)),
                     "kiss_fastconv_dev")
+        return int(done.value)
+
+    def fastconvr_alloc(self, imp_resp, nfft=0):
+        """real samples (the reference's REAL_FASTFIR build): imp_resp is a 1-D array.  Returns (cfg, nfft, ngood)."""
+        imp = np.ascontiguousarray(imp_resp, dtype=self.dtype)
+        n = ctypes.c_size_t(int(nfft))
+        cfg = self.lib.kiss_fastconvr_alloc(_ptr(imp), imp.shape[0], ctypes.byref(n))
+        if not cfg:
+            raise KissFFTError("kiss_fastconvr_alloc failed")
+        return cfg, int(n.value), int(self.lib.kiss_fastconv_block_advance(cfg))
+
+    def fastconvr_dev(self, cfg, d_in, d_out, n, stream=0):
+        done = ctypes.c_size_t(0)
+        self._check(self.lib.kiss_fastconvr_dev(cfg, _ptr(d_in), _ptr(d_out), n, ctypes.byref(done), ctypes.c_void_p(stream)),
+                    "kiss_fastconvr_dev")
         return int(done.value)
 
     def fastconv_free(self, cfg):

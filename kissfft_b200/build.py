@@ -48,7 +48,7 @@ def _stale(target, sources=None):
 
 def _cuda_sources():
     """what the kernel object depends on: everything but the C host layer"""
-    return [s for s in _sources() if not s.endswith("kf_api.c")]
+    return [s for s in _sources() if not s.endswith(".c")]
 
 
 def _host_sources():
@@ -71,15 +71,17 @@ def build_one(tname, force=False, verbose=False):
     tf = TYPEFLAGS[tname]
     o_cu = os.path.join(OBJDIR, "kf_launch-%s.o" % tname)
     o_c = os.path.join(OBJDIR, "kf_api-%s.o" % tname)
+    o_m = os.path.join(OBJDIR, "kf_mgpu-%s.o" % tname)
     if force or _stale(o_cu, _cuda_sources()):
         log = _run([NVCC, "-std=c++20", "--expt-relaxed-constexpr", *ARCH, "-lineinfo", "-O3", "-Xcompiler", "-fPIC,-fvisibility=hidden",
                     "-ccbin", HOSTCXX, "-Xptxas", "-v", "-DKISS_FFT_SHARED", *tf, "-c", os.path.join(CSRC, "kf_launch.cu"), "-o", o_cu])
         if verbose:
             print(log)
-    if force or _stale(o_c, _host_sources()):
-        _run([HOSTCC, "-std=gnu11", "-O2", "-fPIC", "-fvisibility=hidden", "-Wall", "-DKISS_FFT_SHARED", *tf,
-              "-I", os.path.join(CUDA_HOME, "include"), "-c", os.path.join(CSRC, "kf_api.c"), "-o", o_c])
-    _run([NVCC, "-shared", *ARCH, "-ccbin", HOSTCXX, o_cu, o_c, "-o", out, "-lpthread", "-lm"])
+    for src, obj in (("kf_api.c", o_c), ("kf_mgpu.c", o_m)):
+        if force or _stale(obj, _host_sources()):
+            _run([HOSTCC, "-std=gnu11", "-O2", "-fPIC", "-fvisibility=hidden", "-Wall", "-DKISS_FFT_SHARED", *tf,
+                  "-I", os.path.join(CUDA_HOME, "include"), "-c", os.path.join(CSRC, src), "-o", obj])
+    _run([NVCC, "-shared", *ARCH, "-ccbin", HOSTCXX, o_cu, o_c, o_m, "-o", out, "-lpthread", "-lm", "-ldl"])
     return out
 
 

@@ -743,20 +743,29 @@ int kiss_fft_planes_pass_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_ff
     return 0;
 }
 
-int kiss_fft_planes_pass_peers_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *const *d_peers, int npeers,
-                                   size_t nplanes, size_t cols_per_peer, size_t col_stride, size_t in_plane_dist,
-                                   size_t out_plane_dist, void *stream)
+int kiss_fft_planes_pass_peers2_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *const *d_peers, int npeers,
+                                    size_t nplanes, size_t cols_per_peer, size_t peer_col_dist, size_t col_stride,
+                                    size_t in_plane_dist, size_t out_plane_dist, void *stream)
 {
-    if (!cfg || cfg->magic != KF_MAGIC_1D || !d_in || !d_peers || npeers < 1 || npeers > 16 || col_stride < 1) {
+    if (!cfg || cfg->magic != KF_MAGIC_1D || !d_in || !d_peers || npeers < 1 || npeers > 16 || col_stride < 1 ||
+        peer_col_dist < cols_per_peer) {
         KF_ERROR("kiss_fft_planes_pass_peers_dev: bad argument");
         return KISS_FFT_CUDA_EINVAL;
     }
     const kf_devplan *dp;
     KF_CHECK(kf_get_devplan(cfg, NULL, &dp));
     KF_CHECK(kfcu_exec_planes_peers((kfcu_plan *)&dp->plan, d_in, (void *const *)d_peers, npeers, (long long)nplanes,
-                                    (long long)cols_per_peer, (long long)col_stride, (long long)in_plane_dist,
-                                    (long long)out_plane_dist, stream));
+                                    (long long)cols_per_peer, (long long)peer_col_dist, (long long)col_stride,
+                                    (long long)in_plane_dist, (long long)out_plane_dist, stream));
     return 0;
+}
+
+int kiss_fft_planes_pass_peers_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *const *d_peers, int npeers,
+                                   size_t nplanes, size_t cols_per_peer, size_t col_stride, size_t in_plane_dist,
+                                   size_t out_plane_dist, void *stream)
+{
+    return kiss_fft_planes_pass_peers2_dev(cfg, d_in, d_peers, npeers, nplanes, cols_per_peer, cols_per_peer, col_stride, in_plane_dist,
+                                           out_plane_dist, stream);
 }
 
 static int kf_real_args_ok(const void *d_real, size_t real_dist)
@@ -1381,7 +1390,7 @@ int kiss_fft_cuda_plan_kind(int nfft)
 {
     if (nfft <= 0) return -1;
     if (kfcu_has_fused(nfft, KFCU_C2C)) return 1;
-    return nfft <= kfcu_generic_max_nfft() ? 0 : -1;
+    return nfft <= kfcu_generic_max_nfft() ? 0 : 2;
 }
 
 /* ---- kfc: cfg cache (reference kfc.c:13-83) --------------------------------------------------------------- */
@@ -1443,56 +1452,104 @@ void kfc_cleanup(void)
     pthread_mutex_unlock(&g_kfc_lock);
 }
 
-/* ---- fast convolution (reference tools/kiss_fastfir.c, complex-sample build) ------------------------------------ */
+/* ---- fast convolution (reference tools/kiss_fastfir.c: complex-sample build and REAL_FASTFIR build) ------------------ */
 #ifndef FIXED_POINT
 #define KF_MAGIC_FC 0x4b464643u
+#define KF_MAGIC_FCR 0x4b464352u
 struct kiss_fastconv_state {
     uint32_t magic;
-    int nfft, ngood;
+    int nfft, ngood, nbins; /* nbins = nfft (complex samples) or nfft/2+1 (real samples, kiss_fastfir.c:91-95) */
     kiss_fft_cfg fwd, inv;
-    kiss_fft_cpx *h_resp; /* host copy of the scaled frequency response */
-    void *d_resp;         /* device copy (current device at alloc time) */
+    kiss_fftr_cfg rfwd, rinv;
+    void *d_resp;           /* scaled frequency response on the device (current device at alloc time) */
     int device;
 };
+
+/* the reference's default size: next power of two at least twice the impulse response (kiss_fastfir.c:76-84) */
+static size_t kf_fastconv_default_nfft(size_t n_imp_resp)
+{
+    size_t i = n_imp_resp - 1, nfft = 2;
+    do {
+        nfft <<= 1;
+    } while (i >>= 1);
+    return nfft;
+}
 
 kiss_fastconv_cfg kiss_fastconv_alloc(const kiss_fft_cpx *imp_resp, size_t n_imp_resp, size_t *pnfft)
 {
     if (!imp_resp || n_imp_resp < 1) return NULL;
     size_t nfft = pnfft ? *pnfft : 0;
-    if (nfft == 0) { /* next power of two at least twice the impulse response (kiss_fastfir.c:76-84) */
-        size_t i = n_imp_resp - 1;
-        nfft = 2;
-        do {
-            nfft <<= 1;
-        } while (i >>= 1);
-    }
-    if (n_imp_resp > nfft) return NULL;
+    if (nfft == 0) nfft = kf_fastconv_default_nfft(n_imp_resp);
+    if (n_imp_resp > nfft || nfft > (size_t)INT32_MAX) return NULL;
     if (pnfft) *pnfft = nfft;
     kiss_fastconv_cfg st = (kiss_fastconv_cfg)calloc(1, sizeof(*st));
     kiss_fft_cpx *tmp = (kiss_fft_cpx *)calloc(nfft, sizeof(kiss_fft_cpx));
-    if (!st || !tmp) { free(st); free(tmp); return NULL; }
+    kiss_fft_cpx *resp = (kiss_fft_cpx *)malloc(sizeof(kiss_fft_cpx) * nfft);
+    if (!st || !tmp || !resp) { free(st); free(tmp); free(resp); return NULL; }
     st->magic = KF_MAGIC_FC;
     st->nfft = (int)nfft;
+    st->nbins = (int)nfft;
     st->ngood = (int)(nfft - n_imp_resp + 1);
     st->fwd = kiss_fft_alloc((int)nfft, 0, NULL, NULL);
     st->inv = kiss_fft_alloc((int)nfft, 1, NULL, NULL);
-    st->h_resp = (kiss_fft_cpx *)malloc(sizeof(kiss_fft_cpx) * nfft);
-    int ok = st->fwd && st->inv && st->h_resp;
+    int ok = st->fwd && st->inv;
     if (ok) {
         /* zero pad in the middle to left-rotate the impulse response: the scrap samples end up at the END of each
          * inverse-transformed block (kiss_fastfir.c:139-147) */
         tmp[0] = imp_resp[n_imp_resp - 1];
         for (size_t i = 0; i + 1 < n_imp_resp; ++i) tmp[nfft - n_imp_resp + 1 + i] = imp_resp[i];
-        kiss_fft(st->fwd, tmp, st->h_resp); /* on the GPU, through the library itself */
+        kiss_fft(st->fwd, tmp, resp); /* on the GPU, through the library itself */
         const float scale = 1.0f / (float)nfft; /* kiss_fastfir.c:152-162 */
         for (size_t i = 0; i < nfft; ++i) {
-            st->h_resp[i].r *= scale;
-            st->h_resp[i].i *= scale;
+            resp[i].r *= scale;
+            resp[i].i *= scale;
         }
         ok = cudaGetDevice(&st->device) == cudaSuccess && cudaMalloc(&st->d_resp, sizeof(kiss_fft_cpx) * nfft) == cudaSuccess &&
-             cudaMemcpy(st->d_resp, st->h_resp, sizeof(kiss_fft_cpx) * nfft, cudaMemcpyHostToDevice) == cudaSuccess;
+             cudaMemcpy(st->d_resp, resp, sizeof(kiss_fft_cpx) * nfft, cudaMemcpyHostToDevice) == cudaSuccess;
     }
     free(tmp);
+    free(resp);
+    if (!ok) {
+        kiss_fastconv_free(st);
+        return NULL;
+    }
+    return st;
+}
+
+/* REAL_FASTFIR (kiss_fastfir.c:26-33, 91-95): real samples and impulse response, kiss_fftr / kiss_fftri, nfft/2+1 bins */
+kiss_fastconv_cfg kiss_fastconvr_alloc(const kiss_fft_scalar *imp_resp, size_t n_imp_resp, size_t *pnfft)
+{
+    if (!imp_resp || n_imp_resp < 1) return NULL;
+    size_t nfft = pnfft ? *pnfft : 0;
+    if (nfft == 0) nfft = kf_fastconv_default_nfft(n_imp_resp);
+    if (n_imp_resp > nfft || (nfft & 1) || nfft > (size_t)INT32_MAX) return NULL;
+    if (pnfft) *pnfft = nfft;
+    const size_t nbins = nfft / 2 + 1;
+    kiss_fastconv_cfg st = (kiss_fastconv_cfg)calloc(1, sizeof(*st));
+    kiss_fft_scalar *tmp = (kiss_fft_scalar *)calloc(nfft, sizeof(kiss_fft_scalar));
+    kiss_fft_cpx *resp = (kiss_fft_cpx *)malloc(sizeof(kiss_fft_cpx) * nbins);
+    if (!st || !tmp || !resp) { free(st); free(tmp); free(resp); return NULL; }
+    st->magic = KF_MAGIC_FCR;
+    st->nfft = (int)nfft;
+    st->nbins = (int)nbins;
+    st->ngood = (int)(nfft - n_imp_resp + 1);
+    st->rfwd = kiss_fftr_alloc((int)nfft, 0, NULL, NULL);
+    st->rinv = kiss_fftr_alloc((int)nfft, 1, NULL, NULL);
+    int ok = st->rfwd && st->rinv;
+    if (ok) {
+        tmp[0] = imp_resp[n_imp_resp - 1];
+        for (size_t i = 0; i + 1 < n_imp_resp; ++i) tmp[nfft - n_imp_resp + 1 + i] = imp_resp[i];
+        kiss_fftr(st->rfwd, tmp, resp);
+        const float scale = 1.0f / (float)nfft;
+        for (size_t i = 0; i < nbins; ++i) {
+            resp[i].r *= scale;
+            resp[i].i *= scale;
+        }
+        ok = cudaGetDevice(&st->device) == cudaSuccess && cudaMalloc(&st->d_resp, sizeof(kiss_fft_cpx) * nbins) == cudaSuccess &&
+             cudaMemcpy(st->d_resp, resp, sizeof(kiss_fft_cpx) * nbins, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    free(tmp);
+    free(resp);
     if (!ok) {
         kiss_fastconv_free(st);
         return NULL;
@@ -1504,14 +1561,46 @@ void kiss_fastconv_free(kiss_fastconv_cfg st)
 {
     if (!st) return;
     if (st->d_resp) cudaFree(st->d_resp);
-    free(st->h_resp);
     kiss_fft_free(st->fwd);
     kiss_fft_free(st->inv);
+    kiss_fftr_free(st->rfwd);
+    kiss_fftr_free(st->rinv);
     free(st);
 }
 
 size_t kiss_fastconv_block_advance(kiss_fastconv_cfg st) { return st ? (size_t)st->ngood : 0; }
 size_t kiss_fastconv_nfft(kiss_fastconv_cfg st) { return st ? (size_t)st->nfft : 0; }
+
+/* fastconv1buf composed from separate launches, for lengths without a fused kernel and for the real-sample build:
+ * dense copies of the overlapping blocks -> batched forward transform -> pointwise product with the response -> batched
+ * inverse transform -> the ngood valid samples of every block.  Any nfft the transforms accept (four-step beyond 4096 x
+ * 4); scratch comes from a staging context, so this path waits for the stream before it returns. */
+static int kf_fastconv_unfused(kiss_fastconv_cfg st, const void *d_in, void *d_out, size_t nblocks, void *stream)
+{
+    const int real = st->magic == KF_MAGIC_FCR;
+    const size_t nfft = (size_t)st->nfft, nbins = (size_t)st->nbins, ngood = (size_t)st->ngood;
+    const size_t ssz = real ? sizeof(kiss_fft_scalar) : sizeof(kiss_fft_cpx);
+    kf_ctx *cx = NULL;
+    KF_CHECK(kf_ctx_acquire(&cx));
+    void *blk = NULL, *spec = NULL;
+    int rc = kf_ctx_dev(cx, 0, ssz * nfft * nblocks, &blk);
+    if (!rc) rc = kf_ctx_dev(cx, 1, sizeof(kiss_fft_cpx) * nbins * nblocks, &spec);
+    if (!rc) rc = kfcu_gather_blocks(d_in, blk, (long long)nblocks, (int)nfft, (long long)ngood, real, stream);
+    if (!rc) {
+        if (real) rc = kiss_fftr_batch_dev(st->rfwd, (const kiss_fft_scalar *)blk, (kiss_fft_cpx *)spec, nblocks, nfft, nbins, stream);
+        else rc = kiss_fft_batch_dev(st->fwd, (const kiss_fft_cpx *)blk, (kiss_fft_cpx *)spec, nblocks, nfft, nfft, 1, stream);
+    }
+    if (!rc) rc = kfcu_cmul_rows(spec, st->d_resp, (long long)nblocks, (int)nbins, stream);
+    if (!rc) {
+        if (real) rc = kiss_fftri_batch_dev(st->rinv, (const kiss_fft_cpx *)spec, (kiss_fft_scalar *)blk, nblocks, nbins, nfft, stream);
+        else rc = kiss_fft_batch_dev(st->inv, (const kiss_fft_cpx *)spec, (kiss_fft_cpx *)blk, nblocks, nfft, nfft, 1, stream);
+    }
+    if (!rc)
+        rc = (int)cudaMemcpy2DAsync(d_out, ssz * ngood, blk, ssz * nfft, ssz * ngood, nblocks, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    const int e = (int)cudaStreamSynchronize((cudaStream_t)stream);
+    kf_ctx_release(cx);
+    return rc ? rc : e;
+}
 
 /* kff_nocopy (kiss_fastfir.c:191-206) on device buffers: all complete blocks of the n input samples. */
 int kiss_fastconv_dev(kiss_fastconv_cfg st, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, size_t n, size_t *nprocessed,
@@ -1525,16 +1614,30 @@ int kiss_fastconv_dev(kiss_fastconv_cfg st, const kiss_fft_cpx *d_in, kiss_fft_c
     if (n >= (size_t)st->nfft) nblocks = (n - (size_t)st->nfft) / (size_t)st->ngood + 1;
     if (nprocessed) *nprocessed = nblocks * (size_t)st->ngood;
     if (nblocks == 0) return 0;
-    const kf_devplan *pf, *pi;
-    KF_CHECK(kf_get_devplan(st->fwd, NULL, &pf));
-    KF_CHECK(kf_get_devplan(st->inv, NULL, &pi));
-    int rc = kfcu_fastconv((kfcu_plan *)&pf->plan, (kfcu_plan *)&pi->plan, d_in, d_out, (long long)nblocks, st->ngood, st->d_resp,
-                           stream);
-    if (rc == KFCU_ETOOBIG) {
-        KF_ERROR("kiss_fastconv_dev: no fused plan for nfft=%d in this build (supported: 256, 512, 1024, 2048, 4096)", st->nfft);
-        return KISS_FFT_CUDA_ETOOBIG;
+    if (kfcu_has_fastconv(st->nfft)) {
+        const kf_devplan *pf, *pi;
+        KF_CHECK(kf_get_devplan(st->fwd, NULL, &pf));
+        KF_CHECK(kf_get_devplan(st->inv, NULL, &pi));
+        KF_CHECK(kfcu_fastconv((kfcu_plan *)&pf->plan, (kfcu_plan *)&pi->plan, d_in, d_out, (long long)nblocks, st->ngood, st->d_resp,
+                               stream));
+        return 0;
     }
-    KF_CHECK(rc);
+    KF_CHECK(kf_fastconv_unfused(st, d_in, d_out, nblocks, stream));
+    return 0;
+}
+
+int kiss_fastconvr_dev(kiss_fastconv_cfg st, const kiss_fft_scalar *d_in, kiss_fft_scalar *d_out, size_t n, size_t *nprocessed,
+                       void *stream)
+{
+    if (!st || st->magic != KF_MAGIC_FCR || !d_in || !d_out) {
+        KF_ERROR("kiss_fastconvr_dev: bad argument");
+        return KISS_FFT_CUDA_EINVAL;
+    }
+    size_t nblocks = 0;
+    if (n >= (size_t)st->nfft) nblocks = (n - (size_t)st->nfft) / (size_t)st->ngood + 1;
+    if (nprocessed) *nprocessed = nblocks * (size_t)st->ngood;
+    if (nblocks == 0) return 0;
+    KF_CHECK(kf_fastconv_unfused(st, d_in, d_out, nblocks, stream));
     return 0;
 }
 #endif

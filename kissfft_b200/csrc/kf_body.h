@@ -28,6 +28,10 @@ constexpr bool is_col_mode(int m) { return m == kC2CCol || m == kC2CColTw || m =
 
 template <class A>
 struct KParams {
+    // column modes with a tensor-map input ring (PlanDesc::nstage > 0): the CUtensorMap of the input array viewed as
+    // [planes][nfft rows][columns] (opaque here; encoded by the launcher, read by cp.async.bulk.tensor).  First member
+    // so that it sits on the 64-byte boundary the hardware wants.
+    alignas(64) unsigned char tmap[128];
     const typename A::C* in;     // complex view of the input (kR2C: the real rows, 2 scalars per element)
     typename A::C* out;          // complex view of the output (kC2R: the real rows)
     long long howmany;
@@ -38,10 +42,16 @@ struct KParams {
     long long ncols, in_pdist, out_pdist;
     // column mode, fused exchange: when npeers > 0 the columns of a plane are split into npeers blocks of `cols_per_peer`
     // and block s is written through peer[s] (a mapped pointer into rank s's receive buffer: NVLink peer stores)
+    // peer_col_dist: input columns between the blocks of consecutive peers (== cols_per_peer when the blocks are adjacent;
+    // larger when only a chunk of every peer's column range is processed per launch)
     typename A::C* peer[16];
-    long long cols_per_peer;
+    long long cols_per_peer, peer_col_dist;
     int npeers;
-    KF_HD long long in_off(long long b) const { return ncols > 0 ? (b / ncols) * in_pdist + (b % ncols) * in_dist : b * in_dist; }
+    KF_HD long long in_col(long long col) const   // input column index of column `col` of a plane
+    {
+        return (npeers > 0 && peer_col_dist != cols_per_peer) ? (col / cols_per_peer) * peer_col_dist + col % cols_per_peer : col;
+    }
+    KF_HD long long in_off(long long b) const { return ncols > 0 ? (b / ncols) * in_pdist + in_col(b % ncols) * in_dist : b * in_dist; }
     KF_HD long long out_off(long long b) const { return ncols > 0 ? (b / ncols) * out_pdist + (b % ncols) * out_dist : b * out_dist; }
     KF_HD typename A::C* out_ptr(long long b) const
     {
@@ -64,18 +74,21 @@ KF_HD C ld_stream(const C* p)
 #if !defined(__CUDA_ARCH__)
     return *p;
 #else
-    // input rows are read exactly once: bypass L1 allocation
+    // input rows are read exactly once: bypass L1 allocation.  Deliberately NOT the non-coherent (.nc) path: the API
+    // allows in-place operation (fin == fout, kiss_fft.c:377-395; every in-layout axis pass), i.e. the same kernel writes
+    // this memory, which PTX leaves undefined for .nc loads.  In-place safety rests on ownership: a tile is read only by
+    // the CTA that later writes it, and read completely (into registers / shared memory) before its first store.
     if constexpr (sizeof(C) == 4) {
         unsigned u;
-        asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(u) : "l"(p));
+        asm volatile("ld.global.L1::no_allocate.b32 %0, [%1];" : "=r"(u) : "l"(p));
         return *reinterpret_cast<C*>(&u);
     } else if constexpr (sizeof(C) == 8) {
         unsigned long long u;
-        asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(u) : "l"(p));
+        asm volatile("ld.global.L1::no_allocate.b64 %0, [%1];" : "=l"(u) : "l"(p));
         return *reinterpret_cast<C*>(&u);
     } else {
         unsigned long long u0, u1;
-        asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(u0), "=l"(u1) : "l"(p));
+        asm volatile("ld.global.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(u0), "=l"(u1) : "l"(p));
         struct alignas(16) U2 { unsigned long long a, b; } u{u0, u1};
         return *reinterpret_cast<C*>(&u);
     }
@@ -98,6 +111,16 @@ template <class A>
 struct SrcShared {
     const typename A::C* base;   // natural order, unpadded
     KF_HD cx<typename A::R> load(int i) const { return A::load(base[i]); }
+    template <int IT_, int E_>
+    KF_HD cx<typename A::R> get(int i) const { return load(i); }
+};
+// column modes with the tensor-map ring: the tile landed as [nfft rows][ncol adjacent columns]; element i of this
+// thread's column is `ncol` elements further down
+template <class A>
+struct SrcStageCol {
+    const typename A::C* base;   // stage + column index
+    int ncol;
+    KF_HD cx<typename A::R> load(int i) const { return A::load(base[i * ncol]); }
     template <int IT_, int E_>
     KF_HD cx<typename A::R> get(int i) const { return load(i); }
 };
@@ -394,6 +417,11 @@ template <class A, class PT, int MODE>
 struct FusedLayout {
     static constexpr PlanDesc D = PT::D;
     static constexpr bool kRing = D.nstage > 0 && !is_col_mode(MODE);
+    // column modes: tiles of tpc adjacent columns x N rows fetched by tensor-map TMA (cp.async.bulk.tensor) into a ring,
+    // so the strided HBM reads of the next tiles run under the butterflies of the current one
+    static constexpr bool kColRing = D.nstage > 0 && is_col_mode(MODE);
+    static constexpr int kBoxRows = D.N < 256 ? D.N : 256;           // tensor-map boxes hold at most 256 rows
+    static_assert(!kColRing || D.N % kBoxRows == 0, "column ring: nfft must be a multiple of the 256-row box");
     static constexpr int kRowIn = (MODE == kC2R) ? D.N + 1 : D.N;   // complex elements per input row
     static_assert(D.nbuf == 2 || (D.nbuf == 1 && D.G == 2 && (MODE == kC2C || is_col_mode(MODE))) ||
                       (D.nbuf == 1 && D.G == 3 && D.nstage == 1 && D.paired && (MODE == kR2C || MODE == kC2R)) ||
@@ -422,8 +450,8 @@ struct FusedLayout {
     static constexpr int kLandElems = D.tpc * kRowIn + (kSlackRing ? kE16 : 0);
     static constexpr int kStageElems = (kStageExch && D.tpc * D.pitch() > kLandElems) ? D.tpc * D.pitch() : kLandElems;
     static constexpr size_t kStageBytes = ((size_t)kStageElems * sizeof(typename A::C) + 127) / 128 * 128;
-    static constexpr size_t kBarOff = kRingOff + (kRing ? D.nstage * kStageBytes : 0);
-    static constexpr size_t kTotal = kRing ? kBarOff + 8 * (size_t)D.nstage : kExchBytes;
+    static constexpr size_t kBarOff = kRingOff + ((kRing || kColRing) ? D.nstage * kStageBytes : 0);
+    static constexpr size_t kTotal = (kRing || kColRing) ? kBarOff + 8 * (size_t)D.nstage : kExchBytes;
 };
 
 // Groups 1.. of a plan whose input stage doubles as the second exchange buffer (FusedLayout::kStageExch): group g reads
@@ -500,6 +528,17 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
         else return 0;
     };
     auto issue = [&](int s, long long tl) {   // elected thread only
+        if constexpr (LY::kColRing) {
+            // tile tl = tpc adjacent columns of one plane, all N rows, as N / kBoxRows tensor-map boxes on one barrier
+            const long long cb0 = tl * PT::D.tpc;
+            const long long plane = P.ncols > 0 ? cb0 / P.ncols : 0, col0 = P.ncols > 0 ? P.in_col(cb0 % P.ncols) : cb0;
+            env.mbar_expect(bar_ptr(s), (unsigned)((size_t)PT::D.tpc * PT::D.N * sizeof(C)));
+            for (int r0 = 0; r0 < PT::D.N; r0 += LY::kBoxRows)
+                env.tensor_load_box(bar_ptr(s), stage_ptr(s) + (size_t)r0 * PT::D.tpc, P.tmap, col0, r0, plane,
+                                    P.in + plane * P.in_pdist + col0 + (long long)r0 * P.in_stride, P.in_stride, PT::D.tpc,
+                                    LY::kBoxRows, (int)sizeof(C), r0 + LY::kBoxRows >= PT::D.N);
+            return;
+        }
         const long long row0 = tl * D.tpc;
         const long long rows = (P.howmany - row0) < D.tpc ? (P.howmany - row0) : D.tpc;
         if constexpr (LY::kSlackRing) {
@@ -510,7 +549,7 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             env.bulk_load(bar_ptr(s), stage_ptr(s), P.in + row0 * kRowIn, (unsigned)(rows * kRowIn * sizeof(C)));
         }
     };
-    if constexpr (kRing) {
+    if constexpr (kRing || LY::kColRing) {
         if (tid == 0)
             for (int s = 0; s < D.nstage; ++s) env.mbar_init(bar_ptr(s));
         env.mbar_fence_init();
@@ -528,15 +567,18 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
         const bool active = b < P.howmany;
         C* b0 = (par ? bufB : bufA) + team * kPitch;
         C* b1 = (par ? bufA : bufB) + team * kPitch;
-        const int stg = kRing ? it % (D.nstage > 0 ? D.nstage : 1) : 0;
+        const int stg = (kRing || LY::kColRing) ? it % (D.nstage > 0 ? D.nstage : 1) : 0;
         const C* srow = nullptr;
         if constexpr (kRing) {
             env.mbar_wait(bar_ptr(stg), it / (D.nstage > 0 ? D.nstage : 1));
             srow = stage_ptr(stg) + tile_mis(tile) + team * kRowIn;
+        } else if constexpr (LY::kColRing) {
+            env.mbar_wait(bar_ptr(stg), it / (D.nstage > 0 ? D.nstage : 1));
+            srow = stage_ptr(stg);
         }
         // after the CTA barrier that follows the last read of the stage: refill it with the tile nstage rounds ahead
         auto recycle = [&]() {
-            if constexpr (LY::kRing) {
+            if constexpr (LY::kRing || LY::kColRing) {
                 if (tid == 0) {
                     const long long nxt = tile + (long long)PT::D.nstage * env.nblocks();
                     if (nxt < ntiles) issue(stg, nxt);
@@ -728,8 +770,14 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             SrcGlobal<A, false> src{P.in + P.in_off(cb), P.in_stride};
             DstGlobal<A> dst{P.out_ptr(b)};
             C* cb1 = (par ? bufA : bufB) + cteam * kPitch;
-            run_group<A, D, 0, SrcGlobal<A, false>, DstGlobal<A>>(ct, cb < P.howmany, src, dst, nullptr, cb1, tw, P.pc, P.inverse);
+            if constexpr (LY::kColRing) {
+                SrcStageCol<A> ssrc{srow + cteam, PT::D.tpc};
+                run_group<A, D, 0, SrcStageCol<A>, DstGlobal<A>>(ct, cb < P.howmany, ssrc, dst, nullptr, cb1, tw, P.pc, P.inverse);
+            } else {
+                run_group<A, D, 0, SrcGlobal<A, false>, DstGlobal<A>>(ct, cb < P.howmany, src, dst, nullptr, cb1, tw, P.pc, P.inverse);
+            }
             env.sync();
+            recycle();                                    // the landed tile has been consumed: fetch the one nstage rounds ahead
             run_groups<A, D, 1>(env, t, active, src, dst, b1, b0, tw, P.pc, P.inverse);
             par ^= (D.G - 1) & 1;
         }
@@ -744,8 +792,14 @@ KF_HD void fused_body(const KParams<A>& P, Env& env)
             DstGlobal<A> unused{nullptr};
             C* cb1 = (par ? bufA : bufB) + cteam * kPitch;
             C* cb0 = (par ? bufB : bufA) + cteam * kPitch;
-            run_group<A, D, 0, SrcGlobal<A, false>, DstGlobal<A>>(ct, con, src, unused, nullptr, cb1, tw, P.pc, P.inverse);
+            if constexpr (LY::kColRing) {
+                SrcStageCol<A> ssrc{srow + cteam, PT::D.tpc};
+                run_group<A, D, 0, SrcStageCol<A>, DstGlobal<A>>(ct, con, ssrc, unused, nullptr, cb1, tw, P.pc, P.inverse);
+            } else {
+                run_group<A, D, 0, SrcGlobal<A, false>, DstGlobal<A>>(ct, con, src, unused, nullptr, cb1, tw, P.pc, P.inverse);
+            }
             env.sync();
+            recycle();
             run_groups<A, D, 1, SrcGlobal<A, false>, DstGlobal<A>, Env, gl>(env, t, active, src, unused, b1, b0, tw, P.pc, P.inverse);
             if constexpr (MODE == kC2CColTw) {
                 // standard mapping: the team writes its transform as a contiguous row, times W_N^(column * k)

@@ -55,7 +55,12 @@ int kfcu_has_colcol(int nfft);   /* step 1 alone (every datatype): an axis pass 
 /* kfcu_exec_planes with the ncols = npeers*cols_per_peer columns of every plane scattered to npeers destination
  * buffers: column block s is written through peers[s] (+ p*out_pdist + c_local*nfft) */
 int kfcu_exec_planes_peers(kfcu_plan *plan, const void *d_in, void *const *peers, int npeers, long long nplanes,
-                           long long cols_per_peer, long long col_stride, long long in_pdist, long long out_pdist, void *stream);
+                           long long cols_per_peer, long long peer_col_dist, long long col_stride, long long in_pdist,
+                           long long out_pdist, void *stream);
+/* flags between the GPUs of the slab transform: d_flag_ptrs = device array of every rank's flag words (mapped here); a
+ * signal sets word (slot*16 + rank) of every rank to `epoch`, a wait spins until all nranks words of `slot` reached it */
+int kfcu_peer_signal(void *const *d_flag_ptrs, int nranks, int rank, int slot, unsigned epoch, void *stream);
+int kfcu_peer_wait(const void *d_my_flags, int nranks, int slot, unsigned epoch, void *stream);
 
 /* Multi-pass path: stage s of the plan as one launch over global memory (levels in autosort layout, dense rows of nfft
  * in the work buffers).  first: read the caller's rows (in_dist / in_stride); last: write the caller's rows (out_dist). */
@@ -67,10 +72,15 @@ int kfcu_realpass(const kfcu_plan *plan, int post, const void *d_in, void *d_out
 
 /* fused overlap-scrap fast convolution (float / double builds): block b reads nfft samples at d_in + b*ngood, writes
  * ngood samples at d_out + b*ngood; d_h = nfft-point frequency response already scaled by 1/nfft.  KFCU_ETOOBIG when
- * no fused plan exists for the length (the caller then composes it from three calls). */
+ * no fused plan exists for the length (kf_api.c then composes it from the pieces below: kf_fastconv_unfused). */
 int kfcu_has_fastconv(int nfft);
 int kfcu_fastconv(kfcu_plan *fwd, kfcu_plan *inv, const void *d_in, void *d_out, long long nblocks, long long ngood,
                   const void *d_h, void *stream);
+
+/* unfused fast convolution: dense copies of the overlapping blocks (out[b][i] = in[b*advance + i], elements = scalars when
+ * is_real else complex) and the pointwise product with the frequency response */
+int kfcu_gather_blocks(const void *d_in, void *d_out, long long nblocks, int len, long long advance, int is_real, void *stream);
+int kfcu_cmul_rows(void *d_x, const void *d_h, long long rows, int n, void *stream);
 
 /* out[c][r] = in[r][c] for a rows x cols array of complex elements (kiss_fftndr's bin-major <-> row-major
  * scatter loops, kiss_fftndr.c:101-102, 107-108) */

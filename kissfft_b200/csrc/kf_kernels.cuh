@@ -38,6 +38,23 @@ struct DeviceEnv {
                      "l"(src), "r"(bytes), "r"(s32(bar))
                      : "memory");
     }
+    // tensor-map variant (column modes): arm the barrier once for the whole tile, then one 3-D box per call --
+    // box = [ncol adjacent columns][nrows rows][1 plane] of the array described by `tmap`, landing densely as
+    // [row][column].  The trailing arguments describe the same box for the CPU emulator and are unused here.
+    __device__ __forceinline__ void mbar_expect(void* bar, unsigned bytes) const
+    {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+    }
+    __device__ __forceinline__ void tensor_load_box(void* bar, void* dst, const void* tmap, long long col0, int row0, long long plane,
+                                                    const void*, long long, int, int, int elem_bytes, bool) const
+    {
+        // the map counts 4-byte words along the contiguous dimension
+        const int x = (int)(col0 * (elem_bytes / 4)), y = row0, z = (int)plane;
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(s32(dst)),
+            "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(s32(bar))
+            : "memory");
+    }
     // all threads: wait for the k-th completion of the barrier (phase parity k & 1)
     __device__ __forceinline__ void mbar_wait(void* bar, int k) const
     {
@@ -94,6 +111,27 @@ __global__ void __launch_bounds__(256) kf_realpass_kernel(const __grid_constant_
 {
     DeviceEnv env{nullptr};
     realpass_body<A>(S, env);
+}
+
+// overlap-scrap block gather (unfused fast convolution): out[b][i] = in[b*advance + i], i < len.  T = scalar or complex.
+template <class T>
+__global__ void __launch_bounds__(256) kf_gather_blocks_kernel(const T* __restrict__ in, T* __restrict__ out, long long nblocks, int len,
+                                                              long long advance)
+{
+    const long long total = nblocks * len, step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+        const long long b = i / len;
+        out[i] = in[b * advance + (i - b * len)];
+    }
+}
+
+// x[b][k] = C_MUL(x[b][k], h[k]) for b < rows, k < n (fastconv1buf, tools/kiss_fastfir.c:171-176); float / double
+template <class A>
+__global__ void __launch_bounds__(256) kf_cmul_rows_kernel(typename A::C* __restrict__ x, const typename A::C* __restrict__ h, long long rows, int n)
+{
+    const long long total = rows * n, step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step)
+        x[i] = A::store(A::cmul(A::load(x[i]), A::load(h[i % n])));
 }
 
 // tiled transpose of a rows x cols array of storage complexes (32 x 32 tiles, +1 column of padding)

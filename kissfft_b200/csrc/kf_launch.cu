@@ -6,6 +6,7 @@
 // run-time shared-memory kernel.  There is no CPU path: if no kernel applies the call fails.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -15,6 +16,7 @@
 #include "kf_internal.h"
 #include "kf_kernels.cuh"
 #include "kf_twtab.h"
+#include "kf_tmap.h"
 #define KF_SCALAR_BYTES ((int)sizeof(kiss_fft_scalar))
 #include "kf_plan_list.h"
 
@@ -49,10 +51,12 @@ static KParams<AT> make_params(const kfcu_plan* pl, const void* d_in, void* d_ou
                                long long out_dist, long long in_stride)
 {
     KParams<AT> P;
+    memset(P.tmap, 0, sizeof(P.tmap));
     P.ncols = 0;
     P.in_pdist = P.out_pdist = 0;
     P.npeers = 0;
     P.cols_per_peer = 0;
+    P.peer_col_dist = 0;
     P.in = (const CT*)d_in;
     P.out = (CT*)d_out;
     P.howmany = howmany;
@@ -117,6 +121,11 @@ static int launch_fused(kfcu_plan* pl, KParams<AT>& P, cudaStream_t st)
         if (rc != 0 || nfused == 0) return rc;
         P = sub_rows(P, 0, nfused);
     }
+    if constexpr (FusedLayout<AT, PT, MODE>::kColRing) {
+        // tensor-map input ring: the caller (launch_col) has checked col_ring_ok for this plan
+        const int rc = col_ring_encode<AT, PT, MODE>(P);
+        if (rc != 0) return rc;
+    }
     auto kern = kf_fused_kernel<AT, PT, MODE>;
     constexpr size_t smem = FusedLayout<AT, PT, MODE>::kTotal;
     static_assert(smem <= 232448, "plan exceeds the 227 KiB of shared memory a CTA can opt in to");
@@ -164,6 +173,41 @@ struct FusedEntry {
 #define KF_FUSED_REAL(PT) { PT::D.N, { nullptr, nullptr, launch_fused<PT, kR2C>, launch_fused<PT, kC2R>, nullptr, nullptr } }
 
 #include "kf_plans.inc"
+
+// column-ring variants (tensor-map TMA input) of the column plans: preferred whenever the call's geometry allows
+struct ColRingEntry {
+    int N;
+    fused_launch_fn fn[6];
+    bool (*ok)(const KParams<AT>&);
+};
+// X(tag, serves kC2CCol, serves kC2CColTw, serves kC2CColCol)
+#if defined(FIXED_POINT)
+#define KF_RING_TW(PT, on) nullptr
+#else
+#define KF_RING_TW(PT, on) ((on) ? launch_fused<PT, kC2CColTw> : nullptr)
+#endif
+#define KF_COLRING_ROW(PT, c, tw, cc) { PT::D.N, { nullptr, (c) ? launch_fused<PT, kC2CCol> : nullptr, nullptr, nullptr, KF_RING_TW(PT, tw), \
+                                        (cc) ? launch_fused<PT, kC2CColCol> : nullptr }, col_ring_ok<AT, PT> },
+static const ColRingEntry kColRingTable[] = { KF_COLRING_LIST(KF_COLRING_ROW) { 0, { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }, nullptr } };
+static std::atomic<int> g_no_colring{0};
+
+static const FusedEntry* find_fused(int nfft, int mode);
+static const char* env_cached(const char* name)
+{
+    return getenv(name);
+}
+
+// column-mode launch: ring variant when eligible, else the direct-load plan, else the run-time kernel (kC2CCol only)
+static int launch_col(int mode, kfcu_plan* plan, KParams<AT>& P, cudaStream_t st)
+{
+    static const bool off = [] { const char* e = env_cached("KISSFFT_COL_TMA"); return e && e[0] == '0'; }();
+    if (!off && !g_force_generic.load() && !g_no_colring.load())
+        for (const ColRingEntry& e : kColRingTable)
+            if (e.N == plan->nfft && e.fn[mode] && e.ok(P)) return e.fn[mode](plan, P, st);
+    if (const FusedEntry* fe = find_fused(plan->nfft, mode)) return fe->fn[mode](plan, P, st);
+    if (mode == kC2CCol) return launch_generic(kC2CCol, plan, P, st);
+    return KFCU_EINVAL;
+}
 
 static const FusedEntry* find_fused(int nfft, int mode)
 {
@@ -225,6 +269,7 @@ extern "C" int kfcu_exec(int mode, kfcu_plan* plan, const void* d_in, void* d_ou
     if ((mode == kR2C || mode == kC2R) && !plan->d_stw && plan->nfft > 1) return KFCU_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     KParams<AT> P = make_params(plan, d_in, d_out, howmany, in_dist, out_dist, in_stride);
+    if (mode == kC2CCol) return launch_col(mode, plan, P, st);
     if (const FusedEntry* fe = find_fused(plan->nfft, mode)) return fe->fn[mode](plan, P, st);
     return launch_generic(mode, plan, P, st);
 }
@@ -239,8 +284,7 @@ extern "C" int kfcu_exec_planes(kfcu_plan* plan, const void* d_in, void* d_out, 
     P.ncols = ncols;
     P.in_pdist = in_pdist;
     P.out_pdist = out_pdist;
-    if (const FusedEntry* fe = find_fused(plan->nfft, kC2CCol)) return fe->fn[kC2CCol](plan, P, (cudaStream_t)stream);
-    return launch_generic(kC2CCol, plan, P, (cudaStream_t)stream);
+    return launch_col(kC2CCol, plan, P, (cudaStream_t)stream);
 }
 
 // the two passes of the four-step transform of rows of length N = N1 * N2 (float / double; kf_api.c:kf_exec_fourstep).
@@ -253,8 +297,7 @@ extern "C" int kfcu_exec_fourstep(kfcu_plan* plan, int step, const void* d_in, v
     if (!plan || !d_in || !d_out || nrows < 0 || ncols < 1 || step < 0 || step > 1) return KFCU_EINVAL;
     if (nrows == 0) return 0;
     const int mode = step == 0 ? (int)kC2CColTw : (int)kC2CColCol;
-    const FusedEntry* fe = find_fused(plan->nfft, mode);
-    if (!fe) return KFCU_EINVAL;
+    if (!find_fused(plan->nfft, mode)) return KFCU_EINVAL;
     const long long N = (long long)plan->nfft * ncols;
     KParams<AT> P = make_params(plan, d_in, d_out, nrows * ncols, 1, step == 0 ? plan->nfft : 1, ncols);
     P.ncols = ncols;
@@ -264,7 +307,7 @@ extern "C" int kfcu_exec_fourstep(kfcu_plan* plan, int step, const void* d_in, v
         if (!d_twbig) return KFCU_EINVAL;
         P.stw = (const CT*)d_twbig;
     }
-    return fe->fn[mode](plan, P, (cudaStream_t)stream);
+    return launch_col(mode, plan, P, (cudaStream_t)stream);
 }
 
 extern "C" int kfcu_has_colcol(int nfft) { return find_fused(nfft, kC2CColCol) != nullptr; }
@@ -276,10 +319,10 @@ extern "C" int kfcu_has_fourstep(int nfft)
 
 // the same pass with the columns of every plane split into npeers blocks; block s goes through peers[s]
 extern "C" int kfcu_exec_planes_peers(kfcu_plan* plan, const void* d_in, void* const* peers, int npeers, long long nplanes,
-                                      long long cols_per_peer, long long col_stride, long long in_pdist, long long out_pdist,
-                                      void* stream)
+                                      long long cols_per_peer, long long peer_col_dist, long long col_stride, long long in_pdist,
+                                      long long out_pdist, void* stream)
 {
-    if (!plan || !d_in || !peers || npeers < 1 || npeers > 16 || nplanes < 0 || cols_per_peer < 1) return KFCU_EINVAL;
+    if (!plan || !d_in || !peers || npeers < 1 || npeers > 16 || nplanes < 0 || cols_per_peer < 1 || peer_col_dist < cols_per_peer) return KFCU_EINVAL;
     if (nplanes == 0) return 0;
     const long long ncols = cols_per_peer * npeers;
     KParams<AT> P = make_params(plan, d_in, peers[0], nplanes * ncols, 1, plan->nfft, col_stride);
@@ -288,9 +331,9 @@ extern "C" int kfcu_exec_planes_peers(kfcu_plan* plan, const void* d_in, void* c
     P.out_pdist = out_pdist;
     P.npeers = npeers;
     P.cols_per_peer = cols_per_peer;
+    P.peer_col_dist = peer_col_dist;
     for (int s = 0; s < npeers; ++s) P.peer[s] = (CT*)peers[s];
-    if (const FusedEntry* fe = find_fused(plan->nfft, kC2CCol)) return fe->fn[kC2CCol](plan, P, (cudaStream_t)stream);
-    return launch_generic(kC2CCol, plan, P, (cudaStream_t)stream);
+    return launch_col(kC2CCol, plan, P, (cudaStream_t)stream);
 }
 
 // ---- fused fast convolution (float / double) ------------------------------------------------------------------
@@ -383,6 +426,84 @@ extern "C" int kfcu_fastconv(kfcu_plan* fwd, kfcu_plan* inv, const void* d_in, v
         if (e.N == fwd->nfft) return e.fn(fwd, inv, d_in, d_out, nblocks, ngood, d_h, (cudaStream_t)stream);
 #endif
     return KFCU_ETOOBIG;
+}
+
+// ---- flags between the GPUs of the slab transform (kf_mgpu.c): "block (chunk, source rank) has landed" -------------------
+// flags[r] = rank r's flag words, mapped into this process; word (slot * 16 + source rank) of the receiver is set to the
+// epoch by the source once its stores to that receiver are complete (the kernel that made them precedes this one on the
+// stream; the system-scope fence orders them before the flag).
+__global__ void kf_peer_signal_kernel(unsigned* const* flags, int nranks, int rank, int slot, unsigned epoch)
+{
+    const int s = (int)threadIdx.x;
+    if (s < nranks) {
+        __threadfence_system();
+        volatile unsigned* f = flags[s] + slot * 16 + rank;
+        *f = epoch;
+        __threadfence_system();
+    }
+}
+// waits until every source rank has signalled `slot` for this epoch (epochs only grow; wrap-around safe comparison).
+// Gives up after ~2 s and traps, so a lost peer cannot hang the GPU.
+__global__ void kf_peer_wait_kernel(const unsigned* mine, int nranks, int slot, unsigned epoch)
+{
+    const int s = (int)threadIdx.x;
+    if (s < nranks) {
+        const volatile unsigned* f = mine + slot * 16 + s;
+        const long long t0 = clock64();
+        while ((int)(*f - epoch) < 0) {
+            if (clock64() - t0 > 4000000000LL) __trap();
+        }
+        __threadfence_system();
+    }
+}
+
+extern "C" int kfcu_peer_signal(void* const* d_flag_ptrs, int nranks, int rank, int slot, unsigned epoch, void* stream)
+{
+    if (!d_flag_ptrs || nranks < 1 || nranks > 16) return KFCU_EINVAL;
+    kf_peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned* const*)d_flag_ptrs, nranks, rank, slot, epoch);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int kfcu_peer_wait(const void* d_my_flags, int nranks, int slot, unsigned epoch, void* stream)
+{
+    if (!d_my_flags || nranks < 1 || nranks > 16) return KFCU_EINVAL;
+    kf_peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned*)d_my_flags, nranks, slot, epoch);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+// ---- pieces of the unfused fast convolution (any nfft; kf_api.c:kf_fastconv_unfused) ------------------------------------
+extern "C" int kfcu_gather_blocks(const void* d_in, void* d_out, long long nblocks, int len, long long advance, int is_real, void* stream)
+{
+    if (!d_in || !d_out || nblocks < 0 || len < 1 || advance < 1) return KFCU_EINVAL;
+    if (nblocks == 0) return 0;
+    long long grid = (nblocks * len + 255) / 256;
+    const long long cap = (long long)device_info().sms * 16;
+    if (grid > cap) grid = cap;
+    if (is_real)
+        kf_gather_blocks_kernel<kiss_fft_scalar><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const kiss_fft_scalar*)d_in, (kiss_fft_scalar*)d_out, nblocks, len, advance);
+    else
+        kf_gather_blocks_kernel<CT><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const CT*)d_in, (CT*)d_out, nblocks, len, advance);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int kfcu_cmul_rows(void* d_x, const void* d_h, long long rows, int n, void* stream)
+{
+#if !defined(FIXED_POINT)
+    if (!d_x || !d_h || rows < 0 || n < 1) return KFCU_EINVAL;
+    if (rows == 0) return 0;
+    long long grid = (rows * n + 255) / 256;
+    const long long cap = (long long)device_info().sms * 16;
+    if (grid > cap) grid = cap;
+    kf_cmul_rows_kernel<AT><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((CT*)d_x, (const CT*)d_h, rows, n);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+#else
+    (void)d_x; (void)d_h; (void)rows; (void)n; (void)stream;
+    return KFCU_EINVAL;
+#endif
 }
 
 // ---- multi-pass path (lengths beyond the shared-memory kernels) -------------------------------------------------

@@ -1,0 +1,349 @@
+/*
+ * kf_mgpu.c -- kiss_fftnd over several GPUs, one process per GPU, behind a C-ABI (include/kiss_fft_cuda.h:
+ * kiss_fftnd_mgpu_get_id / _alloc / _exec / _free).
+ *
+ * The reference transforms ONE array with kiss_fftnd (kiss_fftnd.c:156-188) and has no distributed code.  Here the
+ * d0 x d1 x d2 array is split into slabs of P = d0/G planes per rank and needs a single exchange:
+ *
+ *   A. rows (axis 2) of the local slab, in place                      kiss_fft_batch_dev          [P][d1][d2]
+ *   B. columns (axis 1) of every local plane, written transposed and already sorted by destination rank -- the k2
+ *      columns are cut into `nchunks` chunks of cw = (d2/G)/nchunks so that the exchange and step C pipeline:
+ *      chunk j of destination s holds k2 in s*d2/G + [j*cw, (j+1)*cw)   kiss_fft_planes_pass_peers_dev
+ *   X. all-to-all: block (s, j) goes to rank s.  Two implementations:
+ *        - NCCL: step B writes a local send buffer, grouped ncclSend/ncclRecv per chunk on a communication stream
+ *          (libnccl is dlopen()ed; the communicator is built from the id rank 0 hands out);
+ *        - peer stores (KISS_FFT_MGPU_P2P): the receive buffers of all ranks are mapped into every process with CUDA
+ *          IPC and step B's kernel stores its rows straight into them over NVLink -- no send buffer, no collective;
+ *          a flag per (chunk, source rank) in the receiver's memory says "landed".
+ *   C. axis 0 of chunk j, as soon as chunk j has arrived from every rank  kiss_fft_axis_pass_dev  [d2/G][d1][d0]
+ *
+ * The receive buffer is laid out [chunk j][source rank r][P][cw][d1]: chunk j is one dense (G*P) x (cw*d1) matrix for
+ * step C and one contiguous piece per (source, chunk) for NCCL.  Output: X[k0][k1][k2] stored as out[k2 - r*d2/G][k1][k0]
+ * on rank r ("transposed out", distributed along k2), the usual contract of slab FFTs.
+ *
+ * Host code is C; the only CUDA code it needs beyond the library's own entry points are the two flag kernels
+ * (kf_launch.cu: kfcu_peer_signal / kfcu_peer_wait).
+ */
+#include <cuda_runtime_api.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/kiss_fft_cuda.h"
+#include "kf_internal.h"
+
+/* ---- the few NCCL declarations used (nccl.h: 2.19+ ABI); the library is loaded at run time --------------------- */
+typedef struct { char internal[128]; } kf_nccl_id;
+typedef void *kf_nccl_comm;
+enum { KF_NCCL_UINT8 = 1, KF_NCCL_SUCCESS = 0 };
+typedef struct {
+    void *lib;
+    int (*GetUniqueId)(kf_nccl_id *);
+    int (*CommInitRank)(kf_nccl_comm *, int, kf_nccl_id, int);
+    int (*CommDestroy)(kf_nccl_comm);
+    int (*Send)(const void *, size_t, int, int, kf_nccl_comm, cudaStream_t);
+    int (*Recv)(void *, size_t, int, int, kf_nccl_comm, cudaStream_t);
+    int (*AllGather)(const void *, void *, size_t, int, kf_nccl_comm, cudaStream_t);
+    int (*GroupStart)(void);
+    int (*GroupEnd)(void);
+    const char *(*GetErrorString)(int);
+} kf_nccl_api;
+
+static kf_nccl_api g_nccl;
+
+static int kf_nccl_load(void)
+{
+    if (g_nccl.lib) return 0;
+    /* a copy already in the process (e.g. the one PyTorch bundles) is preferred over the system one */
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return -1;
+    kf_nccl_api a;
+    memset(&a, 0, sizeof(a));
+    a.lib = h;
+    *(void **)&a.GetUniqueId = dlsym(h, "ncclGetUniqueId");
+    *(void **)&a.CommInitRank = dlsym(h, "ncclCommInitRank");
+    *(void **)&a.CommDestroy = dlsym(h, "ncclCommDestroy");
+    *(void **)&a.Send = dlsym(h, "ncclSend");
+    *(void **)&a.Recv = dlsym(h, "ncclRecv");
+    *(void **)&a.AllGather = dlsym(h, "ncclAllGather");
+    *(void **)&a.GroupStart = dlsym(h, "ncclGroupStart");
+    *(void **)&a.GroupEnd = dlsym(h, "ncclGroupEnd");
+    *(void **)&a.GetErrorString = dlsym(h, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.Send || !a.Recv || !a.AllGather || !a.GroupStart || !a.GroupEnd)
+        return -1;
+    g_nccl = a;
+    return 0;
+}
+
+#define KF_MAGIC_MGPU 0x4b464d47u
+#define KF_MGPU_MAXRANKS 16
+#define KF_MGPU_MAXCHUNKS 8
+#define KF_FLAG_BYTES 4096 /* (MAXCHUNKS + 1) slots x MAXRANKS unsigned, rounded up */
+
+struct kiss_fftnd_mgpu_state {
+    uint32_t magic;
+    int d0, d1, d2, inverse, rank, nranks, device;
+    int planes, cols, nchunks, cw; /* P, C = d2/G, chunks of the k2 columns, columns per chunk */
+    unsigned flags;
+    int p2p;                       /* peer-store exchange active */
+    kiss_fft_cfg cfg0, cfg1, cfg2;
+    kf_nccl_comm comm;
+    char *recv_base;               /* one allocation: receive buffer followed by the flag words */
+    size_t recv_bytes;
+    kiss_fft_cpx *send;            /* NCCL path only */
+    char *peer_base[KF_MGPU_MAXRANKS]; /* every rank's recv_base as mapped here (own entry = recv_base) */
+    unsigned **d_peer_flags;       /* device copy of the G flag-array pointers */
+    unsigned epoch;
+    cudaStream_t s_comm, s_c;
+    cudaEvent_t ev_start, ev_b[KF_MGPU_MAXCHUNKS], ev_x[KF_MGPU_MAXCHUNKS], ev_done;
+    char err[256];
+};
+
+static __thread char tls_mgpu_err[256];
+const char *kiss_fftnd_mgpu_last_error(void) { return tls_mgpu_err; }
+
+static int kf_fail(kiss_fftnd_mgpu_cfg st, const char *what, int code, int is_nccl)
+{
+    const char *msg = is_nccl ? (g_nccl.GetErrorString ? g_nccl.GetErrorString(code) : "nccl error")
+                              : (code > 0 ? cudaGetErrorString((cudaError_t)code) : kiss_fft_cuda_last_error());
+    snprintf(tls_mgpu_err, sizeof(tls_mgpu_err), "%s: %s %d (%s)", what, is_nccl ? "NCCL" : "error", code, msg ? msg : "");
+    if (st) memcpy(st->err, tls_mgpu_err, sizeof(st->err));
+#ifndef NDEBUG
+    fprintf(stderr, "[ERROR] %s:%d %s\n", __FILE__, __LINE__, tls_mgpu_err);
+#endif
+    return code ? code : KISS_FFT_CUDA_EINVAL;
+}
+#define CU(expr)                                                      \
+    do {                                                              \
+        int rc_ = (int)(expr);                                        \
+        if (rc_ != 0) return kf_fail(st, #expr, rc_, 0);              \
+    } while (0)
+#define NC(expr)                                                      \
+    do {                                                              \
+        int rc_ = (int)(expr);                                        \
+        if (rc_ != KF_NCCL_SUCCESS) return kf_fail(st, #expr, rc_, 1); \
+    } while (0)
+
+int kiss_fftnd_mgpu_get_id(void *id)
+{
+    if (!id) return KISS_FFT_CUDA_EINVAL;
+    if (kf_nccl_load() != 0) return kf_fail(NULL, "libnccl.so.2 could not be loaded", KISS_FFT_CUDA_EINVAL, 0);
+    kf_nccl_id nid;
+    const int rc = g_nccl.GetUniqueId(&nid);
+    if (rc != KF_NCCL_SUCCESS) return kf_fail(NULL, "ncclGetUniqueId", rc, 1);
+    memcpy(id, &nid, KISS_FFT_MGPU_ID_BYTES);
+    return 0;
+}
+
+static size_t block_elems(const struct kiss_fftnd_mgpu_state *st) { return (size_t)st->planes * st->cw * st->d1; }
+static size_t chunk_elems(const struct kiss_fftnd_mgpu_state *st) { return block_elems(st) * (size_t)st->nranks; }
+static unsigned *flag_ptr(const struct kiss_fftnd_mgpu_state *st, int r) { return (unsigned *)(st->peer_base[r] + st->recv_bytes); }
+
+/* map every rank's receive buffer into this process (CUDA IPC); handles travel through an NCCL all-gather */
+static int kf_mgpu_map_peers(kiss_fftnd_mgpu_cfg st)
+{
+    cudaIpcMemHandle_t mine, *all = NULL;
+    void *d_h = NULL;
+    const int G = st->nranks;
+    int rc = (int)cudaIpcGetMemHandle(&mine, st->recv_base);
+    if (rc) { cudaGetLastError(); return rc; }
+    all = (cudaIpcMemHandle_t *)malloc(sizeof(*all) * (size_t)G);
+    if (!all) return KISS_FFT_CUDA_ENOMEM;
+    rc = (int)cudaMalloc(&d_h, sizeof(mine) * (size_t)(G + 1));
+    if (!rc) rc = (int)cudaMemcpy(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice);
+    if (!rc) {
+        const int n = g_nccl.AllGather(d_h, (char *)d_h + sizeof(mine), sizeof(mine), KF_NCCL_UINT8, st->comm, (cudaStream_t)0);
+        if (n != KF_NCCL_SUCCESS) rc = KISS_FFT_CUDA_EINVAL;
+    }
+    if (!rc) rc = (int)cudaStreamSynchronize((cudaStream_t)0);
+    if (!rc) rc = (int)cudaMemcpy(all, (char *)d_h + sizeof(mine), sizeof(mine) * (size_t)G, cudaMemcpyDeviceToHost);
+    for (int r = 0; !rc && r < G; ++r) {
+        if (r == st->rank) {
+            st->peer_base[r] = st->recv_base;
+        } else {
+            void *p = NULL;
+            rc = (int)cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
+            if (rc) cudaGetLastError();
+            st->peer_base[r] = (char *)p;
+        }
+    }
+    if (d_h) cudaFree(d_h);
+    free(all);
+    if (rc) {
+        for (int r = 0; r < G; ++r) {
+            if (r != st->rank && st->peer_base[r]) cudaIpcCloseMemHandle(st->peer_base[r]);
+            st->peer_base[r] = NULL;
+        }
+        return rc;
+    }
+    unsigned *ptrs[KF_MGPU_MAXRANKS];
+    for (int r = 0; r < G; ++r) ptrs[r] = flag_ptr(st, r);
+    rc = (int)cudaMalloc((void **)&st->d_peer_flags, sizeof(unsigned *) * (size_t)G);
+    if (!rc) rc = (int)cudaMemcpy(st->d_peer_flags, ptrs, sizeof(unsigned *) * (size_t)G, cudaMemcpyHostToDevice);
+    return rc;
+}
+
+kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int inverse_fft, int rank, int nranks, const void *id,
+                                          unsigned flags)
+{
+    kiss_fftnd_mgpu_cfg st = NULL;
+    if (!dims || ndims != 3 || nranks < 1 || nranks > KF_MGPU_MAXRANKS || rank < 0 || rank >= nranks || (nranks > 1 && !id)) {
+        kf_fail(NULL, "kiss_fftnd_mgpu_alloc: bad argument (3-D arrays, 1..16 ranks, id required beyond one rank)", KISS_FFT_CUDA_EINVAL, 0);
+        return NULL;
+    }
+    if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || dims[0] % nranks || dims[2] % nranks) {
+        kf_fail(NULL, "kiss_fftnd_mgpu_alloc: dims[0] and dims[2] must be divisible by the number of ranks", KISS_FFT_CUDA_EINVAL, 0);
+        return NULL;
+    }
+    st = (kiss_fftnd_mgpu_cfg)calloc(1, sizeof(*st));
+    if (!st) return NULL;
+    st->magic = KF_MAGIC_MGPU;
+    st->d0 = dims[0]; st->d1 = dims[1]; st->d2 = dims[2];
+    st->inverse = inverse_fft ? 1 : 0;
+    st->rank = rank; st->nranks = nranks; st->flags = flags;
+    st->planes = st->d0 / nranks;
+    st->cols = st->d2 / nranks;
+    /* chunks of the k2 columns: as many as requested / up to 4, keeping whole 16-column tiles per chunk where possible */
+    int want = 4;
+    const char *env = getenv("KISSFFT_MGPU_CHUNKS");
+    if (env && atoi(env) > 0) want = atoi(env);
+    if (want > KF_MGPU_MAXCHUNKS) want = KF_MGPU_MAXCHUNKS;
+    if (nranks == 1) want = 1;
+    st->nchunks = 1;
+    for (int c = want; c >= 1; --c)
+        if (st->cols % c == 0 && ((st->cols / c) % 16 == 0 || c == 1)) { st->nchunks = c; break; }
+    st->cw = st->cols / st->nchunks;
+    int ok = cudaGetDevice(&st->device) == cudaSuccess;
+    st->cfg0 = kiss_fft_alloc(st->d0, st->inverse, NULL, NULL);
+    st->cfg1 = kiss_fft_alloc(st->d1, st->inverse, NULL, NULL);
+    st->cfg2 = kiss_fft_alloc(st->d2, st->inverse, NULL, NULL);
+    ok = ok && st->cfg0 && st->cfg1 && st->cfg2;
+    st->recv_bytes = sizeof(kiss_fft_cpx) * (size_t)st->d0 * st->cols * st->d1;
+    st->recv_bytes = (st->recv_bytes + 255u) & ~(size_t)255u;
+    ok = ok && cudaMalloc((void **)&st->recv_base, st->recv_bytes + KF_FLAG_BYTES) == cudaSuccess &&
+         cudaMemset(st->recv_base + st->recv_bytes, 0, KF_FLAG_BYTES) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&st->s_comm, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&st->s_c, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&st->ev_start, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&st->ev_done, cudaEventDisableTiming) == cudaSuccess;
+    for (int j = 0; ok && j < KF_MGPU_MAXCHUNKS; ++j)
+        ok = cudaEventCreateWithFlags(&st->ev_b[j], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&st->ev_x[j], cudaEventDisableTiming) == cudaSuccess;
+    if (ok && nranks > 1) {
+        ok = kf_nccl_load() == 0;
+        if (!ok) kf_fail(st, "libnccl.so.2 could not be loaded", KISS_FFT_CUDA_EINVAL, 0);
+        if (ok) {
+            kf_nccl_id nid;
+            memcpy(&nid, id, sizeof(nid));
+            const int rc = g_nccl.CommInitRank(&st->comm, nranks, nid, rank);
+            if (rc != KF_NCCL_SUCCESS) { kf_fail(st, "ncclCommInitRank", rc, 1); ok = 0; }
+        }
+        if (ok && (flags & KISS_FFT_MGPU_P2P)) st->p2p = kf_mgpu_map_peers(st) == 0;   /* falls back to NCCL when IPC is unavailable */
+        if (ok && !st->p2p) ok = cudaMalloc((void **)&st->send, st->recv_bytes) == cudaSuccess;
+    }
+    if (ok) ok = cudaDeviceSynchronize() == cudaSuccess;
+    if (!ok) {
+        if (!st->err[0]) kf_fail(st, "kiss_fftnd_mgpu_alloc: resource allocation failed", (int)cudaGetLastError(), 0);
+        kiss_fftnd_mgpu_free(st);
+        return NULL;
+    }
+    st->peer_base[rank] = st->recv_base;
+    return st;
+}
+
+void kiss_fftnd_mgpu_free(kiss_fftnd_mgpu_cfg st)
+{
+    if (!st || st->magic != KF_MAGIC_MGPU) return;
+    cudaDeviceSynchronize();
+    for (int r = 0; r < st->nranks; ++r)
+        if (r != st->rank && st->peer_base[r]) cudaIpcCloseMemHandle(st->peer_base[r]);
+    if (st->d_peer_flags) cudaFree(st->d_peer_flags);
+    if (st->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(st->comm);
+    if (st->recv_base) cudaFree(st->recv_base);
+    if (st->send) cudaFree(st->send);
+    if (st->s_comm) cudaStreamDestroy(st->s_comm);
+    if (st->s_c) cudaStreamDestroy(st->s_c);
+    if (st->ev_start) cudaEventDestroy(st->ev_start);
+    if (st->ev_done) cudaEventDestroy(st->ev_done);
+    for (int j = 0; j < KF_MGPU_MAXCHUNKS; ++j) {
+        if (st->ev_b[j]) cudaEventDestroy(st->ev_b[j]);
+        if (st->ev_x[j]) cudaEventDestroy(st->ev_x[j]);
+    }
+    kiss_fft_free(st->cfg0);
+    kiss_fft_free(st->cfg1);
+    kiss_fft_free(st->cfg2);
+    st->magic = 0;
+    free(st);
+}
+
+size_t kiss_fftnd_mgpu_local_in_elems(kiss_fftnd_mgpu_cfg st) { return st ? (size_t)st->planes * st->d1 * st->d2 : 0; }
+size_t kiss_fftnd_mgpu_local_out_elems(kiss_fftnd_mgpu_cfg st) { return st ? (size_t)st->cols * st->d1 * st->d0 : 0; }
+int kiss_fftnd_mgpu_uses_p2p(kiss_fftnd_mgpu_cfg st) { return st ? st->p2p : 0; }
+int kiss_fftnd_mgpu_chunks(kiss_fftnd_mgpu_cfg st) { return st ? st->nchunks : 0; }
+size_t kiss_fftnd_mgpu_a2a_bytes(kiss_fftnd_mgpu_cfg st)
+{
+    return st ? sizeof(kiss_fft_cpx) * (size_t)(st->nranks - 1) * st->planes * st->cols * st->d1 : 0;
+}
+
+int kiss_fftnd_mgpu_exec(kiss_fftnd_mgpu_cfg st, kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, void *stream)
+{
+    if (!st || st->magic != KF_MAGIC_MGPU || !d_in || !d_out) return kf_fail(st, "kiss_fftnd_mgpu_exec: bad argument", KISS_FFT_CUDA_EINVAL, 0);
+    const int G = st->nranks, P = st->planes, d0 = st->d0, d1 = st->d1, d2 = st->d2, cw = st->cw, C = st->cols;
+    cudaStream_t main = (cudaStream_t)stream;
+    kiss_fft_cpx *recv = (kiss_fft_cpx *)st->recv_base;
+    const size_t blk = block_elems(st), chk = chunk_elems(st);
+
+    /* A: rows of the local slab, in place */
+    CU(kiss_fft_batch_dev(st->cfg2, d_in, d_in, (size_t)P * d1, (size_t)d2, (size_t)d2, 1, main));
+    if (G == 1) {
+        /* one rank: B writes the whole planes transposed into the "receive" buffer, C follows -- no exchange */
+        CU(kiss_fft_planes_pass_dev(st->cfg1, d_in, recv, (size_t)P, (size_t)d2, (size_t)d2, (size_t)d1 * d2, (size_t)d2 * d1, main));
+        CU(kiss_fft_axis_pass_dev(st->cfg0, recv, d_out, (size_t)C * d1, (size_t)C * d1, main));
+        return 0;
+    }
+    const unsigned epoch = ++st->epoch;
+    CU(cudaEventRecord(st->ev_start, main));
+    CU(cudaStreamWaitEvent(st->s_c, st->ev_start, 0));
+    if (st->p2p) {
+        /* every peer has finished reading its receive buffer (step C of the previous call) before anyone stores into it */
+        CU(kfcu_peer_signal((void *const *)st->d_peer_flags, G, st->rank, st->nchunks, epoch, main));
+        CU(kfcu_peer_wait(flag_ptr(st, st->rank), G, st->nchunks, epoch, main));
+    } else {
+        CU(cudaStreamWaitEvent(st->s_comm, st->ev_start, 0));
+    }
+    for (int j = 0; j < st->nchunks; ++j) {
+        /* B, chunk j: k2 columns s*C + j*cw + [0, cw) of every plane go to rank s, transposed */
+        kiss_fft_cpx *dst[KF_MGPU_MAXRANKS];
+        for (int s = 0; s < G; ++s) {
+            kiss_fft_cpx *base = st->p2p ? (kiss_fft_cpx *)st->peer_base[s] : st->send;
+            /* p2p: the receiver's layout [chunk][source = me][P][cw][d1]; NCCL: the local send buffer [chunk][dest s][P][cw][d1] */
+            dst[s] = base + (size_t)j * chk + (size_t)(st->p2p ? st->rank : s) * blk;
+        }
+        CU(kiss_fft_planes_pass_peers2_dev(st->cfg1, d_in + (size_t)j * cw, (kiss_fft_cpx *const *)dst, G, (size_t)P, (size_t)cw,
+                                           (size_t)C, (size_t)d2, (size_t)d1 * d2, (size_t)cw * d1, main));
+        if (st->p2p) {
+            CU(kfcu_peer_signal((void *const *)st->d_peer_flags, G, st->rank, j, epoch, main));
+            CU(kfcu_peer_wait(flag_ptr(st, st->rank), G, j, epoch, st->s_c));
+        } else {
+            CU(cudaEventRecord(st->ev_b[j], main));
+            CU(cudaStreamWaitEvent(st->s_comm, st->ev_b[j], 0));
+            NC(g_nccl.GroupStart());
+            for (int s = 0; s < G; ++s) {
+                NC(g_nccl.Send(st->send + (size_t)j * chk + (size_t)s * blk, blk * sizeof(kiss_fft_cpx), KF_NCCL_UINT8, s, st->comm, st->s_comm));
+                NC(g_nccl.Recv(recv + (size_t)j * chk + (size_t)s * blk, blk * sizeof(kiss_fft_cpx), KF_NCCL_UINT8, s, st->comm, st->s_comm));
+            }
+            NC(g_nccl.GroupEnd());
+            CU(cudaEventRecord(st->ev_x[j], st->s_comm));
+            CU(cudaStreamWaitEvent(st->s_c, st->ev_x[j], 0));
+        }
+        /* C, chunk j: axis 0 of the (G*P) x (cw*d1) matrix that has arrived from every rank */
+        CU(kiss_fft_axis_pass_dev(st->cfg0, recv + (size_t)j * chk, d_out + (size_t)j * cw * d1 * d0, (size_t)cw * d1, (size_t)cw * d1, st->s_c));
+    }
+    CU(cudaEventRecord(st->ev_done, st->s_c));
+    CU(cudaStreamWaitEvent(main, st->ev_done, 0));
+    return 0;
+}

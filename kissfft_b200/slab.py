@@ -84,6 +84,14 @@ class SlabGeometry:
         return (self.world - 1) * self.block_elems * itemsize
 
 
+class _null_ctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 def batch_shard(howmany, rank, world):
     """contiguous share of a batch of independent transforms: (first, count).  No communication is ever needed."""
     base, rem = divmod(howmany, world)
@@ -148,14 +156,19 @@ class SlabFFT3D:
             be.rows_inplace(x, stream)                               # A
             for s in range(g.world):
                 be.planes_cols(x, send, dst_rank=s, stream=stream, dst_block=s)
-            self._exchange(recv, send)                               # X
+            self._exchange(recv, send, stream)                       # X
         be.axis0(recv, out, stream)                                  # C
         return out
 
-    def _exchange(self, recv, send):
-        """block s of `send` goes to rank s; moved as bytes so that every datatype (Q15 included) is a type NCCL knows"""
-        u8 = self.torch.uint8
-        self.dist.all_to_all_single(recv.view(-1).view(u8), send.view(-1).view(u8), group=self.group)
+    def _exchange(self, recv, send, stream=0):
+        """block s of `send` goes to rank s; moved as bytes so that every datatype (Q15 included) is a type NCCL knows.
+        The collective is enqueued on `stream` (torch orders NCCL work against its CURRENT stream, so the caller's raw
+        stream is made current for the call -- otherwise the exchange would race with the kernels around it)."""
+        torch = self.torch
+        u8 = torch.uint8
+        ctx = torch.cuda.stream(torch.cuda.ExternalStream(stream)) if (stream and torch.cuda.is_available()) else _null_ctx()
+        with ctx:
+            self.dist.all_to_all_single(recv.view(-1).view(u8), send.view(-1).view(u8), group=self.group)
 
     def _forward_p2p(self, x, recv, stream):
         """steps A, B and the exchange fused and overlapped.
@@ -216,7 +229,7 @@ class SlabFFT3D:
         else:
             for s in range(g.world):
                 be.ref_axis1(work, send, s, stream)                  # B'
-            self._exchange(recv, send)                               # X'
+            self._exchange(recv, send, stream)                       # X'
         be.ref_axis2(recv, out, stream)                              # C'
         return out
 
@@ -240,6 +253,48 @@ class SlabFFT3D:
             dist.all_gather(parts, out.contiguous(), group=self.group)
             full = torch.cat(parts, dim=0)                # [d2][d1][d0][2]
         return full.permute(2, 1, 0, 3).contiguous()
+
+
+class MgpuFFT3D:
+    """kiss_fftnd_mgpu_* of the C library (include/kiss_fft_cuda.h, csrc/kf_mgpu.c) bound for torch tensors: the slab
+    transform with its orchestration, NCCL communicator, peer mapping and pipelining all inside the library.  This class
+    only carries the rendezvous id from rank 0 to the other ranks (through torch.distributed, as an MPI program would use
+    MPI_Bcast) and hands device pointers over.  Fast axis order (2, 1, exchange, 0), transposed-out result like SlabFFT3D."""
+
+    def __init__(self, dims, tname="float", inverse=False, p2p=True, group=None):
+        import torch
+        import torch.distributed as dist
+        import kissfft_b200
+        self.torch = torch
+        self.lib = kissfft_b200.get(tname)
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.geo = SlabGeometry(int(dims[0]), int(dims[1]), int(dims[2]), world, rank)
+        self.torch_dtype = {"float": torch.float32, "double": torch.float64, "int16_t": torch.int16, "int32_t": torch.int32}[tname]
+        ident = None
+        if world > 1:
+            box = [self.lib.mgpu_get_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0, group=group)
+            ident = box[0]
+        self.cfg = self.lib.mgpu_alloc(dims, rank, world, ident, inverse, self.lib.MGPU_P2P if p2p else 0)
+        self.info = self.lib.mgpu_info(self.cfg)
+
+    def alloc(self):
+        """(local input slab [P][d1][d2][2], output [C][d1][d0][2])"""
+        g = self.geo
+        dev = self.torch.device("cuda", self.torch.cuda.current_device())
+        return (self.torch.empty((g.planes, g.d1, g.d2, 2), dtype=self.torch_dtype, device=dev),
+                self.torch.empty((g.cols, g.d1, g.d0, 2), dtype=self.torch_dtype, device=dev))
+
+    def forward(self, x, out, stream=0):
+        """x is overwritten (rows transformed in place); stream-ordered on `stream`"""
+        self.lib.mgpu_exec(self.cfg, x, out, stream)
+        return out
+
+    def close(self):
+        if self.cfg:
+            self.lib.mgpu_free(self.cfg)
+            self.cfg = None
 
 
 class CudaBackend:

@@ -62,6 +62,16 @@ struct EmuEnv {
         std::memcpy(dst, src, bytes);
         ctr(bar)->fetch_add(1, std::memory_order_release);
     }
+    void mbar_expect(void*, unsigned) const {}
+    // emulated tensor-map box: gather ncol adjacent elements of nrows rows (`row_stride` elements apart) starting at src
+    void tensor_load_box(void* bar, void* dst, const void*, long long, int, long long, const void* src, long long row_stride, int ncol,
+                         int nrows, int elem_bytes, bool last) const
+    {
+        if (((uintptr_t)dst % 128) || ((uintptr_t)src % 16) || ((size_t)row_stride * elem_bytes) % 16 || ((size_t)ncol * elem_bytes) % 16) abort();
+        for (int r = 0; r < nrows; ++r)
+            std::memcpy((char*)dst + (size_t)r * ncol * elem_bytes, (const char*)src + (size_t)r * row_stride * elem_bytes, (size_t)ncol * elem_bytes);
+        if (last) ctr(bar)->fetch_add(1, std::memory_order_release);
+    }
     void mbar_wait(void* bar, int k) const
     {
         while (ctr(bar)->load(std::memory_order_acquire) < (unsigned long long)k + 1) std::this_thread::yield();
@@ -208,6 +218,33 @@ extern "C" int emul_fourstep(int nfft, int step, int inverse, const void* in, vo
             P.ncols = ncols;
             P.in_pdist = N;
             P.out_pdist = N;
+            return e.fn[mode](P, nblocks);
+        }
+    return -1;
+}
+
+// column-ring variants (tensor-map TMA input ring, KF_COLRING_LIST): mode kC2CCol (transposing, out row = column),
+// kC2CColTw / kC2CColCol with the geometry kf_launch.cu builds.  Returns -1 when this datatype build has no ring
+// plan for nfft, -2 when the geometry is not eligible (the launcher would then take the direct-load plan).
+#if defined(FIXED_POINT)
+#define KF_RING_TW(PT, on) nullptr
+#else
+#define KF_RING_TW(PT, on) ((on) ? run_fused<PT, kC2CColTw> : nullptr)
+#endif
+#define KF_RING_ROW(PT, c, tw, cc) { PT::D.N, { nullptr, (c) ? run_fused<PT, kC2CCol> : nullptr, nullptr, nullptr, KF_RING_TW(PT, tw), \
+                                     (cc) ? run_fused<PT, kC2CColCol> : nullptr } },
+static const Entry kRingTable[] = { KF_COLRING_LIST(KF_RING_ROW) { 0, { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr } } };
+extern "C" int emul_colring(int nfft, int mode, int inverse, const void* in, void* out, long long nplanes, long long ncols,
+                            long long col_stride, long long in_pdist, long long out_pdist, long long out_dist, const void* tw,
+                            const void* twbig, long long nblocks)
+{
+    for (const Entry& e : kRingTable)
+        if (e.N == nfft && e.fn[mode]) {
+            KParams<AT> P = mk_params(nfft, inverse, in, out, nplanes * ncols, 1, out_dist, col_stride, tw, twbig);
+            P.ncols = ncols;
+            P.in_pdist = in_pdist;
+            P.out_pdist = out_pdist;
+            if (ncols % 8 != 0) return -2;
             return e.fn[mode](P, nblocks);
         }
     return -1;

@@ -48,6 +48,7 @@ class Emulator:
         vp, ci, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
         self.lib.emul_fused.argtypes = [ci, ci, ci, vp, vp, ll, ll, ll, ll, vp, vp, ll]
         self.lib.emul_fourstep.argtypes = [ci, ci, ci, vp, vp, ll, ll, vp, vp, ll]
+        self.lib.emul_colring.argtypes = [ci, ci, ci, vp, vp, ll, ll, ll, ll, ll, ll, vp, vp, ll]
         self.lib.emul_fused_experimental.argtypes = [ci, ci, ci, vp, vp, ll, ll, ll, ll, vp, vp, ll]
         self.lib.emul_generic.argtypes = [ci, ci, ci, vp, ci, vp, vp, ll, ll, ll, ll, vp, vp, ci, ci, ll]
         self.lib.emul_stage.argtypes = [ci, ci, ci, ci, ci, vp, vp, ll, ll, ll, ll, ci, ci, vp, ci, ll]
@@ -97,6 +98,11 @@ class Emulator:
     def colcol(self, nfft, inverse, inp, out, nplanes, ncols, tw, nblocks=3):
         """axis pass that keeps the layout: plane p, column c: inp[p][j][c] (j < nfft) -> out[p][k][c]; False without a plan"""
         return self.lib.emul_fourstep(nfft, 1, int(inverse), _p(inp), _p(out), nplanes, ncols, _p(tw), None, nblocks) >= 0
+
+    def colring(self, nfft, mode, inverse, inp, out, nplanes, ncols, col_stride, in_pdist, out_pdist, out_dist, tw, twbig=None, nblocks=2):
+        """column modes through the tensor-map ring plans; returns the emulator's code (< 0: no plan / not eligible)"""
+        return self.lib.emul_colring(nfft, mode, int(inverse), _p(inp), _p(out), nplanes, ncols, col_stride, in_pdist, out_pdist,
+                                     out_dist, _p(tw), _p(twbig), nblocks)
 
     def generic(self, nfft, mode, inverse, factors, inp, out, howmany, in_dist, out_dist, in_stride, tw, stw=None,
                 tpc=2, nthreads=32, nblocks=2):

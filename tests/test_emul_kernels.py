@@ -112,6 +112,25 @@ def test_fftnd_in_layout(env):
     check(tname, c, o.fftnd(x), 64 * 128 * 4)
 
 
+def test_column_ring_plans(env):
+    """the tensor-map (TMA) input ring of the column modes: tiles of adjacent columns land as [row][column] boxes; the
+    transposing pass (kiss_fftnd.c:172-178) and the layout-keeping pass must match the oracle's 1-D transforms"""
+    tname, o, em = env
+    nfft, nplanes, ncols = 1024, 2, 24
+    x = random_input(tname, (nplanes, nfft, ncols), 77)
+    want = o.fft(np.ascontiguousarray(x.transpose(0, 2, 1, 3)).reshape(nplanes * ncols, nfft, 2)).reshape(nplanes, ncols, nfft, 2)
+    out = np.zeros((nplanes, ncols, nfft, 2), x.dtype)
+    rc = em.colring(nfft, 1, 0, x, out, nplanes, ncols, ncols, nfft * ncols, ncols * nfft, nfft, o.twiddles(nfft, 0), nblocks=2)
+    if rc == -1:
+        pytest.skip("no column-ring plan for this datatype build")
+    assert rc >= 0
+    check(tname, out, want, nfft)
+    out2 = np.zeros_like(x)
+    rc = em.colring(nfft, 5, 0, x, out2, nplanes, ncols, ncols, nfft * ncols, nfft * ncols, 1, o.twiddles(nfft, 0), nblocks=3)
+    assert rc >= 0
+    check(tname, out2, want.transpose(0, 2, 1, 3), nfft)
+
+
 def test_experimental_real_plans(env):
     """plan variants that are not in the product list yet (tests/emul/experimental_plans.h): paired groups with the
     even/odd lane mapping, with and without the input stage as second exchange buffer"""

@@ -608,6 +608,67 @@ def test_fused_fast_convolution(tname, nfft, nimp):
 
 
 @pytest.mark.parametrize("tname", ["float", "double"])
+@pytest.mark.parametrize("nfft,nimp", [(1000, 101), (300, 7), (8192, 2500), (0, 3000), (32768, 4097)])
+def test_fast_convolution_any_length(tname, nfft, nimp):
+    """lengths without a fused kernel (the reference's kiss_fastfir works for any size; its default rule gives 8192 for
+    filters over 2048 taps): composed from block gather + batched transforms + pointwise product, vs np.convolve"""
+    import kissfft_b200
+    lib = kissfft_b200.get(tname)
+    rng = np.random.default_rng(nimp)
+    imp = (rng.random((nimp, 2)) - 0.5).astype(lib.dtype)
+    cfg, n, ngood = lib.fastconv_alloc(imp, nfft)
+    assert n >= nimp and ngood == n - nimp + 1
+    nsamp = 5 * ngood + n + 3
+    x = (rng.random((nsamp, 2)) * 2 - 1).astype(lib.dtype)
+    d_in = dev(x)
+    d_out = torch.zeros_like(d_in)
+    done = lib.fastconv_dev(cfg, d_in, d_out, nsamp, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert done == ((nsamp - n) // ngood + 1) * ngood
+    got = host(d_out)
+    assert not got[done:].any()
+    xc, hc = x[:, 0].astype(np.float64) + 1j * x[:, 1], imp[:, 0].astype(np.float64) + 1j * imp[:, 1]
+    # the reference scales the response by a FLOAT 1/nfft in every build (kiss_fastfir.c:72,152): exact for powers of two only
+    full = np.convolve(xc, hc)[nimp - 1: nimp - 1 + done] * (float(np.float32(1.0 / n)) * n)
+    assert rel_rms(got[:done], np.stack([full.real, full.imag], -1)) <= 20 * TOL[tname] * np.log2(n)
+    lib.fastconv_free(cfg)
+
+
+@pytest.mark.parametrize("tname", ["float", "double"])
+@pytest.mark.parametrize("nfft,nimp", [(256, 33), (4096, 1000), (1000, 100), (0, 200), (16384, 5000)])
+def test_real_fast_convolution(tname, nfft, nimp):
+    """the reference's REAL_FASTFIR build (tools/kiss_fastfir.c:26-33, 91-95): real samples through kiss_fftr / kiss_fftri;
+    odd block advances (ngood) included.  Checked against the oracle's own fftr -> multiply -> fftri pipeline on one block
+    and against np.convolve on all of them."""
+    import kissfft_b200
+    lib, o = kissfft_b200.get(tname), Oracle(tname)
+    rng = np.random.default_rng(nimp + 1)
+    imp = (rng.random(nimp) - 0.5).astype(lib.dtype)
+    cfg, n, ngood = lib.fastconvr_alloc(imp, nfft)
+    nsamp = 4 * ngood + n + 5
+    x = (rng.random(nsamp) * 2 - 1).astype(lib.dtype)
+    d_in = dev(x)
+    d_out = torch.zeros_like(d_in)
+    done = lib.fastconvr_dev(cfg, d_in, d_out, nsamp, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert done == ((nsamp - n) // ngood + 1) * ngood
+    got = host(d_out)
+    assert not got[done:].any()
+    full = np.convolve(x.astype(np.float64), imp.astype(np.float64))[nimp - 1: nimp - 1 + done] * (float(np.float32(1.0 / n)) * n)
+    assert rel_rms(got[:done], full) <= 20 * TOL[tname] * np.log2(n)
+    # first block against the reference's arithmetic: fftr(block) * (fftr(rotated response) / nfft) -> fftri
+    rot = np.zeros(n, lib.dtype)
+    rot[0] = imp[nimp - 1]
+    rot[n - nimp + 1:] = imp[:nimp - 1]
+    H = o.fftr(rot[None])[0] * lib.dtype(np.float32(1.0 / n))
+    X = o.fftr(x[None, :n])[0]
+    Y = np.stack([X[:, 0] * H[:, 0] - X[:, 1] * H[:, 1], X[:, 0] * H[:, 1] + X[:, 1] * H[:, 0]], -1).astype(lib.dtype)
+    want = o.fftri(Y[None])[0][:ngood]
+    assert rel_rms(got[:ngood], want) <= 4 * TOL[tname] * np.log2(n)
+    lib.fastconv_free(cfg)
+
+
+@pytest.mark.parametrize("tname", ["float", "double"])
 @pytest.mark.parametrize("nfft", [16384, 65536, 1 << 20])
 def test_fourstep_long_rows(tname, nfft, monkeypatch):
     """default for float/double (KISSFFT_FOURSTEP=0 opts out): long contiguous rows as two fused column passes instead of one launch per radix stage"""

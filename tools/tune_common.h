@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../kissfft_b200/csrc/kf_twtab.h"
+#include "../kissfft_b200/csrc/kf_tmap.h"
 
 typedef kf::Arith<kiss_fft_scalar> AT;
 typedef AT::C CT;
@@ -30,9 +31,12 @@ static void launch_variant(const kf::KParams<AT>& P, unsigned grid, size_t smem)
     kf::kf_fused_kernel<AT, PT, MODE><<<grid, PT::D.threads(), smem>>>(P);
 }
 
-template <class PT>
+template <class PT, int MODE>
 static void prepare_variant(kf::KParams<AT>& P, const CT* h_tw, CT** d_gtw)
 {
+    if constexpr (kf::FusedLayout<AT, PT, MODE>::kColRing) {
+        if (!kf::col_ring_ok<AT, PT>(P) || kf::col_ring_encode<AT, PT, MODE>(P) != 0) { fprintf(stderr, "tensor map not encodable\n"); exit(3); }
+    }
     std::vector<CT> tab = kf::build_gtw<AT, PT>(h_tw);
     if (*d_gtw) cudaFree(*d_gtw);
     cudaMalloc(d_gtw, tab.size() * sizeof(CT));
@@ -52,7 +56,7 @@ static TuneEntry make_entry(const char* label)
     e.smem = kf::FusedLayout<AT, PT, MODE>::kTotal;
     e.kernel = (const void*)kf::kf_fused_kernel<AT, PT, MODE>;
     e.launch = launch_variant<PT, MODE>;
-    e.prepare = prepare_variant<PT>;
+    e.prepare = prepare_variant<PT, MODE>;
     e.rows_ok = kf::fused_rows<AT, PT, MODE>;
     return e;
 }
@@ -125,7 +129,15 @@ static int tune_main(int argc, char** argv, std::vector<TuneEntry>& vars, int nf
     P.cols_per_peer = 0;
     P.in = d_in; P.out = d_out; P.howmany = batch;
     P.in_dist = in_row; P.out_dist = out_row; P.in_stride = 1;
-    if (mode == kf::kC2CCol) { P.in_dist = 1; P.in_stride = batch; P.out_dist = nfft; }
+    if (mode == kf::kC2CCol || mode == kf::kC2CColCol) {
+        // TUNE_NCOLS=c: planes of c columns (row stride c elements, like an inner axis of an N-D array); default: one plane
+        const char* nc = getenv("TUNE_NCOLS");
+        const long long ncols = nc ? atoll(nc) : 0;
+        P.in_dist = 1;
+        P.in_stride = ncols > 0 ? ncols : batch;
+        P.out_dist = (mode == kf::kC2CCol) ? nfft : 1;
+        if (ncols > 0) { P.ncols = ncols; P.in_pdist = (long long)nfft * ncols; P.out_pdist = (long long)nfft * ncols; }
+    }
     P.tw = d_tw; P.stw = d_stw;
     CT z{};
     P.pc.epi3 = AT::load(nfft % 3 == 0 ? h_tw[nfft / 3] : z);
