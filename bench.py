@@ -490,9 +490,10 @@ def run_ours(args, w, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dist = None
-    # keep stdout to the single JSON line: the image exports NCCL_DEBUG=VERSION, which makes NCCL print its banner there
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # (the image exports NCCL_DEBUG=VERSION, which makes NCCL print its banner on stdout: main() has moved fd 1 to stderr
+    # for the duration of the run, and the variable is dropped so the banner does not appear at all)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ.pop("NCCL_DEBUG")
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
@@ -706,8 +707,7 @@ def run_ours(args, w, rank, world, local_rank):
                 line["cpu_baseline"] = best_cpu_reference(w, 3, detail=True)
             except Exception as exc:   # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"error": str(exc)}
-        print(json.dumps(line))
-        sys.stdout.flush()
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -750,10 +750,28 @@ def run_reference(args, w, rank, world):
             "cpu_baseline": info,
             "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line, on the real stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL banners, warnings) goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

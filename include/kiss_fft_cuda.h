@@ -80,10 +80,15 @@ int KISS_FFT_API kiss_fft_planes_pass_peers_dev(kiss_fft_cfg cfg, const kiss_fft
 
 /* the same with the peers' column blocks spread out in the input: block s reads the input columns
  * s*peer_col_dist + [0, cols_per_peer) of every plane (peer_col_dist >= cols_per_peer).  Lets one launch handle a CHUNK
- * of every destination's column range, so that the exchange pipelines chunk by chunk (kiss_fftnd_mgpu_exec). */
+ * of every destination's column range, so that the exchange pipelines chunk by chunk (kiss_fftnd_mgpu_exec).
+ * out_col_dist > 0: row (plane p, column c of block s) lands at d_peers[s][p*out_plane_dist + c*out_col_dist + k] (0: the
+ * rows of a plane back to back, c*nfft) -- lets the receiver keep all planes of one column together.
+ * max_ctas > 0 caps the persistent grid of this launch: a pass whose stores cross NVLink is link-bound and needs only a
+ * fraction of the SMs, the rest stay free for HBM-bound kernels on other streams. */
 int KISS_FFT_API kiss_fft_planes_pass_peers2_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *const *d_peers,
                                                  int npeers, size_t nplanes, size_t cols_per_peer, size_t peer_col_dist,
-                                                 size_t col_stride, size_t in_plane_dist, size_t out_plane_dist, void *stream);
+                                                 size_t col_stride, size_t in_plane_dist, size_t out_plane_dist, size_t out_col_dist,
+                                                 int max_ctas, void *stream);
 
 /* kiss_fftndr / kiss_fftndri on device buffers (kiss_fftndr.c:86-132) */
 int KISS_FFT_API kiss_fftndr_dev(kiss_fftndr_cfg cfg, const kiss_fft_scalar *d_time, kiss_fft_cpx *d_freq, void *stream);

@@ -97,7 +97,7 @@ class KissFFT:
         L.kiss_fft_axis_pass_dev.argtypes = [vp, vp, vp, sz, sz, vp]
         L.kiss_fft_planes_pass_dev.argtypes = [vp, vp, vp, sz, sz, sz, sz, sz, vp]
         L.kiss_fft_planes_pass_peers_dev.argtypes = [vp, vp, ctypes.POINTER(vp), ci, sz, sz, sz, sz, sz, vp]
-        L.kiss_fft_planes_pass_peers2_dev.argtypes = [vp, vp, ctypes.POINTER(vp), ci, sz, sz, sz, sz, sz, sz, vp]
+        L.kiss_fft_planes_pass_peers2_dev.argtypes = [vp, vp, ctypes.POINTER(vp), ci, sz, sz, sz, sz, sz, sz, sz, ci, vp]
         L.kiss_fftnd_mgpu_get_id.argtypes = [vp]
         L.kiss_fftnd_mgpu_alloc.restype = vp
         L.kiss_fftnd_mgpu_alloc.argtypes = [ctypes.POINTER(ci), ci, ci, ci, ci, vp, ctypes.c_uint]

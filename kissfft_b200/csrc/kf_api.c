@@ -745,7 +745,7 @@ int kiss_fft_planes_pass_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_ff
 
 int kiss_fft_planes_pass_peers2_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *const *d_peers, int npeers,
                                     size_t nplanes, size_t cols_per_peer, size_t peer_col_dist, size_t col_stride,
-                                    size_t in_plane_dist, size_t out_plane_dist, void *stream)
+                                    size_t in_plane_dist, size_t out_plane_dist, size_t out_col_dist, int max_ctas, void *stream)
 {
     if (!cfg || cfg->magic != KF_MAGIC_1D || !d_in || !d_peers || npeers < 1 || npeers > 16 || col_stride < 1 ||
         peer_col_dist < cols_per_peer) {
@@ -756,7 +756,7 @@ int kiss_fft_planes_pass_peers2_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, 
     KF_CHECK(kf_get_devplan(cfg, NULL, &dp));
     KF_CHECK(kfcu_exec_planes_peers((kfcu_plan *)&dp->plan, d_in, (void *const *)d_peers, npeers, (long long)nplanes,
                                     (long long)cols_per_peer, (long long)peer_col_dist, (long long)col_stride,
-                                    (long long)in_plane_dist, (long long)out_plane_dist, stream));
+                                    (long long)in_plane_dist, (long long)out_plane_dist, (long long)out_col_dist, max_ctas, stream));
     return 0;
 }
 
@@ -765,7 +765,7 @@ int kiss_fft_planes_pass_peers_dev(kiss_fft_cfg cfg, const kiss_fft_cpx *d_in, k
                                    size_t out_plane_dist, void *stream)
 {
     return kiss_fft_planes_pass_peers2_dev(cfg, d_in, d_peers, npeers, nplanes, cols_per_peer, cols_per_peer, col_stride, in_plane_dist,
-                                           out_plane_dist, stream);
+                                           out_plane_dist, 0, 0, stream);
 }
 
 static int kf_real_args_ok(const void *d_real, size_t real_dist)

@@ -47,6 +47,7 @@ struct KParams {
     typename A::C* peer[16];
     long long cols_per_peer, peer_col_dist;
     int npeers;
+    int max_ctas;                // host side only: cap on the persistent grid of this launch (0 = fill the device)
     KF_HD long long in_col(long long col) const   // input column index of column `col` of a plane
     {
         return (npeers > 0 && peer_col_dist != cols_per_peer) ? (col / cols_per_peer) * peer_col_dist + col % cols_per_peer : col;

@@ -56,7 +56,7 @@ int kfcu_has_colcol(int nfft);   /* step 1 alone (every datatype): an axis pass 
  * buffers: column block s is written through peers[s] (+ p*out_pdist + c_local*nfft) */
 int kfcu_exec_planes_peers(kfcu_plan *plan, const void *d_in, void *const *peers, int npeers, long long nplanes,
                            long long cols_per_peer, long long peer_col_dist, long long col_stride, long long in_pdist,
-                           long long out_pdist, void *stream);
+                           long long out_pdist, long long out_col_dist, int max_ctas, void *stream);
 /* flags between the GPUs of the slab transform: d_flag_ptrs = device array of every rank's flag words (mapped here); a
  * signal sets word (slot*16 + rank) of every rank to `epoch`, a wait spins until all nranks words of `slot` reached it */
 int kfcu_peer_signal(void *const *d_flag_ptrs, int nranks, int rank, int slot, unsigned epoch, void *stream);

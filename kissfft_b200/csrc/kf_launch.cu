@@ -57,6 +57,7 @@ static KParams<AT> make_params(const kfcu_plan* pl, const void* d_in, void* d_ou
     P.npeers = 0;
     P.cols_per_peer = 0;
     P.peer_col_dist = 0;
+    P.max_ctas = 0;
     P.in = (const CT*)d_in;
     P.out = (CT*)d_out;
     P.howmany = howmany;
@@ -146,6 +147,7 @@ static int launch_fused(kfcu_plan* pl, KParams<AT>& P, cudaStream_t st)
     long long grid = (long long)device_info().sms * blocks_per_sm[dev];
     if (grid > ntiles) grid = ntiles;
     if (const int lim = g_grid_limit.load(std::memory_order_relaxed); lim > 0 && grid > lim) grid = lim;
+    if (P.max_ctas > 0 && grid > P.max_ctas) grid = P.max_ctas;      // per-launch cap (link-bound launches share the SMs)
     if (grid < 1) return 0;
     kern<<<(unsigned)grid, D.threads(), smem, st>>>(P);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -320,12 +322,13 @@ extern "C" int kfcu_has_fourstep(int nfft)
 // the same pass with the columns of every plane split into npeers blocks; block s goes through peers[s]
 extern "C" int kfcu_exec_planes_peers(kfcu_plan* plan, const void* d_in, void* const* peers, int npeers, long long nplanes,
                                       long long cols_per_peer, long long peer_col_dist, long long col_stride, long long in_pdist,
-                                      long long out_pdist, void* stream)
+                                      long long out_pdist, long long out_col_dist, int max_ctas, void* stream)
 {
     if (!plan || !d_in || !peers || npeers < 1 || npeers > 16 || nplanes < 0 || cols_per_peer < 1 || peer_col_dist < cols_per_peer) return KFCU_EINVAL;
     if (nplanes == 0) return 0;
     const long long ncols = cols_per_peer * npeers;
-    KParams<AT> P = make_params(plan, d_in, peers[0], nplanes * ncols, 1, plan->nfft, col_stride);
+    // row (plane p, column c of peer s) lands at peers[s] + p*out_pdist + c*out_col_dist (default: rows back to back)
+    KParams<AT> P = make_params(plan, d_in, peers[0], nplanes * ncols, 1, out_col_dist > 0 ? out_col_dist : plan->nfft, col_stride);
     P.ncols = ncols;
     P.in_pdist = in_pdist;
     P.out_pdist = out_pdist;
@@ -333,6 +336,7 @@ extern "C" int kfcu_exec_planes_peers(kfcu_plan* plan, const void* d_in, void* c
     P.cols_per_peer = cols_per_peer;
     P.peer_col_dist = peer_col_dist;
     for (int s = 0; s < npeers; ++s) P.peer[s] = (CT*)peers[s];
+    P.max_ctas = max_ctas;
     return launch_col(kC2CCol, plan, P, (cudaStream_t)stream);
 }
 
@@ -443,7 +447,7 @@ __global__ void kf_peer_signal_kernel(unsigned* const* flags, int nranks, int ra
     }
 }
 // waits until every source rank has signalled `slot` for this epoch (epochs only grow; wrap-around safe comparison).
-// Gives up after ~2 s and traps, so a lost peer cannot hang the GPU.
+// Gives up after ~20 s and traps, so a lost peer cannot hang the GPU.
 __global__ void kf_peer_wait_kernel(const unsigned* mine, int nranks, int slot, unsigned epoch)
 {
     const int s = (int)threadIdx.x;
@@ -451,7 +455,7 @@ __global__ void kf_peer_wait_kernel(const unsigned* mine, int nranks, int slot, 
         const volatile unsigned* f = mine + slot * 16 + s;
         const long long t0 = clock64();
         while ((int)(*f - epoch) < 0) {
-            if (clock64() - t0 > 4000000000LL) __trap();
+            if (clock64() - t0 > 40000000000LL) __trap();
         }
         __threadfence_system();
     }

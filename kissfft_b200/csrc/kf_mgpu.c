@@ -17,8 +17,19 @@
  *          a flag per (chunk, source rank) in the receiver's memory says "landed".
  *   C. axis 0 of chunk j, as soon as chunk j has arrived from every rank  kiss_fft_axis_pass_dev  [d2/G][d1][d0]
  *
- * The receive buffer is laid out [chunk j][source rank r][P][cw][d1]: chunk j is one dense (G*P) x (cw*d1) matrix for
- * step C and one contiguous piece per (source, chunk) for NCCL.  Output: X[k0][k1][k2] stored as out[k2 - r*d2/G][k1][k0]
+ * Pipeline (three streams): the local planes are cut into `pchunks` groups as well.  A(i) runs on the caller's stream;
+ * B(i, 0) follows A(i) on a second stream, so the link-bound stores of the first k2 chunk overlap the rows of the next
+ * plane groups; then B(., 1), B(., 2), ... while C(j-1) runs on a third stream as soon as chunk j-1 has landed from every
+ * rank.  Exposed: A(0), the exchange itself, and C of the last chunk.  Launches of B whose stores cross NVLink are
+ * capped to a fraction of the SMs (KISSFFT_MGPU_B_CTAS, default 48): they are link-bound, and the persistent CTAs of an
+ * uncapped launch would keep the HBM-bound kernels of the other streams off the SMs until it ends.
+ *
+ * Receive buffer layout.  NCCL: [chunk j][source rank r][P][cw][d1] -- one contiguous piece per (source, chunk), and chunk
+ * j is a dense (G*P) x (cw*d1) matrix for step C (kiss_fft_axis_pass_dev).  Peer stores: [chunk j][c][i0 = r*P + p][d1] --
+ * the source's kernel places every row itself, so all d0 planes of one k2 column sit together and step C is a
+ * plane-batched pass (kiss_fft_planes_pass_dev, cw planes of d0 x d1) whose rows are 8 KiB apart instead of cw*d1*8
+ * bytes: address translation stays within a few pages per tile and the tensor-map input ring applies
+ * (profiles/r02/tune_r2c_f32_col1024_*: 0.88 of the HBM peak against 0.6 for rows on different pages).  Output: X[k0][k1][k2] stored as out[k2 - r*d2/G][k1][k0]
  * on rank r ("transposed out", distributed along k2), the usual contract of slab FFTs.
  *
  * Host code is C; the only CUDA code it needs beyond the library's own entry points are the two flag kernels
@@ -88,6 +99,7 @@ struct kiss_fftnd_mgpu_state {
     uint32_t magic;
     int d0, d1, d2, inverse, rank, nranks, device;
     int planes, cols, nchunks, cw; /* P, C = d2/G, chunks of the k2 columns, columns per chunk */
+    int pchunks, b_ctas;           /* groups of local planes (pipelining of A against B); CTA cap of link-bound B launches */
     unsigned flags;
     int p2p;                       /* peer-store exchange active */
     kiss_fft_cfg cfg0, cfg1, cfg2;
@@ -98,8 +110,8 @@ struct kiss_fftnd_mgpu_state {
     char *peer_base[KF_MGPU_MAXRANKS]; /* every rank's recv_base as mapped here (own entry = recv_base) */
     unsigned **d_peer_flags;       /* device copy of the G flag-array pointers */
     unsigned epoch;
-    cudaStream_t s_comm, s_c;
-    cudaEvent_t ev_start, ev_b[KF_MGPU_MAXCHUNKS], ev_x[KF_MGPU_MAXCHUNKS], ev_done;
+    cudaStream_t s_comm, s_c, s_b;
+    cudaEvent_t ev_start, ev_a[KF_MGPU_MAXCHUNKS], ev_b[KF_MGPU_MAXCHUNKS], ev_x[KF_MGPU_MAXCHUNKS], ev_done, ev_bdone;
     char err[256];
 };
 
@@ -208,7 +220,7 @@ kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int invers
     st->planes = st->d0 / nranks;
     st->cols = st->d2 / nranks;
     /* chunks of the k2 columns: as many as requested / up to 4, keeping whole 16-column tiles per chunk where possible */
-    int want = 4;
+    int want = nranks <= 2 ? 2 : 4;    /* measured at G = 2 (profiles/r02/mgpu_g2_knobs.txt): more chunks only add launches */
     const char *env = getenv("KISSFFT_MGPU_CHUNKS");
     if (env && atoi(env) > 0) want = atoi(env);
     if (want > KF_MGPU_MAXCHUNKS) want = KF_MGPU_MAXCHUNKS;
@@ -217,6 +229,21 @@ kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int invers
     for (int c = want; c >= 1; --c)
         if (st->cols % c == 0 && ((st->cols / c) % 16 == 0 || c == 1)) { st->nchunks = c; break; }
     st->cw = st->cols / st->nchunks;
+    st->pchunks = 1;
+    if (nranks > 1)
+        for (int c = 2; c >= 1; --c)
+            if (st->planes % c == 0) { st->pchunks = c; break; }
+    env = getenv("KISSFFT_MGPU_PCHUNKS");
+    if (env && atoi(env) > 0 && atoi(env) <= KF_MGPU_MAXCHUNKS && st->planes % atoi(env) == 0) st->pchunks = atoi(env);
+    /* link-bound B launches need sms * (B at full rate / its NVLink time) CTAs: about 0.32 * G/(G-1) of the device
+     * (2 x 8 GiB/G at 5.7 TB/s against 8 GiB (G-1)/G^2 at 0.77 TB/s), measured best at G = 2: 96 of 148 */
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        st->b_ctas = nranks > 1 ? (int)(0.325 * sms * nranks / (nranks - 1)) : 0;
+    }
+    env = getenv("KISSFFT_MGPU_B_CTAS");
+    if (env && atoi(env) >= 0) st->b_ctas = atoi(env);
     int ok = cudaGetDevice(&st->device) == cudaSuccess;
     st->cfg0 = kiss_fft_alloc(st->d0, st->inverse, NULL, NULL);
     st->cfg1 = kiss_fft_alloc(st->d1, st->inverse, NULL, NULL);
@@ -228,10 +255,13 @@ kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int invers
          cudaMemset(st->recv_base + st->recv_bytes, 0, KF_FLAG_BYTES) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&st->s_comm, cudaStreamNonBlocking) == cudaSuccess &&
          cudaStreamCreateWithFlags(&st->s_c, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&st->s_b, cudaStreamNonBlocking) == cudaSuccess &&
          cudaEventCreateWithFlags(&st->ev_start, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&st->ev_bdone, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&st->ev_done, cudaEventDisableTiming) == cudaSuccess;
     for (int j = 0; ok && j < KF_MGPU_MAXCHUNKS; ++j)
         ok = cudaEventCreateWithFlags(&st->ev_b[j], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&st->ev_a[j], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&st->ev_x[j], cudaEventDisableTiming) == cudaSuccess;
     if (ok && nranks > 1) {
         ok = kf_nccl_load() == 0;
@@ -267,10 +297,13 @@ void kiss_fftnd_mgpu_free(kiss_fftnd_mgpu_cfg st)
     if (st->send) cudaFree(st->send);
     if (st->s_comm) cudaStreamDestroy(st->s_comm);
     if (st->s_c) cudaStreamDestroy(st->s_c);
+    if (st->s_b) cudaStreamDestroy(st->s_b);
+    if (st->ev_bdone) cudaEventDestroy(st->ev_bdone);
     if (st->ev_start) cudaEventDestroy(st->ev_start);
     if (st->ev_done) cudaEventDestroy(st->ev_done);
     for (int j = 0; j < KF_MGPU_MAXCHUNKS; ++j) {
         if (st->ev_b[j]) cudaEventDestroy(st->ev_b[j]);
+        if (st->ev_a[j]) cudaEventDestroy(st->ev_a[j]);
         if (st->ev_x[j]) cudaEventDestroy(st->ev_x[j]);
     }
     kiss_fft_free(st->cfg0);
@@ -296,40 +329,52 @@ int kiss_fftnd_mgpu_exec(kiss_fftnd_mgpu_cfg st, kiss_fft_cpx *d_in, kiss_fft_cp
     cudaStream_t main = (cudaStream_t)stream;
     kiss_fft_cpx *recv = (kiss_fft_cpx *)st->recv_base;
     const size_t blk = block_elems(st), chk = chunk_elems(st);
-
-    /* A: rows of the local slab, in place */
-    CU(kiss_fft_batch_dev(st->cfg2, d_in, d_in, (size_t)P * d1, (size_t)d2, (size_t)d2, 1, main));
     if (G == 1) {
-        /* one rank: B writes the whole planes transposed into the "receive" buffer, C follows -- no exchange */
+        /* one rank: rows, then B writes the whole planes transposed into the "receive" buffer, C follows -- no exchange */
+        CU(kiss_fft_batch_dev(st->cfg2, d_in, d_in, (size_t)P * d1, (size_t)d2, (size_t)d2, 1, main));
         CU(kiss_fft_planes_pass_dev(st->cfg1, d_in, recv, (size_t)P, (size_t)d2, (size_t)d2, (size_t)d1 * d2, (size_t)d2 * d1, main));
         CU(kiss_fft_axis_pass_dev(st->cfg0, recv, d_out, (size_t)C * d1, (size_t)C * d1, main));
         return 0;
     }
     const unsigned epoch = ++st->epoch;
+    const int NP = st->pchunks, Pc = P / NP;
     CU(cudaEventRecord(st->ev_start, main));
     CU(cudaStreamWaitEvent(st->s_c, st->ev_start, 0));
+    CU(cudaStreamWaitEvent(st->s_b, st->ev_start, 0));
     if (st->p2p) {
         /* every peer has finished reading its receive buffer (step C of the previous call) before anyone stores into it */
-        CU(kfcu_peer_signal((void *const *)st->d_peer_flags, G, st->rank, st->nchunks, epoch, main));
-        CU(kfcu_peer_wait(flag_ptr(st, st->rank), G, st->nchunks, epoch, main));
+        CU(kfcu_peer_signal((void *const *)st->d_peer_flags, G, st->rank, st->nchunks, epoch, st->s_b));
+        CU(kfcu_peer_wait(flag_ptr(st, st->rank), G, st->nchunks, epoch, st->s_b));
     } else {
         CU(cudaStreamWaitEvent(st->s_comm, st->ev_start, 0));
     }
+    /* A(i): rows of plane group i, in place, on the caller's stream */
+    for (int i = 0; i < NP; ++i) {
+        kiss_fft_cpx *rows = d_in + (size_t)i * Pc * d1 * d2;
+        CU(kiss_fft_batch_dev(st->cfg2, rows, rows, (size_t)Pc * d1, (size_t)d2, (size_t)d2, 1, main));
+        CU(cudaEventRecord(st->ev_a[i], main));
+    }
     for (int j = 0; j < st->nchunks; ++j) {
-        /* B, chunk j: k2 columns s*C + j*cw + [0, cw) of every plane go to rank s, transposed */
-        kiss_fft_cpx *dst[KF_MGPU_MAXRANKS];
-        for (int s = 0; s < G; ++s) {
-            kiss_fft_cpx *base = st->p2p ? (kiss_fft_cpx *)st->peer_base[s] : st->send;
-            /* p2p: the receiver's layout [chunk][source = me][P][cw][d1]; NCCL: the local send buffer [chunk][dest s][P][cw][d1] */
-            dst[s] = base + (size_t)j * chk + (size_t)(st->p2p ? st->rank : s) * blk;
+        for (int i = 0; i < NP; ++i) {
+            /* B(i, j): k2 columns s*C + j*cw + [0, cw) of the planes of group i go to rank s, transposed */
+            kiss_fft_cpx *dst[KF_MGPU_MAXRANKS];
+            for (int s = 0; s < G; ++s) {
+                if (st->p2p)    /* the receiver's layout [chunk][c][i0 = me*P + plane][d1] */
+                    dst[s] = (kiss_fft_cpx *)st->peer_base[s] + (size_t)j * chk + ((size_t)st->rank * P + (size_t)i * Pc) * d1;
+                else            /* the local send buffer [chunk][dest s][P][cw][d1] */
+                    dst[s] = st->send + (size_t)j * chk + (size_t)s * blk + (size_t)i * Pc * cw * d1;
+            }
+            if (j == 0) CU(cudaStreamWaitEvent(st->s_b, st->ev_a[i], 0));
+            CU(kiss_fft_planes_pass_peers2_dev(st->cfg1, d_in + (size_t)i * Pc * d1 * d2 + (size_t)j * cw, (kiss_fft_cpx *const *)dst, G,
+                                               (size_t)Pc, (size_t)cw, (size_t)C, (size_t)d2, (size_t)d1 * d2,
+                                               st->p2p ? (size_t)d1 : (size_t)cw * d1, st->p2p ? (size_t)d0 * d1 : 0,
+                                               st->p2p ? st->b_ctas : 0, st->s_b));
         }
-        CU(kiss_fft_planes_pass_peers2_dev(st->cfg1, d_in + (size_t)j * cw, (kiss_fft_cpx *const *)dst, G, (size_t)P, (size_t)cw,
-                                           (size_t)C, (size_t)d2, (size_t)d1 * d2, (size_t)cw * d1, main));
         if (st->p2p) {
-            CU(kfcu_peer_signal((void *const *)st->d_peer_flags, G, st->rank, j, epoch, main));
+            CU(kfcu_peer_signal((void *const *)st->d_peer_flags, G, st->rank, j, epoch, st->s_b));
             CU(kfcu_peer_wait(flag_ptr(st, st->rank), G, j, epoch, st->s_c));
         } else {
-            CU(cudaEventRecord(st->ev_b[j], main));
+            CU(cudaEventRecord(st->ev_b[j], st->s_b));
             CU(cudaStreamWaitEvent(st->s_comm, st->ev_b[j], 0));
             NC(g_nccl.GroupStart());
             for (int s = 0; s < G; ++s) {
@@ -340,10 +385,16 @@ int kiss_fftnd_mgpu_exec(kiss_fftnd_mgpu_cfg st, kiss_fft_cpx *d_in, kiss_fft_cp
             CU(cudaEventRecord(st->ev_x[j], st->s_comm));
             CU(cudaStreamWaitEvent(st->s_c, st->ev_x[j], 0));
         }
-        /* C, chunk j: axis 0 of the (G*P) x (cw*d1) matrix that has arrived from every rank */
-        CU(kiss_fft_axis_pass_dev(st->cfg0, recv + (size_t)j * chk, d_out + (size_t)j * cw * d1 * d0, (size_t)cw * d1, (size_t)cw * d1, st->s_c));
+        /* C(j): axis 0 of what has arrived from every rank */
+        if (st->p2p)
+            CU(kiss_fft_planes_pass_dev(st->cfg0, recv + (size_t)j * chk, d_out + (size_t)j * cw * d1 * d0, (size_t)cw, (size_t)d1, (size_t)d1,
+                                        (size_t)d0 * d1, (size_t)d1 * d0, st->s_c));
+        else
+            CU(kiss_fft_axis_pass_dev(st->cfg0, recv + (size_t)j * chk, d_out + (size_t)j * cw * d1 * d0, (size_t)cw * d1, (size_t)cw * d1, st->s_c));
     }
+    CU(cudaEventRecord(st->ev_bdone, st->s_b));
     CU(cudaEventRecord(st->ev_done, st->s_c));
+    CU(cudaStreamWaitEvent(main, st->ev_bdone, 0));
     CU(cudaStreamWaitEvent(main, st->ev_done, 0));
     return 0;
 }

@@ -35,6 +35,30 @@ static int run_rank(int rank, int G, const int *dims, unsigned flags, int iters,
 {
     const size_t d0 = dims[0], d1 = dims[1], d2 = dims[2], n = d0 * d1 * d2, P = d0 / G, C = d2 / G;
     CK(cudaSetDevice(rank));
+    if (getenv("MGPU_TEST_TIMING_ONLY")) {      /* tuning aid: no host arrays, no verification, just the fenced timing */
+        kiss_fftnd_mgpu_cfg c2 = kiss_fftnd_mgpu_alloc(dims, 3, 0, rank, G, id, flags);
+        if (!c2) { fprintf(stderr, "rank %d: alloc failed: %s\n", rank, kiss_fftnd_mgpu_last_error()); return 11; }
+        kiss_fft_cpx *a, *b;
+        CK(cudaMalloc((void **)&a, sizeof(kiss_fft_cpx) * P * d1 * d2));
+        CK(cudaMalloc((void **)&b, sizeof(kiss_fft_cpx) * C * d1 * d0));
+        CK(cudaMemset(a, 0, sizeof(kiss_fft_cpx) * P * d1 * d2));
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        for (int i = 0; i < 3; ++i) CK(kiss_fftnd_mgpu_exec(c2, a, b, NULL));
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0, NULL));
+        for (int i = 0; i < iters; ++i) CK(kiss_fftnd_mgpu_exec(c2, a, b, NULL));
+        CK(cudaEventRecord(e1, NULL));
+        CK(cudaEventSynchronize(e1));
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, e0, e1));
+        printf("{\"rank\": %d, \"ranks\": %d, \"p2p\": %d, \"chunks\": %d, \"ms\": %.4f}\n", rank, G, kiss_fftnd_mgpu_uses_p2p(c2),
+               kiss_fftnd_mgpu_chunks(c2), t / (iters > 0 ? iters : 1));
+        fflush(stdout);
+        kiss_fftnd_mgpu_free(c2);
+        return 0;
+    }
     kiss_fft_cpx *h = (kiss_fft_cpx *)malloc(sizeof(kiss_fft_cpx) * n);
     unsigned long long s = 88172645463325252ULL;
     for (size_t i = 0; i < n; ++i) { h[i].r = rnd(&s); h[i].i = rnd(&s); }

@@ -86,6 +86,8 @@ static KParams<AT> mk_params(int nfft, int inverse, const void* in, void* out, l
     P.in_pdist = P.out_pdist = 0;
     P.npeers = 0;
     P.cols_per_peer = 0;
+    P.peer_col_dist = 0;
+    P.max_ctas = 0;
     P.in = (const CT*)in;
     P.out = (CT*)out;
     P.howmany = howmany;

@@ -127,6 +127,8 @@ static int tune_main(int argc, char** argv, std::vector<TuneEntry>& vars, int nf
     P.in_pdist = P.out_pdist = 0;
     P.npeers = 0;
     P.cols_per_peer = 0;
+    P.peer_col_dist = 0;
+    P.max_ctas = 0;
     P.in = d_in; P.out = d_out; P.howmany = batch;
     P.in_dist = in_row; P.out_dist = out_row; P.in_stride = 1;
     if (mode == kf::kC2CCol || mode == kf::kC2CColCol) {
