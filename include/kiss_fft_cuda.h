@@ -111,8 +111,15 @@ int KISS_FFT_API kiss_fftndri_dev(kiss_fftndr_cfg cfg, const kiss_fft_cpx *d_fre
  *   kiss_fftnd_mgpu_exec     COLLECTIVE, stream-ordered on `stream`: d_in is overwritten (its rows are transformed in
  *                            place, like kiss_fft with fin == fout); d_out receives the transposed-out slab.
  *   kiss_fftnd_mgpu_free     COLLECTIVE. */
+/*                            KISS_FFT_MGPU_REFERENCE_ORDER: the exact mode for the fixed-point builds.  kiss_fftnd sweeps the
+ *                            axes in the order 0, 1, 2 and Q15 / Q31 results depend on it; this mode keeps that order with
+ *                            the same single exchange by starting from slabs along the LAST axis: rank r passes
+ *                            x[i0][i1][r*d2/G + c] stored [d0][d1][d2/G] and receives X[r*d0/G + p][k1][k2] stored
+ *                            [d0/G][d1][d2] -- natural order, bit-identical to the rows kiss_fftnd writes (every datatype).
+ *                            Can be combined with KISS_FFT_MGPU_P2P. */
 #define KISS_FFT_MGPU_ID_BYTES 128
 #define KISS_FFT_MGPU_P2P 1u
+#define KISS_FFT_MGPU_REFERENCE_ORDER 2u
 typedef struct kiss_fftnd_mgpu_state *kiss_fftnd_mgpu_cfg;
 int KISS_FFT_API kiss_fftnd_mgpu_get_id(void *id);
 kiss_fftnd_mgpu_cfg KISS_FFT_API kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int inverse_fft, int rank, int nranks,

@@ -212,6 +212,7 @@ class KissFFT:
 
     # ---- kiss_fftnd over several GPUs (one process per GPU), include/kiss_fft_cuda.h ----
     MGPU_P2P = 1
+    MGPU_REFERENCE_ORDER = 2
 
     def mgpu_get_id(self):
         """rank 0: the 128-byte rendezvous id to hand to every rank's mgpu_alloc"""

@@ -895,12 +895,74 @@ static int kf_axes_inlayout(kiss_fftnd_cfg st, int naxes, long long inner, const
     return 0;
 }
 
+#ifndef FIXED_POINT
+/* 3-D, float / double: three transposing passes, none of which strides over whole planes.
+ *
+ * kiss_fftnd.c:156-188 views the buffer as dims[k] x stride in every sweep, so each sweep walks columns whose elements lie
+ * a whole plane apart (8 MiB at 1024^3): every row segment of a tile sits on its own page and the pass is bound by
+ * address translation, not by HBM (profiles/r02/stride_experiment.txt: time ~ 1 / segment width, whatever the stride's
+ * alignment).  A transposing pass may put each finished row wherever it likes at no cost -- rows are written as whole
+ * contiguous lines anyway -- which is enough to keep the columns of EVERY pass inside one plane (row pitch = one line):
+ *     in  [i0][i1][i2]  --axis 1 of plane i0-->  A [i2][i0][k1]     (row (i0, i2) of the result goes to A[i2][i0])
+ *     A   [i2][i0][k1]  --axis 0 of plane i2-->  B [k1][i2][k0]
+ *     B   [k1][i2][k0]  --axis 2 of plane k1-->  out [k0][k1][k2]   natural order, as kiss_fftnd leaves it
+ * Axis order 1, 0, 2 instead of the reference's 0, 1, 2: equal to rounding in float / double, NOT the same bits in fixed
+ * point, which therefore keeps the in-layout path.  Needs one work buffer the size of the array (A lives in d_out, B in
+ * d_work) -- what the reference carries in every kiss_fftnd cfg (tmpbuf, kiss_fftnd.c:38). */
+static int kf_fftnd3_permuted(kiss_fftnd_cfg st, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, kiss_fft_cpx *d_work, void *stream)
+{
+    const long long d0 = st->dims[0], d1 = st->dims[1], d2 = st->dims[2];
+    const kf_devplan *p0, *p1, *p2;
+    KF_CHECK(kf_get_devplan(st->states[0], NULL, &p0));
+    KF_CHECK(kf_get_devplan(st->states[1], NULL, &p1));
+    KF_CHECK(kf_get_devplan(st->states[2], NULL, &p2));
+    void *dst = d_out;     /* (plan, in, {out}, 1, planes, columns, columns, column stride, plane pitch in, plane pitch out, row pitch out) */
+    KF_CHECK(kfcu_exec_planes_peers((kfcu_plan *)&p1->plan, d_in, &dst, 1, d0, d2, d2, d2, d1 * d2, d1, d0 * d1, 0, stream));
+    dst = d_work;
+    KF_CHECK(kfcu_exec_planes_peers((kfcu_plan *)&p0->plan, d_out, &dst, 1, d2, d1, d1, d1, d0 * d1, d0, d2 * d0, 0, stream));
+    dst = d_out;
+    KF_CHECK(kfcu_exec_planes_peers((kfcu_plan *)&p2->plan, d_work, &dst, 1, d1, d0, d0, d0, d2 * d0, d2, d1 * d2, 0, stream));
+    return 0;
+}
+
+/* auto: when a sweep of the plain layout would stride further than the tensor-map input ring accepts (kf_tmap.h: 128 KiB)
+ * and the array is big enough to live in HBM rather than L2.  KISSFFT_FFTND_PERMUTE=0 / 1 forces the choice. */
+static int kf_fftnd3_permuted_wanted(kiss_fftnd_cfg st, const kiss_fft_cpx *d_in, const kiss_fft_cpx *d_out)
+{
+    if (st->ndims != 3 || d_in == d_out) return 0;
+    const char *opt = getenv("KISSFFT_FFTND_PERMUTE");
+    if (opt && opt[0] == '0') return 0;
+    if (opt && opt[0] == '1') return 1;
+    const size_t plane = sizeof(kiss_fft_cpx) * (size_t)st->dims[1] * (size_t)st->dims[2];
+    return plane > ((size_t)128 << 10) && plane * (size_t)st->dims[0] >= ((size_t)256 << 20);
+}
+#endif
+
 int kiss_fftnd_dev(kiss_fftnd_cfg cfg, const kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, kiss_fft_cpx *d_work, void *stream)
 {
     if (!cfg || cfg->magic != KF_MAGIC_ND || !d_in || !d_out) {
         KF_ERROR("kiss_fftnd_dev: bad argument");
         return KISS_FFT_CUDA_EINVAL;
     }
+#ifndef FIXED_POINT
+    if (kf_fftnd3_permuted_wanted(cfg, d_in, d_out)) {
+        if (d_work) return kf_fftnd3_permuted(cfg, d_in, d_out, d_work, stream);
+        /* internal work buffer from a staging context (kept for the next call); if the device cannot spare it the
+         * in-layout path below needs none */
+        kf_ctx *cx = NULL;
+        void *w = NULL;
+        if (kf_ctx_acquire(&cx) == 0) {
+            if (kf_ctx_dev(cx, 2, sizeof(kiss_fft_cpx) * (size_t)cfg->dimprod, &w) == 0) {
+                int rc = kf_fftnd3_permuted(cfg, d_in, d_out, (kiss_fft_cpx *)w, stream);
+                int e = (int)cudaStreamSynchronize((cudaStream_t)stream);      /* the context goes back to the pool */
+                kf_ctx_release(cx);
+                return rc ? rc : e;
+            }
+            cudaGetLastError();
+            kf_ctx_release(cx);
+        }
+    }
+#endif
     if (cfg->ndims >= 2 && kf_axes_inlayout_ok(cfg, cfg->ndims, 1)) return kf_axes_inlayout(cfg, cfg->ndims, 1, d_in, d_out, stream);
     if (d_work) return kf_fftnd_dev_locked(cfg, d_in, d_out, d_work, stream);
     /* internal scratch from a staging context: this variant waits for completion before giving the context back */
@@ -1320,6 +1382,10 @@ static int kf_body_nd(void *cfg, const void *d_in, void *d_out, void *d_work, lo
     (void)arg;
     kiss_fftnd_cfg st = (kiss_fftnd_cfg)cfg;
     if (!d_work) return kf_axes_inlayout(st, st->ndims, 1, (const kiss_fft_cpx *)d_in, (kiss_fft_cpx *)d_out, stream);
+#ifndef FIXED_POINT
+    if (kf_fftnd3_permuted_wanted(st, (const kiss_fft_cpx *)d_in, (const kiss_fft_cpx *)d_out))
+        return kf_fftnd3_permuted(st, (const kiss_fft_cpx *)d_in, (kiss_fft_cpx *)d_out, (kiss_fft_cpx *)d_work, stream);
+#endif
     return kf_fftnd_dev_locked(st, (const kiss_fft_cpx *)d_in, (kiss_fft_cpx *)d_out, (kiss_fft_cpx *)d_work, stream);
 }
 static int kf_body_ndr(void *cfg, const void *d_in, void *d_out, void *d_work, long long arg, void *stream)
@@ -1344,7 +1410,10 @@ void kiss_fftnd(kiss_fftnd_cfg st, const kiss_fft_cpx *fin, kiss_fft_cpx *fout)
         return;
     }
     const size_t bytes = sizeof(kiss_fft_cpx) * (size_t)st->dimprod;
-    const int inlay = st->ndims >= 2 && kf_axes_inlayout_ok(st, st->ndims, 1);      /* then no work buffer is needed */
+    int inlay = st->ndims >= 2 && kf_axes_inlayout_ok(st, st->ndims, 1);      /* then no work buffer is needed */
+#ifndef FIXED_POINT
+    if (kf_fftnd3_permuted_wanted(st, fin, NULL)) inlay = 0;
+#endif
     int rc = kf_stage_through_device(kf_body_nd, st, fin, bytes, fout, bytes, inlay ? 0 : bytes, 0);
     if (rc) kf_cuda_fail(__FILE__, __LINE__, "kiss_fftnd", rc);
 }

@@ -114,6 +114,12 @@ struct Arith<int16_t> {
 };
 
 // Q31: int32_t storage, int64 products (FRACBITS 31, SAMP_MAX 2^31-1; _kiss_fft_guts.h:45-49)
+//
+// On the device every product-sum is a chain of mad.wide.s32 (IMAD.WIDE: 32 x 32 + 64 -> 64 in one instruction) seeded with
+// the rounding constant 2^30, and "(x >> 31) truncated to 32 bits" is one funnel shift of the accumulator's two halves.
+// Written as plain int64 C the compiler narrows the expression to the bits it needs and rebuilds it from 32-bit
+// mul.lo / mul.hi pieces with carry chains -- 2.9 k instructions per 16-point work item instead of ~1.5 k (round 2,
+// profiles/r02/ncu_all_kernels.txt: 622 IMAD + 752 IADD3/.X + 420 SHF around 466 wide multiplies).  Same integers either way.
 template <>
 struct Arith<int32_t> {
     typedef int32_t S;
@@ -124,6 +130,7 @@ struct Arith<int32_t> {
     static constexpr bool kFixed = true;
     static constexpr int kFrac = 31;
     static constexpr int32_t kSampMax = 2147483647;
+    static constexpr int64_t kRound = (int64_t)1 << (kFrac - 1);
     static KF_HD cx<R> load(const C& c) { return cx<R>{c.r, c.i}; }
     static KF_HD C store(const cx<R>& v) { return C{v.r, v.i}; }
     static KF_HD R add(R a, R b) { return (R)((uint32_t)a + (uint32_t)b); }
@@ -132,15 +139,51 @@ struct Arith<int32_t> {
     static KF_HD R mad_sign(R sg, R a, R b) { return (R)((uint32_t)sg * (uint32_t)a + (uint32_t)b); }
     static KF_HD R sign_of(int inverse) { return inverse ? -1 : 1; }
     static KF_HD R wrap(R a) { return a; }
-    static KF_HD R sround(int64_t x) { return (R)((x + ((int64_t)1 << (kFrac - 1))) >> kFrac); }
-    static KF_HD R smul(R a, R b) { return sround((int64_t)a * b); }
+    // a*b + c in 64 bits
+    static KF_HD int64_t madw(int32_t a, int32_t b, int64_t c)
+    {
+#if defined(__CUDA_ARCH__)
+        int64_t d;
+        asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+        return d;
+#else
+        return (int64_t)a * b + c;
+#endif
+    }
+    // low 32 bits of x >> 31 (the rounding constant is already in x): sround, _kiss_fft_guts.h:65
+    static KF_HD R shr31(int64_t x)
+    {
+#if defined(__CUDA_ARCH__)
+        unsigned lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x));
+        return (R)__funnelshift_l(lo, hi, 1);
+#else
+        return (R)(x >> kFrac);
+#endif
+    }
+    static KF_HD R sround(int64_t x) { return shr31(x + kRound); }
+    static KF_HD R smul(R a, R b) { return shr31(madw(a, b, kRound)); }                           // S_MUL, :67
     static KF_HD R half(R a) { return a >> 1; }
+    // C_FIXDIV (:73-78): (a*c + 2^30) >> 31 with c = SAMP_MAX/K < 2^30.  Doubling the constant moves the wanted bits into
+    // the upper word: (a*2c + 2^31) >> 32 = hi + (lo >> 31) -- one wide multiply and one shift-add, no 64-bit addition
+    static KF_HD R divc(R a, int32_t c)
+    {
+#if defined(__CUDA_ARCH__)
+        unsigned lo, hi;
+        asm("{\n\t.reg .b64 t;\n\tmul.wide.s32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(2 * c));
+        return (R)(hi + (lo >> 31));
+#else
+        return shr31(madw(a, c, kRound));
+#endif
+    }
     template <int K>
-    static KF_HD R divk(R a) { return sround((int64_t)a * (kSampMax / K)); }
-    static KF_HD R divk_rt(R a, int k) { return sround((int64_t)a * (kSampMax / k)); }
+    static KF_HD R divk(R a) { return divc(a, kSampMax / K); }
+    static KF_HD R divk_rt(R a, int k) { return divc(a, kSampMax / k); }
+    // C_MUL (:69-71); b is always the table operand (a twiddle, |b| <= SAMP_MAX), so negating b.i cannot overflow and
+    // a.r*b.r + a.i*(-b.i) is the reference's a.r*b.r - a.i*b.i in exact 64-bit arithmetic
     static KF_HD cx<R> cmul(const cx<R>& a, const cx<R>& b)
     {
-        return cx<R>{sround((int64_t)a.r * b.r - (int64_t)a.i * b.i), sround((int64_t)a.r * b.i + (int64_t)a.i * b.r)};
+        return cx<R>{shr31(madw(a.i, (R)(0 - b.i), madw(a.r, b.r, kRound))), shr31(madw(a.i, b.r, madw(a.r, b.i, kRound)))};
     }
     static KF_HD cx<R> cmul_bf(const cx<R>& a, const cx<R>& b) { return cmul(a, b); }
     static KF_HD R smul_bf(R a, R b) { return smul(a, b); }

@@ -107,6 +107,7 @@ struct kiss_fftnd_mgpu_state {
     char *recv_base;               /* one allocation: receive buffer followed by the flag words */
     size_t recv_bytes;
     kiss_fft_cpx *send;            /* NCCL path only */
+    kiss_fft_cpx *work;            /* reference-order mode only: the slab after the axis-0 pass, [d1][C][d0] */
     char *peer_base[KF_MGPU_MAXRANKS]; /* every rank's recv_base as mapped here (own entry = recv_base) */
     unsigned **d_peer_flags;       /* device copy of the G flag-array pointers */
     unsigned epoch;
@@ -228,9 +229,10 @@ kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int invers
     st->nchunks = 1;
     for (int c = want; c >= 1; --c)
         if (st->cols % c == 0 && ((st->cols / c) % 16 == 0 || c == 1)) { st->nchunks = c; break; }
+    if (flags & KISS_FFT_MGPU_REFERENCE_ORDER) st->nchunks = 1;     /* one exchange block per peer (see kf_exec_reference_order) */
     st->cw = st->cols / st->nchunks;
     st->pchunks = 1;
-    if (nranks > 1)
+    if (nranks > 1 && !(flags & KISS_FFT_MGPU_REFERENCE_ORDER))
         for (int c = 2; c >= 1; --c)
             if (st->planes % c == 0) { st->pchunks = c; break; }
     env = getenv("KISSFFT_MGPU_PCHUNKS");
@@ -253,6 +255,8 @@ kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int invers
     st->recv_bytes = (st->recv_bytes + 255u) & ~(size_t)255u;
     ok = ok && cudaMalloc((void **)&st->recv_base, st->recv_bytes + KF_FLAG_BYTES) == cudaSuccess &&
          cudaMemset(st->recv_base + st->recv_bytes, 0, KF_FLAG_BYTES) == cudaSuccess;
+    if (flags & KISS_FFT_MGPU_REFERENCE_ORDER)
+        ok = ok && cudaMalloc((void **)&st->work, st->recv_bytes) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&st->s_comm, cudaStreamNonBlocking) == cudaSuccess &&
          cudaStreamCreateWithFlags(&st->s_c, cudaStreamNonBlocking) == cudaSuccess &&
          cudaStreamCreateWithFlags(&st->s_b, cudaStreamNonBlocking) == cudaSuccess &&
@@ -295,6 +299,7 @@ void kiss_fftnd_mgpu_free(kiss_fftnd_mgpu_cfg st)
     if (st->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(st->comm);
     if (st->recv_base) cudaFree(st->recv_base);
     if (st->send) cudaFree(st->send);
+    if (st->work) cudaFree(st->work);
     if (st->s_comm) cudaStreamDestroy(st->s_comm);
     if (st->s_c) cudaStreamDestroy(st->s_c);
     if (st->s_b) cudaStreamDestroy(st->s_b);
@@ -313,6 +318,7 @@ void kiss_fftnd_mgpu_free(kiss_fftnd_mgpu_cfg st)
     free(st);
 }
 
+/* both layouts hold d0*d1*d2/G elements per rank: [P][d1][d2] / [C][d1][d0] (fast order), [d0][d1][C] / [P][d1][d2] (reference order) */
 size_t kiss_fftnd_mgpu_local_in_elems(kiss_fftnd_mgpu_cfg st) { return st ? (size_t)st->planes * st->d1 * st->d2 : 0; }
 size_t kiss_fftnd_mgpu_local_out_elems(kiss_fftnd_mgpu_cfg st) { return st ? (size_t)st->cols * st->d1 * st->d0 : 0; }
 int kiss_fftnd_mgpu_uses_p2p(kiss_fftnd_mgpu_cfg st) { return st ? st->p2p : 0; }
@@ -322,9 +328,54 @@ size_t kiss_fftnd_mgpu_a2a_bytes(kiss_fftnd_mgpu_cfg st)
     return st ? sizeof(kiss_fft_cpx) * (size_t)(st->nranks - 1) * st->planes * st->cols * st->d1 : 0;
 }
 
+/* The reference's axis order 0, 1, 2 across GPUs (KISS_FFT_MGPU_REFERENCE_ORDER; SURVEY.md 8e "fixed-point N-D").
+ * kiss_fftnd.c:156-188 sweeps the axes in the order 0, 1, ..., and the Q15 / Q31 roundings depend on that order, so the
+ * fast pipeline above (axes 2, 1, 0) is not bit-identical to it.  Starting from slabs along the LAST axis -- rank r holds
+ * x[i0][i1][r*C + c] as [d0][d1][C] -- axes 0 and 1 are local, the same single all-to-all completes axis 2, and the result
+ * comes out in natural order as axis-0 slabs: rank r holds X[r*P + p][k1][k2] as [P][d1][d2], the very rows kiss_fftnd
+ * would have written.  Every pass is the transposing axis pass of kiss_fftnd.c:172-178 on the reference's operands:
+ *   1. axis 0:  [d0][d1*C]  ->  work [d1][C][d0]                                     kiss_fft_axis_pass_dev
+ *   2. axis 1:  work viewed as C planes of d0 columns (stride C*d0)  ->  [C][d0][d1], column block s = planes s*P.. of
+ *      the result goes to rank s, which collects [d2 = r*C + c][P][d1]              kiss_fft_planes_pass_peers2_dev
+ *   3. axis 2:  [d2][P*d1]  ->  d_out [P][d1][d2]                                    kiss_fft_axis_pass_dev
+ * Same butterflies on the same operands in the same order => bit-identical to the single-GPU kiss_fftnd in every
+ * datatype.  One exchange block per peer (no chunk pipeline: this is the exact mode, not the fast one). */
+static int kf_exec_reference_order(kiss_fftnd_mgpu_cfg st, kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, cudaStream_t main)
+{
+    const int G = st->nranks, P = st->planes, d0 = st->d0, d1 = st->d1, C = st->cols;
+    kiss_fft_cpx *recv = (kiss_fft_cpx *)st->recv_base;
+    const size_t blk = (size_t)C * P * d1;                 /* what one rank sends to one rank */
+    const unsigned epoch = ++st->epoch;
+    CU(kiss_fft_axis_pass_dev(st->cfg0, d_in, st->work, (size_t)d1 * C, (size_t)d1 * C, main));
+    kiss_fft_cpx *dst[KF_MGPU_MAXRANKS];
+    for (int s = 0; s < G; ++s)
+        dst[s] = (G > 1 && !st->p2p) ? st->send + (size_t)s * blk : (kiss_fft_cpx *)st->peer_base[s] + (size_t)st->rank * blk;
+    if (G > 1 && st->p2p) {
+        /* every peer has finished reading its receive buffer (step 3 of the previous call) before anyone stores into it */
+        CU(kfcu_peer_signal((void *const *)st->d_peer_flags, G, st->rank, 1, epoch, main));
+        CU(kfcu_peer_wait(flag_ptr(st, st->rank), G, 1, epoch, main));
+    }
+    CU(kiss_fft_planes_pass_peers2_dev(st->cfg1, st->work, (kiss_fft_cpx *const *)dst, G, (size_t)C, (size_t)P, (size_t)P,
+                                       (size_t)C * d0, (size_t)d0, (size_t)P * d1, 0, 0, main));
+    if (G > 1 && st->p2p) {
+        CU(kfcu_peer_signal((void *const *)st->d_peer_flags, G, st->rank, 0, epoch, main));
+        CU(kfcu_peer_wait(flag_ptr(st, st->rank), G, 0, epoch, main));
+    } else if (G > 1) {
+        NC(g_nccl.GroupStart());
+        for (int s = 0; s < G; ++s) {
+            NC(g_nccl.Send(st->send + (size_t)s * blk, blk * sizeof(kiss_fft_cpx), KF_NCCL_UINT8, s, st->comm, main));
+            NC(g_nccl.Recv(recv + (size_t)s * blk, blk * sizeof(kiss_fft_cpx), KF_NCCL_UINT8, s, st->comm, main));
+        }
+        NC(g_nccl.GroupEnd());
+    }
+    CU(kiss_fft_axis_pass_dev(st->cfg2, recv, d_out, (size_t)P * d1, (size_t)P * d1, main));
+    return 0;
+}
+
 int kiss_fftnd_mgpu_exec(kiss_fftnd_mgpu_cfg st, kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, void *stream)
 {
     if (!st || st->magic != KF_MAGIC_MGPU || !d_in || !d_out) return kf_fail(st, "kiss_fftnd_mgpu_exec: bad argument", KISS_FFT_CUDA_EINVAL, 0);
+    if (st->flags & KISS_FFT_MGPU_REFERENCE_ORDER) return kf_exec_reference_order(st, d_in, d_out, (cudaStream_t)stream);
     const int G = st->nranks, P = st->planes, d0 = st->d0, d1 = st->d1, d2 = st->d2, cw = st->cw, C = st->cols;
     cudaStream_t main = (cudaStream_t)stream;
     kiss_fft_cpx *recv = (kiss_fft_cpx *)st->recv_base;

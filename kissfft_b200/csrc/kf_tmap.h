@@ -10,6 +10,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "kf_body.h"
@@ -44,7 +45,7 @@ bool col_ring_ok(const KParams<A>& P)
     // Rows further apart than this land on different 2 MiB pages almost every time; the pass is then bound by address
     // translation per row segment and wants the widest segments (the direct-load plans' 16 columns), measured:
     // profiles/r02/tune_r2c_f32_col*_{a,b}.txt (8 MiB stride: ring of 8 columns 7.4 ms vs 4.35 ms; 8 KiB: 3.39 vs 3.95)
-    if ((size_t)P.in_stride * es > ((size_t)128 << 10)) return false;
+    if ((size_t)P.in_stride * es > ((size_t)128 << 10) && !getenv("KISSFFT_RING_ANY_STRIDE")) return false;   // (override: tuning aid)
     if (((uintptr_t)P.in % 16) != 0 || ((size_t)P.in_stride * es) % 16 != 0) return false;
     if (P.howmany / nc > 1 && ((size_t)P.in_pdist * es) % 16 != 0) return false;
     if ((size_t)nc * (es / 4) >= ((size_t)1 << 32) || (size_t)P.in_stride * es >= ((size_t)1 << 40) ||

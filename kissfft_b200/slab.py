@@ -259,9 +259,11 @@ class MgpuFFT3D:
     """kiss_fftnd_mgpu_* of the C library (include/kiss_fft_cuda.h, csrc/kf_mgpu.c) bound for torch tensors: the slab
     transform with its orchestration, NCCL communicator, peer mapping and pipelining all inside the library.  This class
     only carries the rendezvous id from rank 0 to the other ranks (through torch.distributed, as an MPI program would use
-    MPI_Bcast) and hands device pointers over.  Fast axis order (2, 1, exchange, 0), transposed-out result like SlabFFT3D."""
+    MPI_Bcast) and hands device pointers over.  Fast axis order (2, 1, exchange, 0), transposed-out result like SlabFFT3D;
+    reference_order=True: the exact mode (axes 0, 1, exchange, 2 -- kiss_fftnd's own order, bit-identical in every datatype),
+    input slabs along the last axis [d0][d1][d2/G], natural-order output rows [d0/G][d1][d2]."""
 
-    def __init__(self, dims, tname="float", inverse=False, p2p=True, group=None):
+    def __init__(self, dims, tname="float", inverse=False, p2p=True, group=None, reference_order=False):
         import torch
         import torch.distributed as dist
         import kissfft_b200
@@ -276,13 +278,18 @@ class MgpuFFT3D:
             box = [self.lib.mgpu_get_id() if rank == 0 else None]
             dist.broadcast_object_list(box, src=0, group=group)
             ident = box[0]
-        self.cfg = self.lib.mgpu_alloc(dims, rank, world, ident, inverse, self.lib.MGPU_P2P if p2p else 0)
+        self.reference_order = bool(reference_order)
+        flags = (self.lib.MGPU_P2P if p2p else 0) | (self.lib.MGPU_REFERENCE_ORDER if reference_order else 0)
+        self.cfg = self.lib.mgpu_alloc(dims, rank, world, ident, inverse, flags)
         self.info = self.lib.mgpu_info(self.cfg)
 
     def alloc(self):
-        """(local input slab [P][d1][d2][2], output [C][d1][d0][2])"""
+        """(local input slab [P][d1][d2][2], output [C][d1][d0][2]); reference order: ([d0][d1][C][2], [P][d1][d2][2])"""
         g = self.geo
         dev = self.torch.device("cuda", self.torch.cuda.current_device())
+        if self.reference_order:
+            return (self.torch.empty((g.d0, g.d1, g.cols, 2), dtype=self.torch_dtype, device=dev),
+                    self.torch.empty((g.planes, g.d1, g.d2, 2), dtype=self.torch_dtype, device=dev))
         return (self.torch.empty((g.planes, g.d1, g.d2, 2), dtype=self.torch_dtype, device=dev),
                 self.torch.empty((g.cols, g.d1, g.d0, 2), dtype=self.torch_dtype, device=dev))
 

@@ -1,7 +1,10 @@
 /*
  * test_mgpu.c -- the multi-GPU kiss_fftnd through the C-ABI alone (no Python, no torch): one process per GPU.
  *
- *   test_mgpu G d0 d1 d2 [p2p] [iters]
+ *   test_mgpu G d0 d1 d2 [flags] [iters]          flags: 1 = peer-store exchange, 2 = reference axis order (exact mode)
+ *
+ * Builds for every datatype (-DFIXED_POINT=16|32, -Dkiss_fft_scalar=...): the fixed-point builds must reproduce the
+ * single-GPU kiss_fftnd bit for bit in the reference-order mode.
  *
  * The parent forks G children before any CUDA call.  Child 0 asks the library for the rendezvous id and hands it to the
  * others through pipes; every child selects GPU `rank`, transforms its slab with kiss_fftnd_mgpu_exec and compares the
@@ -25,10 +28,15 @@
         if (e_ != 0) { fprintf(stderr, "rank %d: %s failed (%d) %s\n", rank, #x, e_, kiss_fftnd_mgpu_last_error()); return 10; } \
     } while (0)
 
-static float rnd(unsigned long long *s)
+static kiss_fft_scalar rnd(unsigned long long *s)
 {
     *s ^= *s << 13; *s ^= *s >> 7; *s ^= *s << 17;
-    return (float)((double)(*s & 0xffffff) / 0x1000000 * 2.0 - 1.0);
+    const double u = (double)(*s & 0xffffff) / 0x1000000 * 2.0 - 1.0;
+#ifdef FIXED_POINT      /* uniform in +-SAMP_MAX/2: the range where the reference is compiler-independent */
+    return (kiss_fft_scalar)floor(u * (FIXED_POINT == 16 ? 16383.0 : 1073741823.0));
+#else
+    return (kiss_fft_scalar)u;
+#endif
 }
 
 static int run_rank(int rank, int G, const int *dims, unsigned flags, int iters, const void *id)
@@ -78,15 +86,30 @@ static int run_rank(int rank, int G, const int *dims, unsigned flags, int iters,
     if (nin != P * d1 * d2 || nout != C * d1 * d0) { fprintf(stderr, "rank %d: slab sizes\n", rank); return 12; }
     CK(cudaMalloc((void **)&d_in, sizeof(kiss_fft_cpx) * nin));
     CK(cudaMalloc((void **)&d_out, sizeof(kiss_fft_cpx) * nout));
+    const int reford = (flags & KISS_FFT_MGPU_REFERENCE_ORDER) != 0;
+    kiss_fft_cpx *hslab = NULL;
+    if (reford) {                            /* this rank's slab along the last axis: [d0][d1][C] */
+        hslab = (kiss_fft_cpx *)malloc(sizeof(kiss_fft_cpx) * nin);
+        for (size_t a = 0; a < d0 * d1; ++a) memcpy(hslab + a * C, h + a * d2 + (size_t)rank * C, sizeof(kiss_fft_cpx) * C);
+    }
     double worst = 0;
+    long long mismatches = 0;
     for (int rep = 0; rep < 2; ++rep) {      /* twice: the second call exercises the buffer-reuse handshake */
-        CK(cudaMemcpy(d_in, h + (size_t)rank * nin, sizeof(kiss_fft_cpx) * nin, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_in, reford ? hslab : h + (size_t)rank * nin, sizeof(kiss_fft_cpx) * nin, cudaMemcpyHostToDevice));
         CK(cudaMemset(d_out, 0, sizeof(kiss_fft_cpx) * nout));
         CK(kiss_fftnd_mgpu_exec(cfg, d_in, d_out, NULL));
         CK(cudaDeviceSynchronize());
         kiss_fft_cpx *got = (kiss_fft_cpx *)malloc(sizeof(kiss_fft_cpx) * nout);
         CK(cudaMemcpy(got, d_out, sizeof(kiss_fft_cpx) * nout, cudaMemcpyDeviceToHost));
         double num = 0, den = 0;
+        if (reford) {                        /* natural-order rows rank*P .. of kiss_fftnd's output, compared bit for bit too */
+            const kiss_fft_cpx *w = ref + (size_t)rank * nout;
+            for (size_t i = 0; i < nout; ++i) {
+                num += ((double)got[i].r - w[i].r) * ((double)got[i].r - w[i].r) + ((double)got[i].i - w[i].i) * ((double)got[i].i - w[i].i);
+                den += (double)w[i].r * w[i].r + (double)w[i].i * w[i].i;
+                mismatches += (got[i].r != w[i].r) || (got[i].i != w[i].i);
+            }
+        } else
         for (size_t c = 0; c < C; ++c)
             for (size_t k1 = 0; k1 < d1; ++k1)
                 for (size_t k0 = 0; k0 < d0; ++k0) {
@@ -98,7 +121,11 @@ static int run_rank(int rank, int G, const int *dims, unsigned flags, int iters,
         if (err > worst) worst = err;
         free(got);
     }
-    const double tol = 2e-6 * log2((double)n);
+#ifdef FIXED_POINT
+    const double tol = reford ? 0.0 : 1.0;        /* exact mode: bit-identical; the fast order is not defined for fixed point */
+#else
+    const double tol = (sizeof(kiss_fft_scalar) == 8 ? 2e-14 : 2e-6) * log2((double)n);
+#endif
     float ms = 0;
     if (iters > 0) {
         cudaEvent_t e0, e1;
@@ -113,20 +140,24 @@ static int run_rank(int rank, int G, const int *dims, unsigned flags, int iters,
         CK(cudaEventElapsedTime(&ms, e0, e1));
         ms /= (float)iters;
     }
-    printf("{\"rank\": %d, \"ranks\": %d, \"dims\": [%zu, %zu, %zu], \"p2p\": %d, \"chunks\": %d, \"rel_rms\": %.3g, \"tol\": %.3g, \"ms\": %.4f}\n",
-           rank, G, d0, d1, d2, kiss_fftnd_mgpu_uses_p2p(cfg), kiss_fftnd_mgpu_chunks(cfg), worst, tol, ms);
+    printf("{\"rank\": %d, \"ranks\": %d, \"dims\": [%zu, %zu, %zu], \"p2p\": %d, \"chunks\": %d, \"reference_order\": %d, \"mismatches\": %lld, "
+           "\"rel_rms\": %.3g, \"tol\": %.3g, \"ms\": %.4f}\n",
+           rank, G, d0, d1, d2, kiss_fftnd_mgpu_uses_p2p(cfg), kiss_fftnd_mgpu_chunks(cfg), reford, mismatches, worst, tol, ms);
     fflush(stdout);
     kiss_fftnd_mgpu_free(cfg);
     free(nd);
+#ifdef FIXED_POINT
+    if (reford && mismatches != 0) return 21;
+#endif
     return worst <= tol ? 0 : 20;
 }
 
 int main(int argc, char **argv)
 {
-    if (argc < 5) { fprintf(stderr, "usage: %s G d0 d1 d2 [p2p] [iters]\n", argv[0]); return 2; }
+    if (argc < 5) { fprintf(stderr, "usage: %s G d0 d1 d2 [flags] [iters]\n", argv[0]); return 2; }
     const int G = atoi(argv[1]);
     const int dims[3] = {atoi(argv[2]), atoi(argv[3]), atoi(argv[4])};
-    const unsigned flags = (argc > 5 && atoi(argv[5])) ? KISS_FFT_MGPU_P2P : 0;
+    const unsigned flags = argc > 5 ? (unsigned)atoi(argv[5]) : 0;      /* KISS_FFT_MGPU_P2P | KISS_FFT_MGPU_REFERENCE_ORDER */
     const int iters = argc > 6 ? atoi(argv[6]) : 0;
     if (G < 1 || G > 16) return 2;
     if (G == 1) return run_rank(0, 1, dims, flags, iters, NULL);
