@@ -9,8 +9,10 @@
  *   - `*_dev` functions take CUDA device pointers and a cudaStream_t (passed as void*, NULL = default stream);
  *     they enqueue work and return without synchronising -- EXCEPT where they need internal scratch memory that goes
  *     back to a shared pool: rows longer than the shared-memory kernels hold (nfft > ~14.5 k complex float),
- *     kiss_fftnd_dev with d_work == NULL when an axis has no layout-keeping plan, kiss_fftndri_dev, kiss_fftndr_dev in
- *     that same fallback case, and the unfused fast convolution.  Those wait for the stream before returning.
+ *     kiss_fftnd_dev with d_work == NULL when an axis has no layout-keeping plan or when a large 3-D float / double
+ *     array takes the three plane-local transposing passes (pass d_work to keep that case stream-ordered),
+ *     kiss_fftndri_dev, kiss_fftndr_dev in the fallback case, and the unfused fast convolution.  Those wait for the
+ *     stream before returning.
  *   - functions without the suffix take HOST pointers and return when the result is in the output buffer.  The batch is
  *     cut into chunks that move through parallel lanes (H2D, kernel, D2H on one stream per lane).  Pinned (or
  *     cudaHostRegister-ed) caller buffers are handed to the copy engines directly; ordinary pageable buffers -- what

@@ -926,7 +926,9 @@ static int kf_fftnd3_permuted(kiss_fftnd_cfg st, const kiss_fft_cpx *d_in, kiss_
 }
 
 /* auto: when a sweep of the plain layout would stride further than the tensor-map input ring accepts (kf_tmap.h: 128 KiB)
- * and the array is big enough to live in HBM rather than L2.  KISSFFT_FFTND_PERMUTE=0 / 1 forces the choice. */
+ * and every axis length has a ring variant of the transposing pass -- measured on B200 (profiles/r02/fftnd_strategies.txt):
+ * 1024^3 11.0 -> 9.02 ms; 512^3, whose passes have no ring variant yet, 1.48 -> 1.70 ms, so it stays in layout.
+ * KISSFFT_FFTND_PERMUTE=0 / 1 forces the choice. */
 static int kf_fftnd3_permuted_wanted(kiss_fftnd_cfg st, const kiss_fft_cpx *d_in, const kiss_fft_cpx *d_out)
 {
     if (st->ndims != 3 || d_in == d_out) return 0;
@@ -934,7 +936,7 @@ static int kf_fftnd3_permuted_wanted(kiss_fftnd_cfg st, const kiss_fft_cpx *d_in
     if (opt && opt[0] == '0') return 0;
     if (opt && opt[0] == '1') return 1;
     const size_t plane = sizeof(kiss_fft_cpx) * (size_t)st->dims[1] * (size_t)st->dims[2];
-    return plane > ((size_t)128 << 10) && plane * (size_t)st->dims[0] >= ((size_t)256 << 20);
+    return plane > ((size_t)128 << 10) && kfcu_has_colring(st->dims[0]) && kfcu_has_colring(st->dims[1]) && kfcu_has_colring(st->dims[2]);
 }
 #endif
 

@@ -51,6 +51,7 @@ int kfcu_exec_fourstep(kfcu_plan *plan, int step, const void *d_in, void *d_out,
                        const void *d_twbig, void *stream);
 int kfcu_has_fourstep(int nfft);
 int kfcu_has_colcol(int nfft);   /* step 1 alone (every datatype): an axis pass that keeps the array layout */
+int kfcu_has_colring(int nfft);  /* the transposing column pass of this length has a tensor-map input-ring variant */
 
 /* kfcu_exec_planes with the ncols = npeers*cols_per_peer columns of every plane scattered to npeers destination
  * buffers: column block s is written through peers[s] (+ p*out_pdist + c_local*nfft) */

@@ -314,6 +314,14 @@ extern "C" int kfcu_exec_fourstep(kfcu_plan* plan, int step, const void* d_in, v
 
 extern "C" int kfcu_has_colcol(int nfft) { return find_fused(nfft, kC2CColCol) != nullptr; }
 
+// does a tensor-map input-ring variant serve the transposing column pass of this length?
+extern "C" int kfcu_has_colring(int nfft)
+{
+    for (const ColRingEntry& e : kColRingTable)
+        if (e.N == nfft && e.fn[kC2CCol]) return 1;
+    return 0;
+}
+
 extern "C" int kfcu_has_fourstep(int nfft)
 {
     return find_fused(nfft, kC2CColTw) != nullptr && find_fused(nfft, kC2CColCol) != nullptr;

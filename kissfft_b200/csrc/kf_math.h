@@ -164,11 +164,12 @@ struct Arith<int32_t> {
     static KF_HD R sround(int64_t x) { return shr31(x + kRound); }
     static KF_HD R smul(R a, R b) { return shr31(madw(a, b, kRound)); }                           // S_MUL, :67
     static KF_HD R half(R a) { return a >> 1; }
-    // C_FIXDIV (:73-78): (a*c + 2^30) >> 31 with c = SAMP_MAX/K < 2^30.  Doubling the constant moves the wanted bits into
+    // C_FIXDIV (:73-78): (a*c + 2^30) >> 31 with c = SAMP_MAX/K, < 2^30 for every K >= 2.  Doubling the constant moves the wanted bits into
     // the upper word: (a*2c + 2^31) >> 32 = hi + (lo >> 31) -- one wide multiply and one shift-add, no 64-bit addition
     static KF_HD R divc(R a, int32_t c)
     {
 #if defined(__CUDA_ARCH__)
+        if (c >= (1 << 30)) return shr31(madw(a, c, kRound));      // K == 1 (nfft == 1, kf_bfly_generic with p == 1): 2c does not fit
         unsigned lo, hi;
         asm("{\n\t.reg .b64 t;\n\tmul.wide.s32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(2 * c));
         return (R)(hi + (lo >> 31));
