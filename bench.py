@@ -467,7 +467,10 @@ def measure_slab(name, args, dist, rank, world, t1_ms):
     local_bytes = algorithmic_bytes(w) * 3 // world
     out = {"workload": w["desc"], "dtype": DTYPE_NAME[w["tname"]], "ms": ms, "scaling": "strong",
            "api": "kiss_fftnd_mgpu_exec (C-ABI)", "exchange": "peer stores over NVLink (CUDA IPC)" if plan.info["p2p"] else "NCCL grouped send/recv",
-           "pipeline_chunks": plan.info["chunks"],
+           "pipeline_chunks": plan.info["chunks"], "pipeline_plane_groups": plan.info.get("pchunks"),
+           "link_bound_cta_cap": plan.info.get("b_ctas"), "link_stream_priority": plan.info.get("b_prio"),
+           "sm_partition": {"link_bound_sms": plan.info.get("link_sms"), "hbm_bound_sms": plan.info.get("rest_sms"),
+                            "how": "CUDA green contexts"} if plan.info.get("link_sms") else None,
            "gflops": flops_per_step(w) / (ms * 1e-3) / 1e9,
            "parity": "32 sampled bins vs float64 DFT sums rel-rms %.2e, Parseval defect %.1e (<= %.1e)" % (err, pars, tol),
            "parity_ok": bool(err <= tol and pars <= tol),

@@ -136,6 +136,16 @@ int KISS_FFT_API kiss_fftnd_mgpu_uses_p2p(kiss_fftnd_mgpu_cfg cfg);
 int KISS_FFT_API kiss_fftnd_mgpu_chunks(kiss_fftnd_mgpu_cfg cfg);
 size_t KISS_FFT_API kiss_fftnd_mgpu_a2a_bytes(kiss_fftnd_mgpu_cfg cfg);
 const char KISS_FFT_API *kiss_fftnd_mgpu_last_error(void);
+/* tuning aid, COLLECTIVE with no exec in flight: knobs = {chunks of the exchange, plane groups, CTA cap of the link-bound
+ * launches (0 = none), priority stream for them (0/1), SMs the HBM-bound launches leave to them, trace (0/1), SMs of the
+ * link-bound green-context partition (0 = no partition)}, a negative entry keeps the current value; _knob reads one back
+ * (6: SMs of the link partition actually provisioned, 7: SMs of the other one) */
+int KISS_FFT_API kiss_fftnd_mgpu_tune(kiss_fftnd_mgpu_cfg cfg, const int *knobs, int nknobs);
+int KISS_FFT_API kiss_fftnd_mgpu_knob(kiss_fftnd_mgpu_cfg cfg, int which);
+/* tuning aid: with knob 5 (trace) set, every launch of an exec is bracketed by timed events; after the exec this writes one
+ * "name start_ms end_ms" line per launch (A<group> rows, B<group>.<chunk> column pass + exchange stores, X NCCL exchange,
+ * C0.<chunk> axis-0 pass) into buf.  Synchronises the device. */
+int KISS_FFT_API kiss_fftnd_mgpu_trace(kiss_fftnd_mgpu_cfg cfg, char *buf, size_t len);
 
 /* ---- host-pointer batched (parallel lanes of H2D / kernel / D2H, pinned bounce buffers for pageable memory) --- */
 int KISS_FFT_API kiss_fft_batch(kiss_fft_cfg cfg, const kiss_fft_cpx *in, kiss_fft_cpx *out, size_t howmany);
@@ -178,7 +188,7 @@ long long KISS_FFT_API kiss_fft_cuda_launch_count(void);
 int KISS_FFT_API kiss_fft_cuda_plan_kind(int nfft);
 /* testing aid: route every length through the run-time shared-memory kernel (1) or restore the default (0) */
 void KISS_FFT_API kiss_fft_cuda_force_generic(int on);
-/* cap the number of CTAs of the fused kernels launched after this call (0 = fill the device).  Used by the slab
+/* cap the number of CTAs of the fused kernels the CALLING THREAD launches after this call (0 = fill the device).  Used by the slab
  * transform so that its NVLink-bound peer-store launches share the SMs with HBM-bound launches on another stream. */
 void KISS_FFT_API kiss_fft_cuda_set_grid_limit(int max_ctas);
 /* sizeof(kiss_fft_scalar) of this build (4 float, 8 double, 2 Q15, 4 Q31) and 1 for fixed point */

@@ -26,7 +26,7 @@ API_SYMBOLS = (
     "kiss_fft_planes_pass_peers2_dev",
     "kiss_fftnd_mgpu_get_id", "kiss_fftnd_mgpu_alloc", "kiss_fftnd_mgpu_exec", "kiss_fftnd_mgpu_free", "kiss_fftnd_mgpu_local_in_elems",
     "kiss_fftnd_mgpu_local_out_elems", "kiss_fftnd_mgpu_uses_p2p", "kiss_fftnd_mgpu_chunks", "kiss_fftnd_mgpu_a2a_bytes",
-    "kiss_fftnd_mgpu_last_error",
+    "kiss_fftnd_mgpu_last_error", "kiss_fftnd_mgpu_tune", "kiss_fftnd_mgpu_knob", "kiss_fftnd_mgpu_trace",
     "kiss_fftndr_dev", "kiss_fftndri_dev", "kiss_fft_batch", "kiss_fftr_batch", "kiss_fftri_batch",
     "kiss_fft_cuda_last_error", "kiss_fft_cuda_launch_count", "kiss_fft_cuda_plan_kind", "kiss_fft_cuda_scalar_bytes",
     "kiss_fft_cuda_is_fixed_point", "kiss_fft_cuda_force_generic", "kiss_fft_cuda_set_grid_limit",
@@ -110,6 +110,8 @@ class KissFFT:
         for name in ("kiss_fftnd_mgpu_uses_p2p", "kiss_fftnd_mgpu_chunks"):
             getattr(L, name).argtypes = [vp]
         L.kiss_fftnd_mgpu_last_error.restype = ctypes.c_char_p
+        L.kiss_fftnd_mgpu_tune.argtypes = [vp, ctypes.POINTER(ci), ci]
+        L.kiss_fftnd_mgpu_knob.argtypes = [vp, ci]
         L.kiss_fftndr_dev.argtypes = [vp, vp, vp, vp]
         L.kiss_fftndri_dev.argtypes = [vp, vp, vp, vp]
         L.kiss_fft_batch.argtypes = [vp, vp, vp, sz]
@@ -242,7 +244,10 @@ class KissFFT:
         L = self.lib
         return {"in_elems": int(L.kiss_fftnd_mgpu_local_in_elems(cfg)), "out_elems": int(L.kiss_fftnd_mgpu_local_out_elems(cfg)),
                 "p2p": bool(L.kiss_fftnd_mgpu_uses_p2p(cfg)), "chunks": int(L.kiss_fftnd_mgpu_chunks(cfg)),
-                "a2a_bytes": int(L.kiss_fftnd_mgpu_a2a_bytes(cfg))}
+                "a2a_bytes": int(L.kiss_fftnd_mgpu_a2a_bytes(cfg)), "pchunks": int(L.kiss_fftnd_mgpu_knob(cfg, 1)),
+                "b_ctas": int(L.kiss_fftnd_mgpu_knob(cfg, 2)), "b_prio": int(L.kiss_fftnd_mgpu_knob(cfg, 3)),
+                "ac_reserve": int(L.kiss_fftnd_mgpu_knob(cfg, 4)), "link_sms": int(L.kiss_fftnd_mgpu_knob(cfg, 6)),
+                "rest_sms": int(L.kiss_fftnd_mgpu_knob(cfg, 7))}
 
     def fftndr_dev(self, cfg, d_time, d_freq, stream=0):
         self._check(self.lib.kiss_fftndr_dev(cfg, _ptr(d_time), _ptr(d_freq), ctypes.c_void_p(stream)), "kiss_fftndr_dev")

@@ -97,7 +97,8 @@ long long kfcu_launch_count(void);
 void kfcu_force_generic(int on);
 /* cap the persistent grid of the fused kernels launched after this call (0 = no cap): lets a link-bound launch
  * (peer-memory stores of the slab exchange) share the SMs with an HBM-bound one on another stream */
-void kfcu_set_grid_limit(int max_ctas);
+void kfcu_set_grid_limit(int max_ctas);    /* launches of the calling host thread only */
+void kfcu_set_sm_reserve(int sms);         /* persistent grids of the calling thread leave `sms` SMs to a concurrent kernel */
 
 #define KFCU_EINVAL (-1)
 #define KFCU_ETOOBIG (-2)

@@ -28,7 +28,8 @@ static_assert(sizeof(CT) == sizeof(kiss_fft_cpx), "storage complex must match ki
 
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_force_generic{0};
-static std::atomic<int> g_grid_limit{0};   // 0 = fill the device; > 0 caps the persistent grid (lets two kernels share the SMs)
+static thread_local int g_grid_limit = 0;  // launches of THIS host thread: 0 = fill the device; > 0 caps the persistent grid
+static thread_local int g_sm_reserve = 0;  // launches of THIS host thread leave that many SMs free (a concurrent kernel owns them)
 
 struct DeviceInfo {
     int sms = 0;
@@ -144,9 +145,11 @@ static int launch_fused(kfcu_plan* pl, KParams<AT>& P, cudaStream_t st)
         blocks_per_sm[dev] = nb;
     }
     const long long ntiles = (P.howmany + D.tpc - 1) / D.tpc;
-    long long grid = (long long)device_info().sms * blocks_per_sm[dev];
+    int sms = device_info().sms;
+    if (g_sm_reserve > 0) sms = sms - g_sm_reserve > 8 ? sms - g_sm_reserve : 8;
+    long long grid = (long long)sms * blocks_per_sm[dev];
     if (grid > ntiles) grid = ntiles;
-    if (const int lim = g_grid_limit.load(std::memory_order_relaxed); lim > 0 && grid > lim) grid = lim;
+    if (const int lim = g_grid_limit; lim > 0 && grid > lim) grid = lim;
     if (P.max_ctas > 0 && grid > P.max_ctas) grid = P.max_ctas;      // per-launch cap (link-bound launches share the SMs)
     if (grid < 1) return 0;
     kern<<<(unsigned)grid, D.threads(), smem, st>>>(P);
@@ -605,4 +608,5 @@ extern "C" int kfcu_generic_max_nfft(void)
 
 extern "C" long long kfcu_launch_count(void) { return g_launches.load(); }
 extern "C" void kfcu_force_generic(int on) { g_force_generic.store(on); }
-extern "C" void kfcu_set_grid_limit(int max_ctas) { g_grid_limit.store(max_ctas > 0 ? max_ctas : 0); }
+extern "C" void kfcu_set_grid_limit(int max_ctas) { g_grid_limit = max_ctas > 0 ? max_ctas : 0; }
+extern "C" void kfcu_set_sm_reserve(int sms) { g_sm_reserve = sms > 0 ? sms : 0; }

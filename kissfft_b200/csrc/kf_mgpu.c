@@ -35,6 +35,7 @@
  * Host code is C; the only CUDA code it needs beyond the library's own entry points are the two flag kernels
  * (kf_launch.cu: kfcu_peer_signal / kfcu_peer_wait).
  */
+#include <cuda.h>               /* types of the green-context API only; entry points come from cudaGetDriverEntryPoint */
 #include <cuda_runtime_api.h>
 #include <dlfcn.h>
 #include <stdint.h>
@@ -90,15 +91,74 @@ static int kf_nccl_load(void)
     return 0;
 }
 
+
+/* ---- SM partitions (CUDA green contexts, driver API >= 12.4) ------------------------------------------------------
+ * Two persistent kernels on two streams do not overlap by themselves: whichever starts first fills every SM, and a
+ * capped grid does not help either, because the CTA scheduler spreads the capped kernel's small CTAs over all SMs and the
+ * other kernel's 198 KB CTAs then fit nowhere (timeline: profiles/r02/mgpu_g2_timeline_before_partition.txt).  A green
+ * context owns a fixed set of SMs; a stream created in it launches only there.  The link-bound launches (B: column pass
+ * whose stores cross NVLink) get one partition, the HBM-bound launches that run beside them (A(i > 0), C(j < last)) the
+ * other; A(0) and the last C run in the caller's context on the whole device.  Memory, events and kernels are shared
+ * with the primary context, so nothing else changes. */
+typedef struct {
+    int tried, ok;
+    CUresult (*DeviceGet)(CUdevice *, int);
+    CUresult (*DeviceGetDevResource)(CUdevice, CUdevResource *, CUdevResourceType);
+    CUresult (*DevSmResourceSplitByCount)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int);
+    CUresult (*DevResourceGenerateDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int);
+    CUresult (*GreenCtxCreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int);
+    CUresult (*GreenCtxDestroy)(CUgreenCtx);
+    CUresult (*GreenCtxStreamCreate)(CUstream *, CUgreenCtx, unsigned int, int);
+} kf_drv_api;
+static kf_drv_api g_drv;
+
+static int kf_drv_load(void)
+{
+    if (g_drv.tried) return g_drv.ok ? 0 : -1;
+    kf_drv_api a;
+    memset(&a, 0, sizeof(a));
+    a.tried = 1;
+    struct { const char *name; void **fn; } want[] = {
+        {"cuDeviceGet", (void **)&a.DeviceGet},
+        {"cuDeviceGetDevResource", (void **)&a.DeviceGetDevResource},
+        {"cuDevSmResourceSplitByCount", (void **)&a.DevSmResourceSplitByCount},
+        {"cuDevResourceGenerateDesc", (void **)&a.DevResourceGenerateDesc},
+        {"cuGreenCtxCreate", (void **)&a.GreenCtxCreate},
+        {"cuGreenCtxDestroy", (void **)&a.GreenCtxDestroy},
+        {"cuGreenCtxStreamCreate", (void **)&a.GreenCtxStreamCreate},
+    };
+    a.ok = 1;
+    for (size_t i = 0; i < sizeof(want) / sizeof(want[0]); ++i) {
+        enum cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint(want[i].name, want[i].fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !*want[i].fn) {
+            cudaGetLastError();
+            a.ok = 0;
+            break;
+        }
+    }
+    g_drv = a;
+    return a.ok ? 0 : -1;
+}
+
 #define KF_MAGIC_MGPU 0x4b464d47u
 #define KF_MGPU_MAXRANKS 16
 #define KF_MGPU_MAXCHUNKS 8
+#define KF_MGPU_MAXTRACE 96
 #define KF_FLAG_BYTES 4096 /* (MAXCHUNKS + 1) slots x MAXRANKS unsigned, rounded up */
 
 struct kiss_fftnd_mgpu_state {
     uint32_t magic;
     int d0, d1, d2, inverse, rank, nranks, device;
     int planes, cols, nchunks, cw; /* P, C = d2/G, chunks of the k2 columns, columns per chunk */
+    int b_prio;                    /* s_b is a highest-priority stream */
+    int trace, ntr;                /* tuning aid: timed events around every launch of the last exec (kiss_fftnd_mgpu_trace) */
+    cudaEvent_t tr_ev[KF_MGPU_MAXTRACE][2], tr_t0;
+    char tr_name[KF_MGPU_MAXTRACE][12];
+    int gc_on, link_sms, rest_sms, dev_sms;  /* green-context SM partition: SMs of the link-bound / of the HBM-bound partition */
+    CUgreenCtx gc_link, gc_rest;
+    cudaStream_t gs_b, gs_a, gs_c; /* B in the link partition; A(i > 0) and C(j < last) in the other */
+    cudaEvent_t ev_adone, ev_done2;
+    int ac_reserve;                /* SMs the HBM-bound launches (A, C) leave to the concurrent link-bound / NCCL kernels */
     int pchunks, b_ctas;           /* groups of local planes (pipelining of A against B); CTA cap of link-bound B launches */
     unsigned flags;
     int p2p;                       /* peer-store exchange active */
@@ -200,6 +260,95 @@ static int kf_mgpu_map_peers(kiss_fftnd_mgpu_cfg st)
     return rc;
 }
 
+/* The stream of the link-bound B launches gets the highest priority: when a kernel of another stream drains, B's few
+ * CTAs are placed first and the HBM-bound kernel fills the rest of the device, so the NVLink stores start as early as
+ * their inputs allow instead of queueing behind the next full-grid launch. */
+static int kf_make_b_stream(kiss_fftnd_mgpu_cfg st, int prio)
+{
+    int lo = 0, hi = 0;
+    if (st->s_b) { cudaStreamDestroy(st->s_b); st->s_b = NULL; }
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) { cudaGetLastError(); prio = 0; }
+    st->b_prio = prio;
+    return (int)cudaStreamCreateWithPriority(&st->s_b, cudaStreamNonBlocking, prio ? hi : lo);
+}
+
+static void kf_drop_partition(kiss_fftnd_mgpu_cfg st)
+{
+    if (st->gs_b) cudaStreamDestroy(st->gs_b);
+    if (st->gs_a) cudaStreamDestroy(st->gs_a);
+    if (st->gs_c) cudaStreamDestroy(st->gs_c);
+    st->gs_b = st->gs_a = st->gs_c = NULL;
+    if (st->gc_link) g_drv.GreenCtxDestroy(st->gc_link);
+    if (st->gc_rest) g_drv.GreenCtxDestroy(st->gc_rest);
+    st->gc_link = st->gc_rest = NULL;
+    st->gc_on = st->link_sms = st->rest_sms = 0;
+}
+
+/* split the device into `want_link` SMs (rounded up to the hardware's granularity, 8 on sm_90+) and the rest; 0 = no
+ * partition.  Failure of any step leaves the cfg on the unpartitioned pipeline (not an error). */
+static int kf_make_partition(kiss_fftnd_mgpu_cfg st, int want_link)
+{
+    if (st->gc_on || st->gs_b) kf_drop_partition(st);
+    if (want_link <= 0 || kf_drv_load() != 0) return -1;
+    CUdevice dev;
+    CUdevResource all, grp, rest;
+    CUdevResourceDesc d_link = NULL, d_rest = NULL;
+    unsigned int n = 1;
+    memset(&all, 0, sizeof(all)); memset(&grp, 0, sizeof(grp)); memset(&rest, 0, sizeof(rest));
+    int ok = g_drv.DeviceGet(&dev, st->device) == CUDA_SUCCESS &&
+             g_drv.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS;
+    if (ok && (unsigned)want_link + 8 > all.sm.smCount) ok = 0;
+    ok = ok && g_drv.DevSmResourceSplitByCount(&grp, &n, &all, &rest, 0, (unsigned)want_link) == CUDA_SUCCESS && n == 1 &&
+         grp.type == CU_DEV_RESOURCE_TYPE_SM && rest.type == CU_DEV_RESOURCE_TYPE_SM && rest.sm.smCount >= 8;
+    ok = ok && g_drv.DevResourceGenerateDesc(&d_link, &grp, 1) == CUDA_SUCCESS && g_drv.DevResourceGenerateDesc(&d_rest, &rest, 1) == CUDA_SUCCESS;
+    ok = ok && g_drv.GreenCtxCreate(&st->gc_link, d_link, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS &&
+         g_drv.GreenCtxCreate(&st->gc_rest, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
+    ok = ok && g_drv.GreenCtxStreamCreate((CUstream *)&st->gs_b, st->gc_link, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS &&
+         g_drv.GreenCtxStreamCreate((CUstream *)&st->gs_a, st->gc_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS &&
+         g_drv.GreenCtxStreamCreate((CUstream *)&st->gs_c, st->gc_rest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
+    if (!ok) { cudaGetLastError(); kf_drop_partition(st); return -1; }
+    st->dev_sms = (int)all.sm.smCount;
+    st->link_sms = (int)grp.sm.smCount;
+    st->rest_sms = (int)rest.sm.smCount;
+    st->gc_on = 1;
+    return 0;
+}
+
+static void kf_set_chunks(kiss_fftnd_mgpu_cfg st, int want)
+{
+    if (want > KF_MGPU_MAXCHUNKS) want = KF_MGPU_MAXCHUNKS;
+    if (st->nranks == 1 || want < 1) want = 1;
+    st->nchunks = 1;
+    for (int c = want; c >= 1; --c)
+        if (st->cols % c == 0 && ((st->cols / c) % 16 == 0 || c == 1)) { st->nchunks = c; break; }
+    if (st->flags & KISS_FFT_MGPU_REFERENCE_ORDER) st->nchunks = 1;     /* one exchange block per peer (see kf_exec_reference_order) */
+    st->cw = st->cols / st->nchunks;
+}
+
+/* Tuning aid (tests/cpp/test_mgpu.c sweeps with it): change the pipeline shape of an existing cfg.  COLLECTIVE -- every
+ * rank passes the same values, with no exec in flight.  knobs[0] chunks of the k2 columns, [1] plane groups, [2] CTA cap
+ * of the link-bound launches (0 = none), [3] priority of their stream (0/1); a negative entry keeps the current value. */
+int kiss_fftnd_mgpu_tune(kiss_fftnd_mgpu_cfg st, const int *knobs, int nknobs)
+{
+    if (!st || st->magic != KF_MAGIC_MGPU || !knobs) return KISS_FFT_CUDA_EINVAL;
+    CU(cudaDeviceSynchronize());
+    if (nknobs > 0 && knobs[0] > 0) kf_set_chunks(st, knobs[0]);
+    if (nknobs > 1 && knobs[1] > 0 && knobs[1] <= KF_MGPU_MAXCHUNKS && st->planes % knobs[1] == 0 &&
+        !(st->flags & KISS_FFT_MGPU_REFERENCE_ORDER)) st->pchunks = knobs[1];
+    if (nknobs > 2 && knobs[2] >= 0) st->b_ctas = knobs[2];
+    if (nknobs > 3 && knobs[3] >= 0 && (knobs[3] != 0) != (st->b_prio != 0)) CU(kf_make_b_stream(st, knobs[3]));
+    if (nknobs > 4 && knobs[4] >= 0) st->ac_reserve = knobs[4];
+    if (nknobs > 5 && knobs[5] >= 0) st->trace = knobs[5];
+    if (nknobs > 6 && knobs[6] >= 0 && st->p2p && knobs[6] != (st->gc_on ? st->link_sms : 0)) kf_make_partition(st, knobs[6]);
+    return 0;
+}
+int kiss_fftnd_mgpu_knob(kiss_fftnd_mgpu_cfg st, int which)
+{
+    if (!st) return -1;
+    return which == 0 ? st->nchunks : which == 1 ? st->pchunks : which == 2 ? st->b_ctas : which == 3 ? st->b_prio : which == 4 ? st->ac_reserve :
+           which == 6 ? (st->gc_on ? st->link_sms : 0) : which == 7 ? (st->gc_on ? st->rest_sms : 0) : -1;
+}
+
 kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int inverse_fft, int rank, int nranks, const void *id,
                                           unsigned flags)
 {
@@ -224,13 +373,7 @@ kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int invers
     int want = nranks <= 2 ? 2 : 4;    /* measured at G = 2 (profiles/r02/mgpu_g2_knobs.txt): more chunks only add launches */
     const char *env = getenv("KISSFFT_MGPU_CHUNKS");
     if (env && atoi(env) > 0) want = atoi(env);
-    if (want > KF_MGPU_MAXCHUNKS) want = KF_MGPU_MAXCHUNKS;
-    if (nranks == 1) want = 1;
-    st->nchunks = 1;
-    for (int c = want; c >= 1; --c)
-        if (st->cols % c == 0 && ((st->cols / c) % 16 == 0 || c == 1)) { st->nchunks = c; break; }
-    if (flags & KISS_FFT_MGPU_REFERENCE_ORDER) st->nchunks = 1;     /* one exchange block per peer (see kf_exec_reference_order) */
-    st->cw = st->cols / st->nchunks;
+    kf_set_chunks(st, want);
     st->pchunks = 1;
     if (nranks > 1 && !(flags & KISS_FFT_MGPU_REFERENCE_ORDER))
         for (int c = 2; c >= 1; --c)
@@ -242,10 +385,17 @@ kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int invers
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        st->dev_sms = sms;
         st->b_ctas = nranks > 1 ? (int)(0.325 * sms * nranks / (nranks - 1)) : 0;
     }
     env = getenv("KISSFFT_MGPU_B_CTAS");
     if (env && atoi(env) >= 0) st->b_ctas = atoi(env);
+    /* A persistent kernel that fills the device keeps every later kernel off the SMs until it ends, and one that arrives
+     * while another holds part of the device runs its statically striped tiles in two waves -- so overlap between streams
+     * needs the SMs partitioned by hand: the HBM-bound launches that run beside link-bound ones leave those SMs alone. */
+    st->ac_reserve = (flags & KISS_FFT_MGPU_P2P) ? st->b_ctas : 0;
+    env = getenv("KISSFFT_MGPU_AC_RESERVE");
+    if (env && atoi(env) >= 0) st->ac_reserve = atoi(env);
     int ok = cudaGetDevice(&st->device) == cudaSuccess;
     st->cfg0 = kiss_fft_alloc(st->d0, st->inverse, NULL, NULL);
     st->cfg1 = kiss_fft_alloc(st->d1, st->inverse, NULL, NULL);
@@ -259,10 +409,12 @@ kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int invers
         ok = ok && cudaMalloc((void **)&st->work, st->recv_bytes) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&st->s_comm, cudaStreamNonBlocking) == cudaSuccess &&
          cudaStreamCreateWithFlags(&st->s_c, cudaStreamNonBlocking) == cudaSuccess &&
-         cudaStreamCreateWithFlags(&st->s_b, cudaStreamNonBlocking) == cudaSuccess &&
+         kf_make_b_stream(st, getenv("KISSFFT_MGPU_PRIO") ? atoi(getenv("KISSFFT_MGPU_PRIO")) : 1) == 0 &&
          cudaEventCreateWithFlags(&st->ev_start, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&st->ev_bdone, cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&st->ev_done, cudaEventDisableTiming) == cudaSuccess;
+         cudaEventCreateWithFlags(&st->ev_done, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&st->ev_done2, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&st->ev_adone, cudaEventDisableTiming) == cudaSuccess;
     for (int j = 0; ok && j < KF_MGPU_MAXCHUNKS; ++j)
         ok = cudaEventCreateWithFlags(&st->ev_b[j], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&st->ev_a[j], cudaEventDisableTiming) == cudaSuccess &&
@@ -278,6 +430,14 @@ kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int invers
         }
         if (ok && (flags & KISS_FFT_MGPU_P2P)) st->p2p = kf_mgpu_map_peers(st) == 0;   /* falls back to NCCL when IPC is unavailable */
         if (ok && !st->p2p) ok = cudaMalloc((void **)&st->send, st->recv_bytes) == cudaSuccess;
+        if (ok && st->p2p && !(flags & KISS_FFT_MGPU_REFERENCE_ORDER)) {
+            /* SMs of the link partition: B at full rate takes about 0.21 * G/(G-1) of its NVLink time (measured: 2.8/G ms
+             * against 8 GiB (G-1)/G^2 at 0.65 TB/s), plus a margin; the hardware rounds up to a multiple of 8 */
+            int want_link = (int)(0.245 * st->dev_sms * nranks / (nranks - 1));
+            env = getenv("KISSFFT_MGPU_LINK_SMS");
+            if (env && atoi(env) >= 0) want_link = atoi(env);
+            kf_make_partition(st, want_link);
+        }
     }
     if (ok) ok = cudaDeviceSynchronize() == cudaSuccess;
     if (!ok) {
@@ -300,6 +460,9 @@ void kiss_fftnd_mgpu_free(kiss_fftnd_mgpu_cfg st)
     if (st->recv_base) cudaFree(st->recv_base);
     if (st->send) cudaFree(st->send);
     if (st->work) cudaFree(st->work);
+    if (st->gc_on || st->gs_b) kf_drop_partition(st);
+    if (st->ev_done2) cudaEventDestroy(st->ev_done2);
+    if (st->ev_adone) cudaEventDestroy(st->ev_adone);
     if (st->s_comm) cudaStreamDestroy(st->s_comm);
     if (st->s_c) cudaStreamDestroy(st->s_c);
     if (st->s_b) cudaStreamDestroy(st->s_b);
@@ -311,6 +474,11 @@ void kiss_fftnd_mgpu_free(kiss_fftnd_mgpu_cfg st)
         if (st->ev_a[j]) cudaEventDestroy(st->ev_a[j]);
         if (st->ev_x[j]) cudaEventDestroy(st->ev_x[j]);
     }
+    for (int n = 0; n < KF_MGPU_MAXTRACE; ++n) {
+        if (st->tr_ev[n][0]) cudaEventDestroy(st->tr_ev[n][0]);
+        if (st->tr_ev[n][1]) cudaEventDestroy(st->tr_ev[n][1]);
+    }
+    if (st->tr_t0) cudaEventDestroy(st->tr_t0);
     kiss_fft_free(st->cfg0);
     kiss_fft_free(st->cfg1);
     kiss_fft_free(st->cfg2);
@@ -372,6 +540,36 @@ static int kf_exec_reference_order(kiss_fftnd_mgpu_cfg st, kiss_fft_cpx *d_in, k
     return 0;
 }
 
+/* ---- tuning aid: a timeline of the launches of one exec ------------------------------------------------------- */
+static void tr_begin(kiss_fftnd_mgpu_cfg st, const char *what, int i, int j, cudaStream_t s)
+{
+    if (!st->trace || st->ntr >= KF_MGPU_MAXTRACE) return;
+    const int n = st->ntr;
+    if (!st->tr_ev[n][0]) { cudaEventCreate(&st->tr_ev[n][0]); cudaEventCreate(&st->tr_ev[n][1]); }
+    snprintf(st->tr_name[n], sizeof(st->tr_name[n]), "%s%d.%d", what, i, j);
+    cudaEventRecord(st->tr_ev[n][0], s);
+}
+static void tr_end(kiss_fftnd_mgpu_cfg st, cudaStream_t s)
+{
+    if (!st->trace || st->ntr >= KF_MGPU_MAXTRACE) return;
+    cudaEventRecord(st->tr_ev[st->ntr++][1], s);
+}
+/* after the exec has completed: writes "name start_ms end_ms" lines (relative to the start of the exec) into buf */
+int kiss_fftnd_mgpu_trace(kiss_fftnd_mgpu_cfg st, char *buf, size_t len)
+{
+    if (!st || st->magic != KF_MAGIC_MGPU || !buf || !len) return KISS_FFT_CUDA_EINVAL;
+    size_t o = 0;
+    buf[0] = 0;
+    CU(cudaDeviceSynchronize());
+    for (int n = 0; n < st->ntr && o + 48 < len; ++n) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, st->tr_t0, st->tr_ev[n][0]);
+        cudaEventElapsedTime(&b, st->tr_t0, st->tr_ev[n][1]);
+        o += (size_t)snprintf(buf + o, len - o, "%s %.3f %.3f\n", st->tr_name[n], a, b);
+    }
+    return 0;
+}
+
 int kiss_fftnd_mgpu_exec(kiss_fftnd_mgpu_cfg st, kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, void *stream)
 {
     if (!st || st->magic != KF_MAGIC_MGPU || !d_in || !d_out) return kf_fail(st, "kiss_fftnd_mgpu_exec: bad argument", KISS_FFT_CUDA_EINVAL, 0);
@@ -389,21 +587,38 @@ int kiss_fftnd_mgpu_exec(kiss_fftnd_mgpu_cfg st, kiss_fft_cpx *d_in, kiss_fft_cp
     }
     const unsigned epoch = ++st->epoch;
     const int NP = st->pchunks, Pc = P / NP;
+    if (st->trace) {
+        if (!st->tr_t0) CU(cudaEventCreate(&st->tr_t0));
+        st->ntr = 0;
+        CU(cudaEventRecord(st->tr_t0, main));
+    }
+    /* streams: with an SM partition B runs in the link partition, A(i > 0) and C(j < last) in the other one */
+    const int gc = st->gc_on && st->p2p;
+    cudaStream_t sB = gc ? st->gs_b : st->s_b, sA = gc ? st->gs_a : main, sC = gc ? st->gs_c : st->s_c;
+    const int rsv_rest = gc ? st->dev_sms - st->rest_sms : st->ac_reserve;      /* SMs the HBM-bound launches leave alone */
     CU(cudaEventRecord(st->ev_start, main));
     CU(cudaStreamWaitEvent(st->s_c, st->ev_start, 0));
-    CU(cudaStreamWaitEvent(st->s_b, st->ev_start, 0));
+    CU(cudaStreamWaitEvent(sB, st->ev_start, 0));
+    if (gc) CU(cudaStreamWaitEvent(sC, st->ev_start, 0));
     if (st->p2p) {
         /* every peer has finished reading its receive buffer (step C of the previous call) before anyone stores into it */
-        CU(kfcu_peer_signal((void *const *)st->d_peer_flags, G, st->rank, st->nchunks, epoch, st->s_b));
-        CU(kfcu_peer_wait(flag_ptr(st, st->rank), G, st->nchunks, epoch, st->s_b));
+        CU(kfcu_peer_signal((void *const *)st->d_peer_flags, G, st->rank, st->nchunks, epoch, sB));
+        CU(kfcu_peer_wait(flag_ptr(st, st->rank), G, st->nchunks, epoch, sB));
     } else {
         CU(cudaStreamWaitEvent(st->s_comm, st->ev_start, 0));
     }
-    /* A(i): rows of plane group i, in place, on the caller's stream */
+    /* A(i): rows of plane group i, in place; A(0) on the caller's stream and the whole device, the later groups beside B */
     for (int i = 0; i < NP; ++i) {
         kiss_fft_cpx *rows = d_in + (size_t)i * Pc * d1 * d2;
-        CU(kiss_fft_batch_dev(st->cfg2, rows, rows, (size_t)Pc * d1, (size_t)d2, (size_t)d2, 1, main));
-        CU(cudaEventRecord(st->ev_a[i], main));
+        cudaStream_t sa = i > 0 ? sA : main;
+        if (i == 1 && sa != main) CU(cudaStreamWaitEvent(sa, st->ev_a[0], 0));
+        kfcu_set_sm_reserve(i > 0 ? rsv_rest : 0);
+        tr_begin(st, "A", i, 0, sa);
+        const int rc_a = kiss_fft_batch_dev(st->cfg2, rows, rows, (size_t)Pc * d1, (size_t)d2, (size_t)d2, 1, sa);
+        tr_end(st, sa);
+        kfcu_set_sm_reserve(0);
+        CU(rc_a);
+        CU(cudaEventRecord(st->ev_a[i], sa));
     }
     for (int j = 0; j < st->nchunks; ++j) {
         for (int i = 0; i < NP; ++i) {
@@ -415,37 +630,62 @@ int kiss_fftnd_mgpu_exec(kiss_fftnd_mgpu_cfg st, kiss_fft_cpx *d_in, kiss_fft_cp
                 else            /* the local send buffer [chunk][dest s][P][cw][d1] */
                     dst[s] = st->send + (size_t)j * chk + (size_t)s * blk + (size_t)i * Pc * cw * d1;
             }
-            if (j == 0) CU(cudaStreamWaitEvent(st->s_b, st->ev_a[i], 0));
-            CU(kiss_fft_planes_pass_peers2_dev(st->cfg1, d_in + (size_t)i * Pc * d1 * d2 + (size_t)j * cw, (kiss_fft_cpx *const *)dst, G,
-                                               (size_t)Pc, (size_t)cw, (size_t)C, (size_t)d2, (size_t)d1 * d2,
-                                               st->p2p ? (size_t)d1 : (size_t)cw * d1, st->p2p ? (size_t)d0 * d1 : 0,
-                                               st->p2p ? st->b_ctas : 0, st->s_b));
+            if (j == 0) CU(cudaStreamWaitEvent(sB, st->ev_a[i], 0));
+            /* partition: the grid is sized to the link partition.  NCCL path: B is HBM-bound itself; beside a running
+             * exchange (j > 0) it leaves the SMs NCCL's kernel needs */
+            kfcu_set_sm_reserve(gc ? st->dev_sms - st->link_sms : (!st->p2p && j > 0 ? st->ac_reserve : 0));
+            tr_begin(st, "B", i, j, sB);
+            const int rc_b = kiss_fft_planes_pass_peers2_dev(st->cfg1, d_in + (size_t)i * Pc * d1 * d2 + (size_t)j * cw, (kiss_fft_cpx *const *)dst, G,
+                                                             (size_t)Pc, (size_t)cw, (size_t)C, (size_t)d2, (size_t)d1 * d2,
+                                                             st->p2p ? (size_t)d1 : (size_t)cw * d1, st->p2p ? (size_t)d0 * d1 : 0,
+                                                             st->p2p && !gc ? st->b_ctas : 0, sB);
+            tr_end(st, sB);
+            kfcu_set_sm_reserve(0);
+            CU(rc_b);
         }
+        const int last = j + 1 == st->nchunks;
+        cudaStream_t sc = last ? st->s_c : sC;      /* the last C runs after every B of every rank: whole device */
         if (st->p2p) {
-            CU(kfcu_peer_signal((void *const *)st->d_peer_flags, G, st->rank, j, epoch, st->s_b));
-            CU(kfcu_peer_wait(flag_ptr(st, st->rank), G, j, epoch, st->s_c));
+            CU(kfcu_peer_signal((void *const *)st->d_peer_flags, G, st->rank, j, epoch, sB));
+            CU(kfcu_peer_wait(flag_ptr(st, st->rank), G, j, epoch, sc));
         } else {
-            CU(cudaEventRecord(st->ev_b[j], st->s_b));
+            CU(cudaEventRecord(st->ev_b[j], sB));
             CU(cudaStreamWaitEvent(st->s_comm, st->ev_b[j], 0));
+            tr_begin(st, "X", 0, j, st->s_comm);
             NC(g_nccl.GroupStart());
             for (int s = 0; s < G; ++s) {
                 NC(g_nccl.Send(st->send + (size_t)j * chk + (size_t)s * blk, blk * sizeof(kiss_fft_cpx), KF_NCCL_UINT8, s, st->comm, st->s_comm));
                 NC(g_nccl.Recv(recv + (size_t)j * chk + (size_t)s * blk, blk * sizeof(kiss_fft_cpx), KF_NCCL_UINT8, s, st->comm, st->s_comm));
             }
             NC(g_nccl.GroupEnd());
+            tr_end(st, st->s_comm);
             CU(cudaEventRecord(st->ev_x[j], st->s_comm));
-            CU(cudaStreamWaitEvent(st->s_c, st->ev_x[j], 0));
+            CU(cudaStreamWaitEvent(sc, st->ev_x[j], 0));
         }
         /* C(j): axis 0 of what has arrived from every rank */
+        int rc_c;
+        tr_begin(st, "C", 0, j, sc);
+        kfcu_set_sm_reserve(last ? 0 : rsv_rest);
         if (st->p2p)
-            CU(kiss_fft_planes_pass_dev(st->cfg0, recv + (size_t)j * chk, d_out + (size_t)j * cw * d1 * d0, (size_t)cw, (size_t)d1, (size_t)d1,
-                                        (size_t)d0 * d1, (size_t)d1 * d0, st->s_c));
+            rc_c = kiss_fft_planes_pass_dev(st->cfg0, recv + (size_t)j * chk, d_out + (size_t)j * cw * d1 * d0, (size_t)cw, (size_t)d1, (size_t)d1,
+                                            (size_t)d0 * d1, (size_t)d1 * d0, sc);
         else
-            CU(kiss_fft_axis_pass_dev(st->cfg0, recv + (size_t)j * chk, d_out + (size_t)j * cw * d1 * d0, (size_t)cw * d1, (size_t)cw * d1, st->s_c));
+            rc_c = kiss_fft_axis_pass_dev(st->cfg0, recv + (size_t)j * chk, d_out + (size_t)j * cw * d1 * d0, (size_t)cw * d1, (size_t)cw * d1, sc);
+        tr_end(st, sc);
+        kfcu_set_sm_reserve(0);
+        CU(rc_c);
     }
-    CU(cudaEventRecord(st->ev_bdone, st->s_b));
+    CU(cudaEventRecord(st->ev_bdone, sB));
     CU(cudaEventRecord(st->ev_done, st->s_c));
     CU(cudaStreamWaitEvent(main, st->ev_bdone, 0));
     CU(cudaStreamWaitEvent(main, st->ev_done, 0));
+    if (gc) {
+        CU(cudaEventRecord(st->ev_done2, sC));
+        CU(cudaStreamWaitEvent(main, st->ev_done2, 0));
+        if (NP > 1) {       /* implied by the B launches that waited for every A, stated for the reader */
+            CU(cudaEventRecord(st->ev_adone, sA));
+            CU(cudaStreamWaitEvent(main, st->ev_adone, 0));
+        }
+    }
     return 0;
 }
