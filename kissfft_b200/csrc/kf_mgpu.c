@@ -370,7 +370,7 @@ kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int invers
     st->planes = st->d0 / nranks;
     st->cols = st->d2 / nranks;
     /* chunks of the k2 columns: as many as requested / up to 4, keeping whole 16-column tiles per chunk where possible */
-    int want = nranks <= 2 ? 2 : 4;    /* measured at G = 2 (profiles/r02/mgpu_g2_knobs.txt): more chunks only add launches */
+    int want = 2;                      /* measured at G = 2, 4, 8 (profiles/r02/mgpu_*sweep*): more chunks only add launches and gaps */
     const char *env = getenv("KISSFFT_MGPU_CHUNKS");
     if (env && atoi(env) > 0) want = atoi(env);
     kf_set_chunks(st, want);
@@ -431,9 +431,11 @@ kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int invers
         if (ok && (flags & KISS_FFT_MGPU_P2P)) st->p2p = kf_mgpu_map_peers(st) == 0;   /* falls back to NCCL when IPC is unavailable */
         if (ok && !st->p2p) ok = cudaMalloc((void **)&st->send, st->recv_bytes) == cudaSuccess;
         if (ok && st->p2p && !(flags & KISS_FFT_MGPU_REFERENCE_ORDER)) {
-            /* SMs of the link partition: B at full rate takes about 0.21 * G/(G-1) of its NVLink time (measured: 2.8/G ms
-             * against 8 GiB (G-1)/G^2 at 0.65 TB/s), plus a margin; the hardware rounds up to a multiple of 8 */
-            int want_link = (int)(0.245 * st->dev_sms * nranks / (nranks - 1));
+            /* SMs of the link partition.  B must keep NVLink busy (0.62-0.65 TB/s measured for SM stores at every G): at
+             * G = 2 it moves as many HBM bytes as link bytes and needs half the device (72 = one die), at G >= 4 it is
+             * link-bound.  Measured on 1024^3 (profiles/r02/mgpu_*_green_context_sweep*): G = 2: 72, G = 4: 48, G = 8: 64. */
+            int want_link = nranks <= 2 ? 72 : nranks <= 4 ? 48 : 64;
+            if (want_link + 16 > st->dev_sms) want_link = st->dev_sms / 2 / 8 * 8;
             env = getenv("KISSFFT_MGPU_LINK_SMS");
             if (env && atoi(env) >= 0) want_link = atoi(env);
             kf_make_partition(st, want_link);
