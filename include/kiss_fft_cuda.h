@@ -138,7 +138,8 @@ size_t KISS_FFT_API kiss_fftnd_mgpu_a2a_bytes(kiss_fftnd_mgpu_cfg cfg);
 const char KISS_FFT_API *kiss_fftnd_mgpu_last_error(void);
 /* tuning aid, COLLECTIVE with no exec in flight: knobs = {chunks of the exchange, plane groups, CTA cap of the link-bound
  * launches (0 = none), priority stream for them (0/1), SMs the HBM-bound launches leave to them, trace (0/1), SMs of the
- * link-bound green-context partition (0 = no partition)}, a negative entry keeps the current value; _knob reads one back
+ * link-bound green-context partition (0 = no partition), unused, share of the last chunk in sixteenths (0 = equal chunks)},
+ * a negative entry keeps the current value; _knob reads one back
  * (6: SMs of the link partition actually provisioned, 7: SMs of the other one) */
 int KISS_FFT_API kiss_fftnd_mgpu_tune(kiss_fftnd_mgpu_cfg cfg, const int *knobs, int nknobs);
 int KISS_FFT_API kiss_fftnd_mgpu_knob(kiss_fftnd_mgpu_cfg cfg, int which);

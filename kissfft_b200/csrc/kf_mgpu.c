@@ -149,7 +149,9 @@ static int kf_drv_load(void)
 struct kiss_fftnd_mgpu_state {
     uint32_t magic;
     int d0, d1, d2, inverse, rank, nranks, device;
-    int planes, cols, nchunks, cw; /* P, C = d2/G, chunks of the k2 columns, columns per chunk */
+    int planes, cols, nchunks, cw; /* P, C = d2/G, chunks of the k2 columns, columns per chunk (uniform split) */
+    int coff[KF_MGPU_MAXCHUNKS + 1]; /* first column of every chunk; the last chunk may be narrower (tail16) so that the exposed last C is short */
+    int tail16;                    /* share of the last chunk in sixteenths of C (0 = equal chunks) */
     int b_prio;                    /* s_b is a highest-priority stream */
     int trace, ntr;                /* tuning aid: timed events around every launch of the last exec (kiss_fftnd_mgpu_trace) */
     cudaEvent_t tr_ev[KF_MGPU_MAXTRACE][2], tr_t0;
@@ -212,8 +214,6 @@ int kiss_fftnd_mgpu_get_id(void *id)
     return 0;
 }
 
-static size_t block_elems(const struct kiss_fftnd_mgpu_state *st) { return (size_t)st->planes * st->cw * st->d1; }
-static size_t chunk_elems(const struct kiss_fftnd_mgpu_state *st) { return block_elems(st) * (size_t)st->nranks; }
 static unsigned *flag_ptr(const struct kiss_fftnd_mgpu_state *st, int r) { return (unsigned *)(st->peer_base[r] + st->recv_bytes); }
 
 /* map every rank's receive buffer into this process (CUDA IPC); handles travel through an NCCL all-gather */
@@ -323,6 +323,18 @@ static void kf_set_chunks(kiss_fftnd_mgpu_cfg st, int want)
         if (st->cols % c == 0 && ((st->cols / c) % 16 == 0 || c == 1)) { st->nchunks = c; break; }
     if (st->flags & KISS_FFT_MGPU_REFERENCE_ORDER) st->nchunks = 1;     /* one exchange block per peer (see kf_exec_reference_order) */
     st->cw = st->cols / st->nchunks;
+    for (int j = 0; j <= st->nchunks; ++j) st->coff[j] = j * st->cw;
+    /* a narrower last chunk: C of the last chunk is the one pass nothing overlaps (every B of every rank precedes it) */
+    if (st->nchunks >= 2 && st->tail16 > 0 && st->tail16 < 16) {
+        int tail = (int)((long long)st->cols * st->tail16 / 16) / 16 * 16;
+        if (tail < 16) tail = 16;
+        const int head = st->cols - tail, nh = st->nchunks - 1;
+        if (head > 0 && head % (16 * nh) == 0 && tail < head / nh) {
+            for (int j = 0; j < nh; ++j) st->coff[j] = j * (head / nh);
+            st->coff[nh] = head;
+            st->coff[st->nchunks] = st->cols;
+        }
+    }
 }
 
 /* Tuning aid (tests/cpp/test_mgpu.c sweeps with it): change the pipeline shape of an existing cfg.  COLLECTIVE -- every
@@ -339,6 +351,7 @@ int kiss_fftnd_mgpu_tune(kiss_fftnd_mgpu_cfg st, const int *knobs, int nknobs)
     if (nknobs > 3 && knobs[3] >= 0 && (knobs[3] != 0) != (st->b_prio != 0)) CU(kf_make_b_stream(st, knobs[3]));
     if (nknobs > 4 && knobs[4] >= 0) st->ac_reserve = knobs[4];
     if (nknobs > 5 && knobs[5] >= 0) st->trace = knobs[5];
+    if (nknobs > 8 && knobs[8] >= 0) { st->tail16 = knobs[8]; kf_set_chunks(st, st->nchunks); }
     if (nknobs > 6 && knobs[6] >= 0 && st->p2p && knobs[6] != (st->gc_on ? st->link_sms : 0)) kf_make_partition(st, knobs[6]);
     return 0;
 }
@@ -346,7 +359,7 @@ int kiss_fftnd_mgpu_knob(kiss_fftnd_mgpu_cfg st, int which)
 {
     if (!st) return -1;
     return which == 0 ? st->nchunks : which == 1 ? st->pchunks : which == 2 ? st->b_ctas : which == 3 ? st->b_prio : which == 4 ? st->ac_reserve :
-           which == 6 ? (st->gc_on ? st->link_sms : 0) : which == 7 ? (st->gc_on ? st->rest_sms : 0) : -1;
+           which == 6 ? (st->gc_on ? st->link_sms : 0) : which == 7 ? (st->gc_on ? st->rest_sms : 0) : which == 8 ? st->coff[st->nchunks] - st->coff[st->nchunks - 1] : -1;
 }
 
 kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int inverse_fft, int rank, int nranks, const void *id,
@@ -373,6 +386,9 @@ kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int invers
     int want = 2;                      /* measured at G = 2, 4, 8 (profiles/r02/mgpu_*sweep*): more chunks only add launches and gaps */
     const char *env = getenv("KISSFFT_MGPU_CHUNKS");
     if (env && atoi(env) > 0) want = atoi(env);
+    st->tail16 = 4;                    /* last chunk = a quarter of the columns (the others share the rest) */
+    env = getenv("KISSFFT_MGPU_TAIL16");
+    if (env && atoi(env) >= 0) st->tail16 = atoi(env);
     kf_set_chunks(st, want);
     st->pchunks = 1;
     if (nranks > 1 && !(flags & KISS_FFT_MGPU_REFERENCE_ORDER))
@@ -576,10 +592,9 @@ int kiss_fftnd_mgpu_exec(kiss_fftnd_mgpu_cfg st, kiss_fft_cpx *d_in, kiss_fft_cp
 {
     if (!st || st->magic != KF_MAGIC_MGPU || !d_in || !d_out) return kf_fail(st, "kiss_fftnd_mgpu_exec: bad argument", KISS_FFT_CUDA_EINVAL, 0);
     if (st->flags & KISS_FFT_MGPU_REFERENCE_ORDER) return kf_exec_reference_order(st, d_in, d_out, (cudaStream_t)stream);
-    const int G = st->nranks, P = st->planes, d0 = st->d0, d1 = st->d1, d2 = st->d2, cw = st->cw, C = st->cols;
+    const int G = st->nranks, P = st->planes, d0 = st->d0, d1 = st->d1, d2 = st->d2, C = st->cols;
     cudaStream_t main = (cudaStream_t)stream;
     kiss_fft_cpx *recv = (kiss_fft_cpx *)st->recv_base;
-    const size_t blk = block_elems(st), chk = chunk_elems(st);
     if (G == 1) {
         /* one rank: rows, then B writes the whole planes transposed into the "receive" buffer, C follows -- no exchange */
         CU(kiss_fft_batch_dev(st->cfg2, d_in, d_in, (size_t)P * d1, (size_t)d2, (size_t)d2, 1, main));
@@ -623,23 +638,25 @@ int kiss_fftnd_mgpu_exec(kiss_fftnd_mgpu_cfg st, kiss_fft_cpx *d_in, kiss_fft_cp
         CU(cudaEventRecord(st->ev_a[i], sa));
     }
     for (int j = 0; j < st->nchunks; ++j) {
+        const int c0 = st->coff[j], cwj = st->coff[j + 1] - c0;              /* columns [c0, c0 + cwj) of every rank's range */
+        const size_t cbase = (size_t)c0 * d0 * d1, blk = (size_t)P * cwj * d1; /* chunk j in the receive / send buffer; one (source, chunk) block */
         for (int i = 0; i < NP; ++i) {
-            /* B(i, j): k2 columns s*C + j*cw + [0, cw) of the planes of group i go to rank s, transposed */
+            /* B(i, j): k2 columns s*C + c0 + [0, cwj) of the planes of group i go to rank s, transposed */
             kiss_fft_cpx *dst[KF_MGPU_MAXRANKS];
             for (int s = 0; s < G; ++s) {
                 if (st->p2p)    /* the receiver's layout [chunk][c][i0 = me*P + plane][d1] */
-                    dst[s] = (kiss_fft_cpx *)st->peer_base[s] + (size_t)j * chk + ((size_t)st->rank * P + (size_t)i * Pc) * d1;
+                    dst[s] = (kiss_fft_cpx *)st->peer_base[s] + cbase + ((size_t)st->rank * P + (size_t)i * Pc) * d1;
                 else            /* the local send buffer [chunk][dest s][P][cw][d1] */
-                    dst[s] = st->send + (size_t)j * chk + (size_t)s * blk + (size_t)i * Pc * cw * d1;
+                    dst[s] = st->send + cbase + (size_t)s * blk + (size_t)i * Pc * cwj * d1;
             }
             if (j == 0) CU(cudaStreamWaitEvent(sB, st->ev_a[i], 0));
             /* partition: the grid is sized to the link partition.  NCCL path: B is HBM-bound itself; beside a running
              * exchange (j > 0) it leaves the SMs NCCL's kernel needs */
             kfcu_set_sm_reserve(gc ? st->dev_sms - st->link_sms : (!st->p2p && j > 0 ? st->ac_reserve : 0));
             tr_begin(st, "B", i, j, sB);
-            const int rc_b = kiss_fft_planes_pass_peers2_dev(st->cfg1, d_in + (size_t)i * Pc * d1 * d2 + (size_t)j * cw, (kiss_fft_cpx *const *)dst, G,
-                                                             (size_t)Pc, (size_t)cw, (size_t)C, (size_t)d2, (size_t)d1 * d2,
-                                                             st->p2p ? (size_t)d1 : (size_t)cw * d1, st->p2p ? (size_t)d0 * d1 : 0,
+            const int rc_b = kiss_fft_planes_pass_peers2_dev(st->cfg1, d_in + (size_t)i * Pc * d1 * d2 + (size_t)c0, (kiss_fft_cpx *const *)dst, G,
+                                                             (size_t)Pc, (size_t)cwj, (size_t)C, (size_t)d2, (size_t)d1 * d2,
+                                                             st->p2p ? (size_t)d1 : (size_t)cwj * d1, st->p2p ? (size_t)d0 * d1 : 0,
                                                              st->p2p && !gc ? st->b_ctas : 0, sB);
             tr_end(st, sB);
             kfcu_set_sm_reserve(0);
@@ -649,6 +666,11 @@ int kiss_fftnd_mgpu_exec(kiss_fftnd_mgpu_cfg st, kiss_fft_cpx *d_in, kiss_fft_cp
         cudaStream_t sc = last ? st->s_c : sC;      /* the last C runs after every B of every rank: whole device */
         if (st->p2p) {
             CU(kfcu_peer_signal((void *const *)st->d_peer_flags, G, st->rank, j, epoch, sB));
+            /* the spinning wait is submitted only once the local stores of this chunk are done (the peers finish theirs at
+             * about the same time): a kernel that spins from the start of the exec at the head of a hardware queue holds
+             * up whatever other stream shares that queue (CUDA_DEVICE_MAX_CONNECTIONS) */
+            CU(cudaEventRecord(st->ev_b[j], sB));
+            CU(cudaStreamWaitEvent(sc, st->ev_b[j], 0));
             CU(kfcu_peer_wait(flag_ptr(st, st->rank), G, j, epoch, sc));
         } else {
             CU(cudaEventRecord(st->ev_b[j], sB));
@@ -656,8 +678,8 @@ int kiss_fftnd_mgpu_exec(kiss_fftnd_mgpu_cfg st, kiss_fft_cpx *d_in, kiss_fft_cp
             tr_begin(st, "X", 0, j, st->s_comm);
             NC(g_nccl.GroupStart());
             for (int s = 0; s < G; ++s) {
-                NC(g_nccl.Send(st->send + (size_t)j * chk + (size_t)s * blk, blk * sizeof(kiss_fft_cpx), KF_NCCL_UINT8, s, st->comm, st->s_comm));
-                NC(g_nccl.Recv(recv + (size_t)j * chk + (size_t)s * blk, blk * sizeof(kiss_fft_cpx), KF_NCCL_UINT8, s, st->comm, st->s_comm));
+                NC(g_nccl.Send(st->send + cbase + (size_t)s * blk, blk * sizeof(kiss_fft_cpx), KF_NCCL_UINT8, s, st->comm, st->s_comm));
+                NC(g_nccl.Recv(recv + cbase + (size_t)s * blk, blk * sizeof(kiss_fft_cpx), KF_NCCL_UINT8, s, st->comm, st->s_comm));
             }
             NC(g_nccl.GroupEnd());
             tr_end(st, st->s_comm);
@@ -669,10 +691,10 @@ int kiss_fftnd_mgpu_exec(kiss_fftnd_mgpu_cfg st, kiss_fft_cpx *d_in, kiss_fft_cp
         tr_begin(st, "C", 0, j, sc);
         kfcu_set_sm_reserve(last ? 0 : rsv_rest);
         if (st->p2p)
-            rc_c = kiss_fft_planes_pass_dev(st->cfg0, recv + (size_t)j * chk, d_out + (size_t)j * cw * d1 * d0, (size_t)cw, (size_t)d1, (size_t)d1,
+            rc_c = kiss_fft_planes_pass_dev(st->cfg0, recv + cbase, d_out + (size_t)c0 * d1 * d0, (size_t)cwj, (size_t)d1, (size_t)d1,
                                             (size_t)d0 * d1, (size_t)d1 * d0, sc);
         else
-            rc_c = kiss_fft_axis_pass_dev(st->cfg0, recv + (size_t)j * chk, d_out + (size_t)j * cw * d1 * d0, (size_t)cw * d1, (size_t)cw * d1, sc);
+            rc_c = kiss_fft_axis_pass_dev(st->cfg0, recv + cbase, d_out + (size_t)c0 * d1 * d0, (size_t)cwj * d1, (size_t)cwj * d1, sc);
         tr_end(st, sc);
         kfcu_set_sm_reserve(0);
         CU(rc_c);

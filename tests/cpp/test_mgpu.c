@@ -53,14 +53,14 @@ static int run_rank(int rank, int G, const int *dims, unsigned flags, int iters,
         cudaEvent_t e0, e1;
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
-        /* MGPU_TEST_SWEEP="chunks:pchunks:b_ctas:prio:ac_reserve:trace:link_sms,..." : every entry is applied with kiss_fftnd_mgpu_tune and timed */
+        /* MGPU_TEST_SWEEP="chunks:pchunks:b_ctas:prio:ac_reserve:trace:link_sms:tail16,..." : every entry is applied with kiss_fftnd_mgpu_tune and timed */
         const char *sweep = getenv("MGPU_TEST_SWEEP");
         char buf[1024];
         snprintf(buf, sizeof(buf), "%s", sweep && *sweep ? sweep : "-1:-1:-1:-1");
         for (char *save = NULL, *tok = strtok_r(buf, ",", &save); tok; tok = strtok_r(NULL, ",", &save)) {
-            int k[7] = {-1, -1, -1, -1, -1, 0, -1};
-            sscanf(tok, "%d:%d:%d:%d:%d:%d:%d", &k[0], &k[1], &k[2], &k[3], &k[4], &k[5], &k[6]);
-            CK(kiss_fftnd_mgpu_tune(c2, k, 7));
+            int k[9] = {-1, -1, -1, -1, -1, 0, -1, -1, -1};
+            sscanf(tok, "%d:%d:%d:%d:%d:%d:%d:%d", &k[0], &k[1], &k[2], &k[3], &k[4], &k[5], &k[6], &k[8]);
+            CK(kiss_fftnd_mgpu_tune(c2, k, 9));
             for (int i = 0; i < 3; ++i) CK(kiss_fftnd_mgpu_exec(c2, a, b, NULL));
             CK(cudaDeviceSynchronize());
             CK(cudaEventRecord(e0, NULL));
@@ -70,9 +70,9 @@ static int run_rank(int rank, int G, const int *dims, unsigned flags, int iters,
             float t = 0;
             CK(cudaEventElapsedTime(&t, e0, e1));
             if (rank == 0 || getenv("MGPU_TEST_ALL_RANKS"))
-                printf("{\"rank\": %d, \"ranks\": %d, \"p2p\": %d, \"chunks\": %d, \"pchunks\": %d, \"b_ctas\": %d, \"prio\": %d, \"ac_reserve\": %d, \"link_sms\": %d, \"rest_sms\": %d, \"ms\": %.4f}\n", rank, G,
+                printf("{\"rank\": %d, \"ranks\": %d, \"p2p\": %d, \"chunks\": %d, \"pchunks\": %d, \"b_ctas\": %d, \"prio\": %d, \"ac_reserve\": %d, \"link_sms\": %d, \"rest_sms\": %d, \"last_chunk_cols\": %d, \"ms\": %.4f}\n", rank, G,
                        kiss_fftnd_mgpu_uses_p2p(c2), kiss_fftnd_mgpu_knob(c2, 0), kiss_fftnd_mgpu_knob(c2, 1), kiss_fftnd_mgpu_knob(c2, 2),
-                       kiss_fftnd_mgpu_knob(c2, 3), kiss_fftnd_mgpu_knob(c2, 4), kiss_fftnd_mgpu_knob(c2, 6), kiss_fftnd_mgpu_knob(c2, 7), t / (iters > 0 ? iters : 1));
+                       kiss_fftnd_mgpu_knob(c2, 3), kiss_fftnd_mgpu_knob(c2, 4), kiss_fftnd_mgpu_knob(c2, 6), kiss_fftnd_mgpu_knob(c2, 7), kiss_fftnd_mgpu_knob(c2, 8), t / (iters > 0 ? iters : 1));
             fflush(stdout);
             if (k[5] > 0 && rank == 0) {       /* sixth field: print the launch timeline of the last exec */
                 static char tl[8192];

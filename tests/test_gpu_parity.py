@@ -440,6 +440,9 @@ def test_config2_real_4096_x_32768():
     torch.cuda.synchronize()
     assert rel_rms(host(d_y) / nfft, x) <= 2e-6 * np.log2(nfft)
     check(tname, host(d_y)[idx], o.fftri(got[idx]), nfft, "c2r sample")
+    if have_reference(tname):
+        # kiss_fftri of the compiled reference on the same spectra, the WHOLE batch (like R2C above)
+        check(tname, host(d_y), Reference(tname).fftri(got, nthreads=__import__("os").cpu_count()), nfft, "c2r full vs reference")
     lib.free(cfg)
     lib.free(cfgi)
 
