@@ -192,6 +192,9 @@ void KISS_FFT_API kiss_fft_cuda_force_generic(int on);
 /* cap the number of CTAs of the fused kernels the CALLING THREAD launches after this call (0 = fill the device).  Used by the slab
  * transform so that its NVLink-bound peer-store launches share the SMs with HBM-bound launches on another stream. */
 void KISS_FFT_API kiss_fft_cuda_set_grid_limit(int max_ctas);
+/* testing aid (host logic, no CUDA call): the chunks a host-pointer batched call of `howmany` rows is cut into for a
+ * chunk size of `rows` rows -- small chunks at both ends when ramp != 0; returns their number, fills first[] / n[] up to cap */
+size_t KISS_FFT_API kiss_fft_cuda_debug_chunks(size_t howmany, size_t rows, int ramp, size_t *first, size_t *n, size_t cap);
 /* sizeof(kiss_fft_scalar) of this build (4 float, 8 double, 2 Q15, 4 Q31) and 1 for fixed point */
 int KISS_FFT_API kiss_fft_cuda_scalar_bytes(void);
 int KISS_FFT_API kiss_fft_cuda_is_fixed_point(void);

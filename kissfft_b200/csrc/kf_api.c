@@ -1118,12 +1118,16 @@ static int kf_chunk_c2r(void *cfg, const void *d_in, void *d_out, size_t n, void
 #define KF_CHUNK_MIB_PAGEABLE 4
 #define KF_MAX_LANES 16
 
+typedef struct { size_t first, n; } kf_span;   /* rows [first, first + n) of the batch */
+
 typedef struct {
     kf_chunk_fn fn;
     void *cfg;
     const char *in;
     char *out;
-    size_t howmany, rows, in_row_bytes, out_row_bytes;
+    size_t rows, in_row_bytes, out_row_bytes;   /* rows = the largest chunk (buffer size) */
+    const kf_span *chunks;                      /* the chunks of the batch, in order; lanes take the next one when free */
+    size_t nchunks, *next;
     int lane, nlanes, device, in_pinned, out_pinned;
     kf_ctx *cx;
     int rc;
@@ -1134,15 +1138,15 @@ static void *kf_lane_main(void *arg)
     kf_lane *L = (kf_lane *)arg;
     int rc = (int)cudaSetDevice(L->device);
     kf_ctx *cx = L->cx;
-    const size_t nchunks = (L->howmany + L->rows - 1) / L->rows;
     void *din = NULL, *dout = NULL, *pin = NULL, *pout = NULL;
     if (!rc) rc = kf_ctx_dev(cx, 0, L->rows * L->in_row_bytes, &din);
     if (!rc) rc = kf_ctx_dev(cx, 1, L->rows * L->out_row_bytes, &dout);
     if (!rc && !L->in_pinned) rc = kf_ctx_pin(cx, 0, L->rows * L->in_row_bytes, &pin);
     if (!rc && !L->out_pinned) rc = kf_ctx_pin(cx, 1, L->rows * L->out_row_bytes, &pout);
-    for (size_t c = (size_t)L->lane; !rc && c < nchunks; c += (size_t)L->nlanes) {
-        const size_t first = c * L->rows;
-        const size_t n = (L->howmany - first < L->rows) ? L->howmany - first : L->rows;
+    while (!rc) {
+        const size_t c = __atomic_fetch_add(L->next, 1, __ATOMIC_RELAXED);
+        if (c >= L->nchunks) break;
+        const size_t first = L->chunks[c].first, n = L->chunks[c].n;
         const void *src = L->in + first * L->in_row_bytes;
         void *dst = L->out + first * L->out_row_bytes;
         if (!L->in_pinned) {
@@ -1158,6 +1162,42 @@ static void *kf_lane_main(void *arg)
     }
     L->rc = rc;
     return NULL;
+}
+
+/* Cuts the batch into chunks of `rows` rows with a ramp at both ends (rows/8, rows/8, rows/4, rows/2, rows ... rows,
+ * rows/2, rows/4, rows/8, rows/8): nothing leaves the device before the first chunk has gone in and come back, and nothing
+ * enters while the last one comes out, so the first and the last chunk are the part of the call where only one PCIe
+ * direction is busy -- they should be small, the chunks in between large (profiles/r02/pcie_probe.jsonl: both directions
+ * together carry 2 x 50 GB/s, a call with uniform 32 MiB chunks reached 2 x 44).  All sizes are multiples of 64 rows. */
+static size_t kf_make_chunks(size_t howmany, size_t rows, int ramp, kf_span **out)
+{
+    size_t cap = howmany / rows + 12, n = 0, pos = 0;
+    kf_span *v = (kf_span *)malloc(sizeof(kf_span) * cap);
+    if (!v) return 0;
+    size_t head[4], nh = 0;
+    if (ramp && rows >= 512 && howmany >= 6 * rows) {
+        const size_t div[4] = {8, 8, 4, 2};
+        for (int i = 0; i < 4; ++i) head[nh++] = (rows / div[i]) & ~(size_t)63;
+    }
+    size_t tail_rows = 0;
+    for (size_t i = 0; i < nh; ++i) tail_rows += head[i];
+    for (size_t i = 0; i < nh; ++i) { v[n].first = pos; v[n].n = head[i]; pos += head[i]; ++n; }
+    while (howmany - pos > tail_rows + rows) { v[n].first = pos; v[n].n = rows; pos += rows; ++n; }
+    if (howmany - pos > tail_rows) { v[n].first = pos; v[n].n = howmany - pos - tail_rows; pos += v[n].n; ++n; }
+    for (size_t i = nh; i-- > 0;) { v[n].first = pos; v[n].n = head[i]; pos += head[i]; ++n; }
+    if (pos < howmany) { v[n].first = pos; v[n].n = howmany - pos; ++n; }     /* no ramp: the remainder */
+    *out = v;
+    return n;
+}
+
+/* testing aid (host logic only, no CUDA call): the chunk list kf_host_pipeline would use */
+size_t kiss_fft_cuda_debug_chunks(size_t howmany, size_t rows, int ramp, size_t *first, size_t *n, size_t cap)
+{
+    kf_span *v = NULL;
+    const size_t k = kf_make_chunks(howmany, rows, ramp, &v);
+    for (size_t i = 0; i < k && i < cap; ++i) { first[i] = v[i].first; n[i] = v[i].n; }
+    free(v);
+    return k;
 }
 
 static int kf_host_lanes(size_t nchunks, int pinned)
@@ -1191,10 +1231,14 @@ static int kf_host_pipeline(kf_chunk_fn fn, void *cfg, const void *in, void *out
     if (rows < 1) rows = 1;
     if (rows >= 64) rows &= ~(size_t)63; /* whole tiles for every fused plan (tpc <= 16) and 16-byte aligned chunk sizes */
     if (rows > howmany) rows = howmany;
-    const size_t nchunks = (howmany + rows - 1) / rows;
-    const int nlanes = kf_host_lanes(nchunks, in_pinned && out_pinned);
     int dev = 0;
+    size_t next = 0;
     KF_CHECK(cudaGetDevice(&dev));
+    env = getenv("KISSFFT_CHUNK_RAMP");
+    kf_span *chunks = NULL;
+    const size_t nchunks = kf_make_chunks(howmany, rows, env && env[0] == '1', &chunks);    /* opt-in: no gain measured (profiles/r02/e2e_ramp_async.txt) */
+    if (!nchunks) return kf_cuda_fail(__FILE__, __LINE__, "host batch pipeline", KISS_FFT_CUDA_ENOMEM);
+    const int nlanes = kf_host_lanes(nchunks, in_pinned && out_pinned);
     kf_lane lanes[KF_MAX_LANES];
     pthread_t thr[KF_MAX_LANES];
     int started[KF_MAX_LANES];
@@ -1204,11 +1248,36 @@ static int kf_host_pipeline(kf_chunk_fn fn, void *cfg, const void *in, void *out
         memset(L, 0, sizeof(*L));
         started[l] = 0;
         L->fn = fn; L->cfg = cfg; L->in = (const char *)in; L->out = (char *)out;
-        L->howmany = howmany; L->rows = rows; L->in_row_bytes = in_row_bytes; L->out_row_bytes = out_row_bytes;
+        L->rows = rows; L->in_row_bytes = in_row_bytes; L->out_row_bytes = out_row_bytes;
+        L->chunks = chunks; L->nchunks = nchunks; L->next = &next;
         L->lane = l; L->nlanes = nlanes; L->device = dev; L->in_pinned = in_pinned; L->out_pinned = out_pinned;
         if (!rc) rc = kf_ctx_acquire(&L->cx);
     }
-    if (!rc) {
+    env = getenv("KISSFFT_HOST_ASYNC");
+    if (!rc && in_pinned && out_pinned && env && env[0] == '1') {
+        /* opt-in (KISSFFT_HOST_ASYNC=1; measured equal to the threaded lanes within the box-to-box spread,
+         * profiles/r02/e2e_ramp_async.txt).  Pinned caller buffers: nothing for the host to do per chunk, so ONE thread enqueues every chunk up front -- chunk c on
+         * the stream of slot c % nlanes (H2D, kernel, D2H in stream order; the slot's device buffers are reused in stream
+         * order too) -- and waits once at the end.  Both copy engines always have queued work; the per-chunk host wake-up of
+         * the threaded lanes (needed only for the bounce copies of pageable memory) is gone. */
+        void *din[KF_MAX_LANES], *dout[KF_MAX_LANES];
+        for (int l = 0; !rc && l < nlanes; ++l) {
+            rc = kf_ctx_dev(lanes[l].cx, 0, rows * in_row_bytes, &din[l]);
+            if (!rc) rc = kf_ctx_dev(lanes[l].cx, 1, rows * out_row_bytes, &dout[l]);
+        }
+        for (size_t c = 0; !rc && c < nchunks; ++c) {
+            const int l = (int)(c % (size_t)nlanes);
+            cudaStream_t st = lanes[l].cx->stream;
+            const size_t first = chunks[c].first, n = chunks[c].n;
+            rc = (int)cudaMemcpyAsync(din[l], (const char *)in + first * in_row_bytes, n * in_row_bytes, cudaMemcpyHostToDevice, st);
+            if (!rc) rc = fn(cfg, din[l], dout[l], n, st);
+            if (!rc) rc = (int)cudaMemcpyAsync((char *)out + first * out_row_bytes, dout[l], n * out_row_bytes, cudaMemcpyDeviceToHost, st);
+        }
+        for (int l = 0; l < nlanes; ++l) {
+            const int e = (int)cudaStreamSynchronize(lanes[l].cx->stream);
+            if (!rc) rc = e;
+        }
+    } else if (!rc) {
         for (int l = 1; l < nlanes; ++l) {
             if (pthread_create(&thr[l], NULL, kf_lane_main, &lanes[l]) == 0) started[l] = 1;
         }
@@ -1220,6 +1289,7 @@ static int kf_host_pipeline(kf_chunk_fn fn, void *cfg, const void *in, void *out
         for (int l = 0; l < nlanes; ++l)
             if (!rc) rc = lanes[l].rc;
     }
+    free(chunks);
     for (int l = 0; l < nlanes; ++l) kf_ctx_release(lanes[l].cx);
     if (rc) return kf_cuda_fail(__FILE__, __LINE__, "host batch pipeline", rc);
     return 0;

@@ -118,3 +118,27 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     monkeypatch.setattr(kissfft_b200, "HERE", str(tmp_path))
     with pytest.raises(kissfft_b200.KissFFTError):
         kissfft_b200.KissFFT("float")
+
+
+@pytest.mark.parametrize("howmany,rows", [(32768, 1984), (65536, 4096), (100000, 3584), (7, 64), (1, 1), (4096, 512), (11905, 1984), (3071, 512)])
+@pytest.mark.parametrize("ramp", [0, 1])
+def test_host_pipeline_chunks_cover_the_batch(howmany, rows, ramp):
+    """kf_host_pipeline's chunk list (ramped at both ends so that the PCIe fill/drain of a call is short): every row
+    exactly once, in order, no chunk larger than the staging buffers"""
+    import ctypes
+    import kissfft_b200
+    L = kissfft_b200.get("float").lib
+    L.kiss_fft_cuda_debug_chunks.restype = ctypes.c_size_t
+    L.kiss_fft_cuda_debug_chunks.argtypes = [ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t),
+                                             ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t]
+    cap = 4096
+    first, n = (ctypes.c_size_t * cap)(), (ctypes.c_size_t * cap)()
+    k = L.kiss_fft_cuda_debug_chunks(howmany, rows, ramp, first, n, cap)
+    assert 0 < k <= cap
+    pos = 0
+    for i in range(k):
+        assert first[i] == pos and 0 < n[i] <= rows
+        pos += n[i]
+    assert pos == howmany
+    if ramp and howmany >= 6 * rows and rows >= 512:
+        assert n[0] < rows / 4 and n[k - 1] < rows / 4, "the first and the last chunk are the exposed ones"
