@@ -17,12 +17,13 @@
  *          a flag per (chunk, source rank) in the receiver's memory says "landed".
  *   C. axis 0 of chunk j, as soon as chunk j has arrived from every rank  kiss_fft_axis_pass_dev  [d2/G][d1][d0]
  *
- * Pipeline (three streams): the local planes are cut into `pchunks` groups as well.  A(i) runs on the caller's stream;
- * B(i, 0) follows A(i) on a second stream, so the link-bound stores of the first k2 chunk overlap the rows of the next
- * plane groups; then B(., 1), B(., 2), ... while C(j-1) runs on a third stream as soon as chunk j-1 has landed from every
- * rank.  Exposed: A(0), the exchange itself, and C of the last chunk.  Launches of B whose stores cross NVLink are
- * capped to a fraction of the SMs (KISSFFT_MGPU_B_CTAS, default 48): they are link-bound, and the persistent CTAs of an
- * uncapped launch would keep the HBM-bound kernels of the other streams off the SMs until it ends.
+ * Pipeline: the k2 columns are cut into chunks (2; the last one narrower, kf_set_chunks) and the local planes into groups (2).
+ * A(0) runs on the caller's stream; B(i, 0) follows A(i), so the link-bound stores of the first chunk overlap the rows of the
+ * next plane group; then B(., 1), ... while C(j-1) runs as soon as chunk j-1 has landed from every rank.  Exposed: A(0), the
+ * exchange itself, and C of the last chunk.  Overlap between these persistent kernels needs the SMs partitioned by hand
+ * (kf_make_partition: CUDA green contexts) -- B in one partition, A(i > 0) and C(j < last) in the other, A(0) and the last C
+ * on the whole device; without green contexts the launches of B are capped instead (KISSFFT_MGPU_B_CTAS).
+ * kiss_fftnd_mgpu_tune / _knob / _trace are the tuning aids the sweeps in profiles/r02/mgpu_* were made with.
  *
  * Receive buffer layout.  NCCL: [chunk j][source rank r][P][cw][d1] -- one contiguous piece per (source, chunk), and chunk
  * j is a dense (G*P) x (cw*d1) matrix for step C (kiss_fft_axis_pass_dev).  Peer stores: [chunk j][c][i0 = r*P + p][d1] --
