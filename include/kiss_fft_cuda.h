@@ -101,6 +101,8 @@ int KISS_FFT_API kiss_fftndri_dev(kiss_fftndr_cfg cfg, const kiss_fft_cpx *d_fre
  * d0 x d1 x d2 is distributed in slabs of d0/G planes: rank r holds x[r*d0/G .. (r+1)*d0/G)[d1][d2].  One exchange
  * (all-to-all) is needed; the result comes out "transposed": rank r holds X[k0][k1][k2] for k2 in [r*d2/G, (r+1)*d2/G)
  * stored as d_out[k2 - r*d2/G][k1][k0].  dims[0] and dims[2] must be divisible by G (G <= 16).
+ * ndims == 2 (d0 x d1, both divisible by G): rank r holds rows r*d0/G ..., receives X[k0][k1] for its k1 range stored
+ * d_out[k1 - r*d1/G][k0]; rows in place, one transposing exchange (peer stores or NCCL), rows.
  *
  *   kiss_fftnd_mgpu_get_id   rank 0 only: fills a KISS_FFT_MGPU_ID_BYTES rendezvous id (an ncclUniqueId); the caller
  *                            distributes it to the other ranks by whatever it has (MPI_Bcast, a pipe, a file, ...)

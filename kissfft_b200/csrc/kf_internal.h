@@ -86,6 +86,9 @@ int kfcu_cmul_rows(void *d_x, const void *d_h, long long rows, int n, void *stre
 /* out[c][r] = in[r][c] for a rows x cols array of complex elements (kiss_fftndr's bin-major <-> row-major
  * scatter loops, kiss_fftndr.c:101-102, 107-108) */
 int kfcu_transpose(const void *d_in, void *d_out, long long rows, long long cols, void *stream);
+/* columns split into npeers blocks; block s lands transposed in peers[s] as [cols_per_peer][out_pitch] + out_off */
+int kfcu_transpose_peers(const void *d_in, long long in_pitch, void *const *peers, int npeers, long long rows, long long cols_per_peer,
+                         long long out_pitch, long long out_off, void *stream);
 
 /* 1 if a compile-time (fused, register-group) plan exists for this length/mode in this datatype build */
 int kfcu_has_fused(int nfft, int mode);

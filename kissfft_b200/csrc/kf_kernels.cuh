@@ -153,4 +153,31 @@ __global__ void __launch_bounds__(256) kf_transpose_kernel(const C* __restrict__
     }
 }
 
+// the same tiles with the columns split into npeers blocks: block s (columns s*cols_per_peer + [0, cols_per_peer) of a
+// rows x (npeers*cols_per_peer) array with row pitch in_pitch) lands transposed in peers.p[s] as
+// [cols_per_peer][out_pitch], shifted by out_off elements inside every output row.  Exchange step of the 2-D slab transform
+// (kf_mgpu.c): every destination row piece is `rows` contiguous elements, written straight into the owner's memory.
+struct KfPeerPtrs {
+    void* p[16];
+};
+template <class C>
+__global__ void __launch_bounds__(256) kf_transpose_peers_kernel(const C* __restrict__ in, long long in_pitch, KfPeerPtrs peers, int npeers,
+                                                                long long rows, long long cols_per_peer, long long out_pitch, long long out_off)
+{
+    __shared__ C tile[32][33];
+    const long long tiles_c = (cols_per_peer + 31) / 32, tiles_r = (rows + 31) / 32, per = tiles_c * tiles_r;
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;   // 32 x 8
+    for (long long tI = blockIdx.x; tI < per * npeers; tI += gridDim.x) {
+        const int s = (int)(tI / per);
+        const long long q = tI % per, r0 = (q / tiles_c) * 32, c0 = (q % tiles_c) * 32;
+        C* const out = (C*)peers.p[s];
+        for (int j = ty; j < 32; j += 8)
+            if (r0 + j < rows && c0 + tx < cols_per_peer) tile[j][tx] = in[(r0 + j) * in_pitch + s * cols_per_peer + c0 + tx];
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8)
+            if (c0 + j < cols_per_peer && r0 + tx < rows) out[(c0 + j) * out_pitch + out_off + r0 + tx] = tile[tx][j];
+        __syncthreads();
+    }
+}
+
 }   // namespace kf

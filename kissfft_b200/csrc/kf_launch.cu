@@ -591,6 +591,22 @@ extern "C" int kfcu_transpose(const void* d_in, void* d_out, long long rows, lon
     return (int)cudaGetLastError();
 }
 
+extern "C" int kfcu_transpose_peers(const void* d_in, long long in_pitch, void* const* peers, int npeers, long long rows,
+                                    long long cols_per_peer, long long out_pitch, long long out_off, void* stream)
+{
+    if (!d_in || !peers || npeers < 1 || npeers > 16 || rows < 0 || cols_per_peer < 0) return KFCU_EINVAL;
+    if (rows == 0 || cols_per_peer == 0) return 0;
+    KfPeerPtrs pp;
+    for (int s = 0; s < 16; ++s) pp.p[s] = s < npeers ? peers[s] : nullptr;
+    const long long tiles = ((rows + 31) / 32) * ((cols_per_peer + 31) / 32) * npeers;
+    long long grid = (long long)device_info().sms * 8;
+    if (grid > tiles) grid = tiles;
+    kf_transpose_peers_kernel<CT><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const CT*)d_in, in_pitch, pp, npeers, rows, cols_per_peer,
+                                                                                  out_pitch, out_off);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int kfcu_has_fused(int nfft, int mode)
 {
     if (mode < 0 || mode > 3) return 0;

@@ -153,6 +153,7 @@ struct kiss_fftnd_mgpu_state {
     int planes, cols, nchunks, cw; /* P, C = d2/G, chunks of the k2 columns, columns per chunk (uniform split) */
     int coff[KF_MGPU_MAXCHUNKS + 1]; /* first column of every chunk; the last chunk may be narrower (tail16) so that the exposed last C is short */
     int tail16;                    /* share of the last chunk in sixteenths of C (0 = equal chunks) */
+    int ndims;                     /* 3, or 2 (then d1 == 1) */
     int b_prio;                    /* s_b is a highest-priority stream */
     int trace, ntr;                /* tuning aid: timed events around every launch of the last exec (kiss_fftnd_mgpu_trace) */
     cudaEvent_t tr_ev[KF_MGPU_MAXTRACE][2], tr_t0;
@@ -367,10 +368,18 @@ kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int invers
                                           unsigned flags)
 {
     kiss_fftnd_mgpu_cfg st = NULL;
-    if (!dims || ndims != 3 || nranks < 1 || nranks > KF_MGPU_MAXRANKS || rank < 0 || rank >= nranks || (nranks > 1 && !id)) {
-        kf_fail(NULL, "kiss_fftnd_mgpu_alloc: bad argument (3-D arrays, 1..16 ranks, id required beyond one rank)", KISS_FFT_CUDA_EINVAL, 0);
+    if (!dims || (ndims != 3 && ndims != 2) || nranks < 1 || nranks > KF_MGPU_MAXRANKS || rank < 0 || rank >= nranks || (nranks > 1 && !id)) {
+        kf_fail(NULL, "kiss_fftnd_mgpu_alloc: bad argument (2-D or 3-D arrays, 1..16 ranks, id required beyond one rank)", KISS_FFT_CUDA_EINVAL, 0);
         return NULL;
     }
+    /* 2-D n0 x n1 = the 3-D geometry n0 x 1 x n1 (slabs of n0/G rows; output X[k0][k1] stored [k1 - r*n1/G][k0]); it has
+     * its own, simpler exec (kf_exec_2d): rows, transposing exchange, rows */
+    int dims3[3] = {dims[0], ndims == 2 ? 1 : dims[1], ndims == 2 ? dims[1] : dims[2]};
+    if (ndims == 2 && (flags & KISS_FFT_MGPU_REFERENCE_ORDER)) {
+        kf_fail(NULL, "kiss_fftnd_mgpu_alloc: the reference-order mode is 3-D only", KISS_FFT_CUDA_EINVAL, 0);
+        return NULL;
+    }
+    dims = dims3;
     if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || dims[0] % nranks || dims[2] % nranks) {
         kf_fail(NULL, "kiss_fftnd_mgpu_alloc: dims[0] and dims[2] must be divisible by the number of ranks", KISS_FFT_CUDA_EINVAL, 0);
         return NULL;
@@ -381,6 +390,7 @@ kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int invers
     st->d0 = dims[0]; st->d1 = dims[1]; st->d2 = dims[2];
     st->inverse = inverse_fft ? 1 : 0;
     st->rank = rank; st->nranks = nranks; st->flags = flags;
+    st->ndims = ndims;
     st->planes = st->d0 / nranks;
     st->cols = st->d2 / nranks;
     /* chunks of the k2 columns: as many as requested / up to 4, keeping whole 16-column tiles per chunk where possible */
@@ -390,6 +400,7 @@ kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int invers
     st->tail16 = 4;                    /* last chunk = a quarter of the columns (the others share the rest) */
     env = getenv("KISSFFT_MGPU_TAIL16");
     if (env && atoi(env) >= 0) st->tail16 = atoi(env);
+    if (ndims == 2) want = 1;
     kf_set_chunks(st, want);
     st->pchunks = 1;
     if (nranks > 1 && !(flags & KISS_FFT_MGPU_REFERENCE_ORDER))
@@ -415,14 +426,14 @@ kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int invers
     if (env && atoi(env) >= 0) st->ac_reserve = atoi(env);
     int ok = cudaGetDevice(&st->device) == cudaSuccess;
     st->cfg0 = kiss_fft_alloc(st->d0, st->inverse, NULL, NULL);
-    st->cfg1 = kiss_fft_alloc(st->d1, st->inverse, NULL, NULL);
+    st->cfg1 = ndims == 2 ? NULL : kiss_fft_alloc(st->d1, st->inverse, NULL, NULL);
     st->cfg2 = kiss_fft_alloc(st->d2, st->inverse, NULL, NULL);
-    ok = ok && st->cfg0 && st->cfg1 && st->cfg2;
+    ok = ok && st->cfg0 && (st->cfg1 || ndims == 2) && st->cfg2;
     st->recv_bytes = sizeof(kiss_fft_cpx) * (size_t)st->d0 * st->cols * st->d1;
     st->recv_bytes = (st->recv_bytes + 255u) & ~(size_t)255u;
     ok = ok && cudaMalloc((void **)&st->recv_base, st->recv_bytes + KF_FLAG_BYTES) == cudaSuccess &&
          cudaMemset(st->recv_base + st->recv_bytes, 0, KF_FLAG_BYTES) == cudaSuccess;
-    if (flags & KISS_FFT_MGPU_REFERENCE_ORDER)
+    if ((flags & KISS_FFT_MGPU_REFERENCE_ORDER) || (ndims == 2 && nranks > 1 && !(flags & KISS_FFT_MGPU_P2P)))
         ok = ok && cudaMalloc((void **)&st->work, st->recv_bytes) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&st->s_comm, cudaStreamNonBlocking) == cudaSuccess &&
          cudaStreamCreateWithFlags(&st->s_c, cudaStreamNonBlocking) == cudaSuccess &&
@@ -447,7 +458,8 @@ kiss_fftnd_mgpu_cfg kiss_fftnd_mgpu_alloc(const int *dims, int ndims, int invers
         }
         if (ok && (flags & KISS_FFT_MGPU_P2P)) st->p2p = kf_mgpu_map_peers(st) == 0;   /* falls back to NCCL when IPC is unavailable */
         if (ok && !st->p2p) ok = cudaMalloc((void **)&st->send, st->recv_bytes) == cudaSuccess;
-        if (ok && st->p2p && !(flags & KISS_FFT_MGPU_REFERENCE_ORDER)) {
+        if (ok && !st->p2p && ndims == 2 && !st->work) ok = cudaMalloc((void **)&st->work, st->recv_bytes) == cudaSuccess;   /* IPC fell back to NCCL */
+        if (ok && st->p2p && ndims == 3 && !(flags & KISS_FFT_MGPU_REFERENCE_ORDER)) {
             /* SMs of the link partition.  B must keep NVLink busy (0.62-0.65 TB/s measured for SM stores at every G): at
              * G = 2 it moves as many HBM bytes as link bytes and needs half the device (72 = one die), at G >= 4 it is
              * link-bound.  Measured on 1024^3 (profiles/r02/mgpu_*_green_context_sweep*): G = 2: 72, G = 4: 48, G = 8: 64. */
@@ -499,7 +511,7 @@ void kiss_fftnd_mgpu_free(kiss_fftnd_mgpu_cfg st)
     }
     if (st->tr_t0) cudaEventDestroy(st->tr_t0);
     kiss_fft_free(st->cfg0);
-    kiss_fft_free(st->cfg1);
+    if (st->cfg1) kiss_fft_free(st->cfg1);
     kiss_fft_free(st->cfg2);
     st->magic = 0;
     free(st);
@@ -559,6 +571,45 @@ static int kf_exec_reference_order(kiss_fftnd_mgpu_cfg st, kiss_fft_cpx *d_in, k
     return 0;
 }
 
+/* 2-D arrays: rows (axis 1) in place -> tiled transposing exchange (every destination row piece is P contiguous elements,
+ * stored straight into the owner's receive buffer [C][d0], or through a send buffer and NCCL) -> rows (axis 0) of what
+ * arrived.  kiss_fftnd.c:156-188 on two axes with the transposing write of its first sweep done by the exchange. */
+static int kf_exec_2d(kiss_fftnd_mgpu_cfg st, kiss_fft_cpx *d_in, kiss_fft_cpx *d_out, cudaStream_t main)
+{
+    const int G = st->nranks, P = st->planes, d0 = st->d0, d2 = st->d2, C = st->cols;
+    kiss_fft_cpx *recv = (kiss_fft_cpx *)st->recv_base;
+    void *dst[KF_MGPU_MAXRANKS];
+    CU(kiss_fft_batch_dev(st->cfg2, d_in, d_in, (size_t)P, (size_t)d2, (size_t)d2, 1, main));
+    if (G == 1) {
+        dst[0] = recv;
+        CU(kfcu_transpose_peers(d_in, d2, dst, 1, P, C, d0, 0, main));
+    } else if (st->p2p) {
+        const unsigned epoch = ++st->epoch;
+        /* every peer has finished reading its receive buffer (the rows pass of the previous call) before anyone stores into it */
+        CU(kfcu_peer_signal((void *const *)st->d_peer_flags, G, st->rank, 1, epoch, main));
+        CU(kfcu_peer_wait(flag_ptr(st, st->rank), G, 1, epoch, main));
+        for (int s = 0; s < G; ++s) dst[s] = st->peer_base[s];
+        CU(kfcu_transpose_peers(d_in, d2, dst, G, P, C, d0, (long long)st->rank * P, main));
+        CU(kfcu_peer_signal((void *const *)st->d_peer_flags, G, st->rank, 0, epoch, main));
+        CU(kfcu_peer_wait(flag_ptr(st, st->rank), G, 0, epoch, main));
+    } else {
+        const size_t blk = (size_t)C * P;            /* send [s][c][p]; received as work [r][c][p] */
+        for (int s = 0; s < G; ++s) dst[s] = st->send + (size_t)s * blk;
+        CU(kfcu_transpose_peers(d_in, d2, dst, G, P, C, P, 0, main));
+        NC(g_nccl.GroupStart());
+        for (int s = 0; s < G; ++s) {
+            NC(g_nccl.Send(st->send + (size_t)s * blk, blk * sizeof(kiss_fft_cpx), KF_NCCL_UINT8, s, st->comm, main));
+            NC(g_nccl.Recv(st->work + (size_t)s * blk, blk * sizeof(kiss_fft_cpx), KF_NCCL_UINT8, s, st->comm, main));
+        }
+        NC(g_nccl.GroupEnd());
+        for (int r = 0; r < G; ++r)                  /* [r][c][p] -> [c][r*P + p] */
+            CU(cudaMemcpy2DAsync(recv + (size_t)r * P, sizeof(kiss_fft_cpx) * (size_t)d0, st->work + (size_t)r * blk, sizeof(kiss_fft_cpx) * (size_t)P,
+                                 sizeof(kiss_fft_cpx) * (size_t)P, (size_t)C, cudaMemcpyDeviceToDevice, main));
+    }
+    CU(kiss_fft_batch_dev(st->cfg0, recv, d_out, (size_t)C, (size_t)d0, (size_t)d0, 1, main));
+    return 0;
+}
+
 /* ---- tuning aid: a timeline of the launches of one exec ------------------------------------------------------- */
 static void tr_begin(kiss_fftnd_mgpu_cfg st, const char *what, int i, int j, cudaStream_t s)
 {
@@ -593,6 +644,7 @@ int kiss_fftnd_mgpu_exec(kiss_fftnd_mgpu_cfg st, kiss_fft_cpx *d_in, kiss_fft_cp
 {
     if (!st || st->magic != KF_MAGIC_MGPU || !d_in || !d_out) return kf_fail(st, "kiss_fftnd_mgpu_exec: bad argument", KISS_FFT_CUDA_EINVAL, 0);
     if (st->flags & KISS_FFT_MGPU_REFERENCE_ORDER) return kf_exec_reference_order(st, d_in, d_out, (cudaStream_t)stream);
+    if (st->ndims == 2) return kf_exec_2d(st, d_in, d_out, (cudaStream_t)stream);
     const int G = st->nranks, P = st->planes, d0 = st->d0, d1 = st->d1, d2 = st->d2, C = st->cols;
     cudaStream_t main = (cudaStream_t)stream;
     kiss_fft_cpx *recv = (kiss_fft_cpx *)st->recv_base;

@@ -2,6 +2,7 @@
  * test_mgpu.c -- the multi-GPU kiss_fftnd through the C-ABI alone (no Python, no torch): one process per GPU.
  *
  *   test_mgpu G d0 d1 d2 [flags] [iters]          flags: 1 = peer-store exchange, 2 = reference axis order (exact mode)
+ *                                                 d1 = 1: the 2-D transform d0 x d2
  *
  * Builds for every datatype (-DFIXED_POINT=16|32, -Dkiss_fft_scalar=...): the fixed-point builds must reproduce the
  * single-GPU kiss_fftnd bit for bit in the reference-order mode.
@@ -42,9 +43,13 @@ static kiss_fft_scalar rnd(unsigned long long *s)
 static int run_rank(int rank, int G, const int *dims, unsigned flags, int iters, const void *id)
 {
     const size_t d0 = dims[0], d1 = dims[1], d2 = dims[2], n = d0 * d1 * d2, P = d0 / G, C = d2 / G;
+    /* d1 == 1 on the command line = the 2-D transform d0 x d2 (kiss_fftnd_mgpu_alloc with ndims = 2) */
+    const int dims2[2] = {dims[0], dims[2]};
+    const int nd_n = dims[1] == 1 ? 2 : 3;
+    const int *nd_dims = nd_n == 2 ? dims2 : dims;
     CK(cudaSetDevice(rank));
     if (getenv("MGPU_TEST_TIMING_ONLY")) {      /* tuning aid: no host arrays, no verification, just the fenced timing */
-        kiss_fftnd_mgpu_cfg c2 = kiss_fftnd_mgpu_alloc(dims, 3, 0, rank, G, id, flags);
+        kiss_fftnd_mgpu_cfg c2 = kiss_fftnd_mgpu_alloc(nd_dims, nd_n, 0, rank, G, id, flags);
         if (!c2) { fprintf(stderr, "rank %d: alloc failed: %s\n", rank, kiss_fftnd_mgpu_last_error()); return 11; }
         kiss_fft_cpx *a, *b;
         CK(cudaMalloc((void **)&a, sizeof(kiss_fft_cpx) * P * d1 * d2));
@@ -91,13 +96,13 @@ static int run_rank(int rank, int G, const int *dims, unsigned flags, int iters,
     CK(cudaMalloc((void **)&d_full, sizeof(kiss_fft_cpx) * n));
     CK(cudaMalloc((void **)&d_ref, sizeof(kiss_fft_cpx) * n));
     CK(cudaMemcpy(d_full, h, sizeof(kiss_fft_cpx) * n, cudaMemcpyHostToDevice));
-    kiss_fftnd_cfg nd = kiss_fftnd_alloc(dims, 3, 0, NULL, NULL);
+    kiss_fftnd_cfg nd = kiss_fftnd_alloc(nd_dims, nd_n, 0, NULL, NULL);
     CK(kiss_fftnd_dev(nd, d_full, d_ref, NULL, NULL));
     CK(cudaDeviceSynchronize());
     kiss_fft_cpx *ref = (kiss_fft_cpx *)malloc(sizeof(kiss_fft_cpx) * n);
     CK(cudaMemcpy(ref, d_ref, sizeof(kiss_fft_cpx) * n, cudaMemcpyDeviceToHost));
 
-    kiss_fftnd_mgpu_cfg cfg = kiss_fftnd_mgpu_alloc(dims, 3, 0, rank, G, id, flags);
+    kiss_fftnd_mgpu_cfg cfg = kiss_fftnd_mgpu_alloc(nd_dims, nd_n, 0, rank, G, id, flags);
     if (!cfg) { fprintf(stderr, "rank %d: kiss_fftnd_mgpu_alloc failed: %s\n", rank, kiss_fftnd_mgpu_last_error()); return 11; }
     const size_t nin = kiss_fftnd_mgpu_local_in_elems(cfg), nout = kiss_fftnd_mgpu_local_out_elems(cfg);
     if (nin != P * d1 * d2 || nout != C * d1 * d0) { fprintf(stderr, "rank %d: slab sizes\n", rank); return 12; }

@@ -88,3 +88,16 @@ def test_reference_order_multi_rank(G, dims, p2p, tname):
     assert all(o["rel_rms"] <= o["tol"] for o in out)
     if tname.startswith("int"):
         assert all(o["mismatches"] == 0 for o in out)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p2p", [False, True])
+@pytest.mark.parametrize("G,dims", [(1, (256, 1, 512)), (1, (96, 1, 1000)), (2, (256, 1, 512)), (2, (1024, 1, 2048)), (2, (96, 1, 1000)), (4, (512, 1, 256))])
+def test_2d_through_c_abi(G, dims, p2p):
+    """north_star "large 2-D/3-D kiss_fftnd": ndims = 2 (d1 == 1 selects it in the test program) -- rows, transposing exchange,
+    rows; compared with the single-GPU kiss_fftnd_dev of the whole array"""
+    import torch
+    if torch.cuda.device_count() < G:
+        pytest.skip("needs %d GPUs" % G)
+    out = run(G, dims, p2p)
+    assert all(o["rel_rms"] <= o["tol"] for o in out)
