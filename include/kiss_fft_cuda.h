@@ -149,6 +149,8 @@ int KISS_FFT_API kiss_fftnd_mgpu_knob(kiss_fftnd_mgpu_cfg cfg, int which);
  * "name start_ms end_ms" line per launch (A<group> rows, B<group>.<chunk> column pass + exchange stores, X NCCL exchange,
  * C0.<chunk> axis-0 pass) into buf.  Synchronises the device. */
 int KISS_FFT_API kiss_fftnd_mgpu_trace(kiss_fftnd_mgpu_cfg cfg, char *buf, size_t len);
+/* testing aid (host logic, no CUDA call): boundaries of the k2-column chunks for `cols` columns per rank */
+int KISS_FFT_API kiss_fftnd_mgpu_debug_chunks(int cols, int nranks, int want, int tail16, int *coff, int cap);
 
 /* ---- host-pointer batched (parallel lanes of H2D / kernel / D2H, pinned bounce buffers for pageable memory) --- */
 int KISS_FFT_API kiss_fft_batch(kiss_fft_cfg cfg, const kiss_fft_cpx *in, kiss_fft_cpx *out, size_t howmany);

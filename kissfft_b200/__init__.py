@@ -26,7 +26,7 @@ API_SYMBOLS = (
     "kiss_fft_planes_pass_peers2_dev",
     "kiss_fftnd_mgpu_get_id", "kiss_fftnd_mgpu_alloc", "kiss_fftnd_mgpu_exec", "kiss_fftnd_mgpu_free", "kiss_fftnd_mgpu_local_in_elems",
     "kiss_fftnd_mgpu_local_out_elems", "kiss_fftnd_mgpu_uses_p2p", "kiss_fftnd_mgpu_chunks", "kiss_fftnd_mgpu_a2a_bytes",
-    "kiss_fftnd_mgpu_last_error", "kiss_fftnd_mgpu_tune", "kiss_fftnd_mgpu_knob", "kiss_fftnd_mgpu_trace",
+    "kiss_fftnd_mgpu_last_error", "kiss_fftnd_mgpu_tune", "kiss_fftnd_mgpu_knob", "kiss_fftnd_mgpu_trace", "kiss_fftnd_mgpu_debug_chunks",
     "kiss_fftndr_dev", "kiss_fftndri_dev", "kiss_fft_batch", "kiss_fftr_batch", "kiss_fftri_batch",
     "kiss_fft_cuda_last_error", "kiss_fft_cuda_launch_count", "kiss_fft_cuda_plan_kind", "kiss_fft_cuda_scalar_bytes",
     "kiss_fft_cuda_is_fixed_point", "kiss_fft_cuda_force_generic", "kiss_fft_cuda_set_grid_limit", "kiss_fft_cuda_debug_chunks",

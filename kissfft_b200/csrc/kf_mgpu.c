@@ -339,6 +339,18 @@ static void kf_set_chunks(kiss_fftnd_mgpu_cfg st, int want)
     }
 }
 
+/* testing aid (host logic only, no CUDA call): the column chunks a cfg with these parameters would use; returns their number
+ * and writes the nchunks + 1 boundaries */
+int kiss_fftnd_mgpu_debug_chunks(int cols, int nranks, int want, int tail16, int *coff, int cap)
+{
+    struct kiss_fftnd_mgpu_state tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    tmp.cols = cols; tmp.nranks = nranks; tmp.tail16 = tail16;
+    kf_set_chunks(&tmp, want);
+    for (int j = 0; j <= tmp.nchunks && j < cap; ++j) coff[j] = tmp.coff[j];
+    return tmp.nchunks;
+}
+
 /* Tuning aid (tests/cpp/test_mgpu.c sweeps with it): change the pipeline shape of an existing cfg.  COLLECTIVE -- every
  * rank passes the same values, with no exec in flight.  knobs[0] chunks of the k2 columns, [1] plane groups, [2] CTA cap
  * of the link-bound launches (0 = none), [3] priority of their stream (0/1); a negative entry keeps the current value. */

@@ -142,3 +142,25 @@ def test_host_pipeline_chunks_cover_the_batch(howmany, rows, ramp):
     assert pos == howmany
     if ramp and howmany >= 6 * rows and rows >= 512:
         assert n[0] < rows / 4 and n[k - 1] < rows / 4, "the first and the last chunk are the exposed ones"
+
+
+@pytest.mark.parametrize("cols,nranks,want,tail16", [(512, 2, 2, 4), (128, 8, 2, 4), (256, 4, 2, 4), (128, 8, 4, 4), (64, 2, 2, 4), (32, 2, 2, 4),
+                                                     (16, 2, 2, 4), (125, 8, 2, 4), (512, 2, 2, 0), (512, 1, 4, 4), (384, 2, 8, 2)])
+def test_mgpu_column_chunks(cols, nranks, want, tail16):
+    """chunks of the k2 columns of kiss_fftnd_mgpu_exec: cover [0, cols) in order, whole 16-column tiles when there is more than
+    one chunk, and a narrower last chunk (the one whose axis-0 pass nothing overlaps) when asked for"""
+    import ctypes
+    import kissfft_b200
+    L = kissfft_b200.get("float").lib
+    coff = (ctypes.c_int * 16)()
+    n = L.kiss_fftnd_mgpu_debug_chunks(cols, nranks, want, tail16, coff, 16)
+    assert 1 <= n <= max(1, want)
+    assert coff[0] == 0 and coff[n] == cols
+    w = [coff[j + 1] - coff[j] for j in range(n)]
+    assert all(x > 0 for x in w)
+    if nranks == 1:
+        assert n == 1
+    if n > 1:
+        assert all(x % 16 == 0 for x in w)
+        if tail16:
+            assert w[-1] <= min(w[:-1])
