@@ -408,6 +408,10 @@ def measure_config(name, args, barrier):
                 "algorithmic_bytes": abytes, "achieved_GBps": abytes / (ms * 1e-3) / 1e9})
     out["frac"] = out["achieved_GBps"] / peak
     out["frac_of_nominal_8000"] = out["achieved_GBps"] / 8000.0
+    if w["tname"] in ("int16_t", "int32_t"):
+        # fixed point is integer-pipe bound -- report the HBM fraction AND the integer-op rate
+        out["int_gop_per_s_5NlogN"] = out["gflops"]
+        out["bound"] = "integer issue slots, not HBM (ncu: profiles/r02/ncu_all_kernels.txt; exact C_FIXDIV/sround arithmetic fixes the instruction count)"
     del d_x, d_X
     torch.cuda.empty_cache()
     return out
