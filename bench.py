@@ -408,6 +408,8 @@ def measure_config(name, args, barrier):
                 "algorithmic_bytes": abytes, "achieved_GBps": abytes / (ms * 1e-3) / 1e9})
     out["frac"] = out["achieved_GBps"] / peak
     out["frac_of_nominal_8000"] = out["achieved_GBps"] / 8000.0
+    if known_traffic(name):
+        out["traffic"] = known_traffic(name)      # static: dram bytes per launch of the committed ncu capture (profiles/traffic.json)
     if w["tname"] in ("int16_t", "int32_t"):
         # fixed point is integer-pipe bound -- report the HBM fraction AND the integer-op rate
         out["int_gop_per_s_5NlogN"] = out["gflops"]
